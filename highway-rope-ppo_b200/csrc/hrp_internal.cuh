@@ -1,0 +1,82 @@
+// hrp_internal.cuh -- device-side parameter block and helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hrp.h"
+
+#define HRP_VS 64            // vehicle slots per env in every SoA array (two per lane)
+#define HRP_WARPS_PER_CTA 4  // envs per CTA (one warp each)
+#define HRP_FULL 0xffffffffu
+
+typedef unsigned long long ull;
+
+// Everything a kernel needs, passed by value (lives in the constant bank).
+struct EnvDev {
+    int E, V, lanes, frames;
+    int ego_mode, autoreset, normalize_reward, offroad_terminal;
+    float dt;
+    double dt64;     // 1/simulation_frequency (IDM timer is advanced in fp64)
+    double dtime;    // 1/policy_frequency
+    double duration;
+    float collision_reward, right_lane_reward, high_speed_reward, rs_lo, rs_hi;
+    // Kinematics observation
+    int N, F, Fout;
+    int feat[HRP_MAX_FEATURES];
+    int has_range[HRP_MAX_FEATURES];
+    double lo[HRP_MAX_FEATURES], hi[HRP_MAX_FEATURES];
+    int normalize, clip, absolute, sorted, see_behind;
+    // embedding
+    int embed_kind, embed_dim, use_euclid, ego_idx;
+    float max_dist;
+    const float *table;
+    // spawn
+    double ego_spacing, inv_density, gap_factor;
+    int initial_lane;
+    ull env_id_base, seed;
+    // SoA simulator state in HBM: [E][HRP_VS] per vehicle field, [E] per env field
+    double *x, *timer, *time;
+    float *y, *heading, *speed, *tspeed, *delta, *impx, *impy;
+    uint32_t *flags;  // lane | target_lane<<8 | crashed<<16 | has_impact<<17
+    uint32_t *episode, *obs_draw;
+};
+
+// Philox4x32-10 (Salmon et al. SC'11), the counter-based generator behind spawn and shuffle.
+__host__ __device__ __forceinline__ void hrp_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                    uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// library-internal error plumbing (hrp_api.cu)
+void hrp_set_error(const char *fmt, ...);
+#define HRP_CUDA_OK(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            hrp_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                          __LINE__);                                                        \
+            return -2;                                                                      \
+        }                                                                                   \
+    } while (0)
+
+// launchers implemented in hrp_env.cu
+int hrp_launch_step(const EnvDev &P, const float *actions, float *obs, float *reward, uint8_t *term,
+                    uint8_t *trunc, const int32_t *perm, int32_t *row_vehicle, cudaStream_t s);
+int hrp_launch_observe(const EnvDev &P, float *obs, const int32_t *perm, int32_t *row_vehicle,
+                       cudaStream_t s);
+int hrp_launch_reset(const EnvDev &P, const uint8_t *mask, float *obs, cudaStream_t s);
+int hrp_launch_embed(int kind, int embed_dim, int use_euclid, int ego_idx, float max_dist,
+                     const float *table, const float *obs, float *out, long long batch, int rows,
+                     int cols, const float *dist_override, cudaStream_t s);

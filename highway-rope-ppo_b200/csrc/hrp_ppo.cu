@@ -1,0 +1,661 @@
+// hrp_ppo.cu -- the PPO half of the hot path (reference: ppo/agent.py).
+//
+//   ActorCritic.forward / get_action / evaluate      agent.py:46-84
+//   PPOMemory.compute_advantages (GAE)               agent.py:126-138
+//   advantage normalisation                          agent.py:204
+//   clipped surrogate + value MSE + entropy, backward agent.py:218-248
+//   clip_grad_norm_ + Adam.step                      agent.py:249-252
+//
+// Parameters live in one flat fp32 buffer in ActorCritic.parameters() order (the root
+// module's own Parameter first): log_std[A], shared.0.{weight[H,S],bias[H]},
+// shared.2.{weight[H,H],bias[H]}, actor_mean.0.{weight[H,H],bias[H]},
+// actor_mean.2.{weight[A,H],bias[A]}, critic.0.{weight[H,H],bias[H]}, critic.2.{weight[1,H],bias[1]}.
+// Gradients, Adam moments use the same layout, so the optimizer (and the multi-GPU
+// all-reduce) touch one contiguous range.
+#include <math.h>
+
+#include "hrp_internal.cuh"
+
+namespace {
+
+struct Layout {
+    int S, A, H;
+    long long log_std, w1, b1, w2, b2, wa1, ba1, wa2, ba2, wc1, bc1, wc2, bc2, total;
+};
+__host__ __device__ inline Layout make_layout(int S, int A, int H)
+{
+    Layout L;
+    L.S = S; L.A = A; L.H = H;
+    long long o = 0;
+    L.log_std = o; o += A;
+    L.w1 = o; o += (long long)H * S; L.b1 = o; o += H;
+    L.w2 = o; o += (long long)H * H; L.b2 = o; o += H;
+    L.wa1 = o; o += (long long)H * H; L.ba1 = o; o += H;
+    L.wa2 = o; o += (long long)A * H; L.ba2 = o; o += A;
+    L.wc1 = o; o += (long long)H * H; L.bc1 = o; o += H;
+    L.wc2 = o; o += H; L.bc2 = o; o += 1;
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic fp32 GEMM  C[M,N] (+)= op(A)[M,K] * op(B)[K,N]  with fused epilogues.
+//   AT == false: A stored [M,K] (K contiguous);  AT == true: A stored [K,M].
+//   BT == false: B stored [K,N] (N contiguous);  BT == true: B stored [N,K].
+// Epilogue, in this order: + C (accumulate), + bias[n], ReLU, * (mask[m,n] > 0).  gridDim.z > 1 splits K and
+// writes partial tiles to C + z*M*N (reduced by reduce_partials_kernel, deterministic).
+constexpr int GM = 64, GN = 64, GK = 16;
+
+template <bool AT, bool BT>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, const float *__restrict__ A, int lda, const float *__restrict__ B, int ldb,
+             float *__restrict__ C, int ldc, const float *__restrict__ bias, int relu,
+             const float *__restrict__ mask, int ldm, int accumulate, int k_chunk)
+{
+    __shared__ float As[GK][GM + 4];
+    __shared__ float Bs[GK][GN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+    const int kbeg = blockIdx.z * k_chunk, kend = min(K, kbeg + k_chunk);
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = kbeg; k0 < kend; k0 += GK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int m, k;
+            if (AT) { k = (tid >> 6) + 4 * i; m = tid & 63; }
+            else { m = (tid >> 4) + 16 * i; k = tid & 15; }
+            int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < M && gk < kend) v = AT ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            As[k][m] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int n, k;
+            if (BT) { n = (tid >> 4) + 16 * i; k = tid & 15; }
+            else { k = (tid >> 6) + 4 * i; n = tid & 63; }
+            int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < N && gk < kend) v = BT ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *Cz = C + (size_t)blockIdx.z * M * ldc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            size_t o = (size_t)gm * ldc + gn;
+            float v = acc[i][j];
+            if (accumulate) v += Cz[o];
+            if (bias) v += bias[gn];
+            if (relu) v = fmaxf(v, 0.f);
+            if (mask) v = mask[(size_t)gm * ldm + gn] > 0.f ? v : 0.f;
+            Cz[o] = v;
+        }
+    }
+}
+
+__global__ void reduce_partials_kernel(const float *__restrict__ part, float *__restrict__ out, long long n,
+                                       int splits)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(size_t)z * n + i];
+    out[i] = s;
+}
+
+// column sums of G[B, N] -> out[N] (bias gradients); one warp per 32 columns, deterministic
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float *__restrict__ G, int ldg, long long B, int N, float *__restrict__ out)
+{
+    __shared__ float red[8][33];
+    int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    int w = threadIdx.x >> 5;
+    float s = 0.f;
+    if (col < N)
+        for (long long b = w; b < B; b += 8) s += G[(size_t)b * ldg + col];
+    red[w][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (w == 0 && col < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+        out[col] = t;
+    }
+}
+
+// gather minibatch rows: dst[b, :] = src[idx[b], :]
+__global__ void gather_rows_kernel(const float *__restrict__ src, const long long *__restrict__ idx,
+                                   float *__restrict__ dst, long long B, int cols)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = B * cols;
+    if (i >= total) return;
+    long long b = i / cols;
+    int c = (int)(i - b * cols);
+    dst[i] = src[(size_t)idx[b] * cols + c];
+}
+
+// ---------------------------------------------------------------------------------------
+// heads: mean[B,A] = a1 Wa2^T + ba2, value[B] = c1 Wc2^T + bc2  (N is 2 and 1: one warp per row)
+__global__ void __launch_bounds__(256)
+heads_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const float *__restrict__ wa2,
+             const float *__restrict__ ba2, const float *__restrict__ wc2, const float *__restrict__ bc2,
+             long long B, int H, int A, float *__restrict__ mean, float *__restrict__ value)
+{
+    long long b = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const float *ra = a1 + (size_t)b * H, *rc = c1 + (size_t)b * H;
+    for (int a = 0; a <= A; ++a) {
+        const float *w = a < A ? wa2 + (size_t)a * H : wc2;
+        const float *x = a < A ? ra : rc;
+        float s = 0.f;
+        for (int k = lane; k < H; k += 32) s = fmaf(x[k], w[k], s);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(HRP_FULL, s, d);
+        if (lane == 0) {
+            if (a < A) mean[b * A + a] = s + ba2[a];
+            else value[b] = s + bc2[0];
+        }
+    }
+}
+
+// ActorCritic.get_action (agent.py:56-74) after the forward pass
+__global__ void act_kernel(const float *__restrict__ mean, const float *__restrict__ log_std,
+                           const float *__restrict__ noise, long long B, int A, float *__restrict__ action,
+                           float *__restrict__ pre_tanh, float *__restrict__ log_prob)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float lp = 0.f;
+    for (int a = 0; a < A; ++a) {
+        float mu = mean[b * A + a];
+        float ls = log_std[a];
+        float sd = expf(ls);
+        float z = noise ? mu + sd * noise[b * A + a] : mu;
+        float t = tanhf(z);
+        pre_tanh[b * A + a] = z;
+        action[b * A + a] = t;
+        // Normal.log_prob(z) - log1p(-tanh(z)^2 + 1e-6)
+        float d = z - mu;
+        lp += -(d * d) / (2.f * sd * sd) - ls - 0.91893853320467274f;
+        lp -= log1pf(-(t * t) + 1e-6f);
+    }
+    if (log_prob) log_prob[b] = noise ? lp : 0.f;
+}
+
+// PPO loss for one minibatch (agent.py:223-245) and its gradient w.r.t. mean, value, log_std.
+// Single CTA: deterministic reductions.  metrics += (loss, policy, value, entropy, clipfrac, kl, 1, 0)
+__global__ void __launch_bounds__(1024)
+ppo_loss_kernel(const float *__restrict__ mean, const float *__restrict__ value,
+                const float *__restrict__ log_std, const float *__restrict__ pre_tanh,
+                const float *__restrict__ old_lp, const float *__restrict__ adv, const float *__restrict__ ret,
+                long long B, int A, float eps_clip, float value_coef, float entropy_coef, float scale,
+                float *__restrict__ dmean, float *__restrict__ dvalue, float *__restrict__ dlog_std,
+                float *__restrict__ metrics)
+{
+    __shared__ float red[32][8];
+    float s_pol = 0.f, s_val = 0.f, s_clip = 0.f, s_kl = 0.f, s_dls[4] = {0.f, 0.f, 0.f, 0.f};
+    float ent = 0.f;
+    for (int a = 0; a < A; ++a) ent += 0.5f + 0.91893853320467274f + log_std[a];
+    for (long long b = threadIdx.x; b < B; b += blockDim.x) {
+        float lp = 0.f;
+        float dmu[4], dls[4];
+        for (int a = 0; a < A; ++a) {
+            float mu = mean[b * A + a], ls = log_std[a], sd = expf(ls);
+            float z = pre_tanh[b * A + a];
+            float t = tanhf(z);
+            float d = z - mu, var = sd * sd;
+            lp += -(d * d) / (2.f * var) - ls - 0.91893853320467274f;
+            lp -= log1pf(-(t * t) + 1e-6f);
+            dmu[a] = d / var;
+            dls[a] = d * d / var - 1.f;
+        }
+        float lr = lp - old_lp[b];
+        float ratio = expf(lr);
+        float ad = adv[b];
+        float surr1 = ratio * ad;
+        float rc = fminf(fmaxf(ratio, 1.f - eps_clip), 1.f + eps_clip);
+        float surr2 = rc * ad;
+        bool inr = ratio >= 1.f - eps_clip && ratio <= 1.f + eps_clip;
+        // d min(surr1, surr2) / d ratio with torch's tie rule (half each on equality)
+        float g;
+        if (surr1 < surr2) g = ad;
+        else if (surr1 == surr2) g = 0.5f * ad + (inr ? 0.5f * ad : 0.f);
+        else g = inr ? ad : 0.f;
+        float dlp = -g * ratio * scale;
+        for (int a = 0; a < A; ++a) {
+            dmean[b * A + a] = dlp * dmu[a];
+            s_dls[a] += dlp * dls[a];
+        }
+        float v = value[b], dv = v - ret[b];
+        dvalue[b] = value_coef * 2.f * dv * scale;
+        s_pol += -fminf(surr1, surr2);
+        s_val += dv * dv;
+        s_clip += fabsf(ratio - 1.f) > eps_clip ? 1.f : 0.f;
+        s_kl += (ratio - 1.f) - lr;
+    }
+    float vals[8] = {s_pol, s_val, s_clip, s_kl, s_dls[0], s_dls[1], s_dls[2], s_dls[3]};
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float x = vals[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(HRP_FULL, x, d);
+        if (lane == 0) red[w][i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float x = 0.f;
+        int nw = blockDim.x >> 5;
+        for (int i = 0; i < nw; ++i) x += red[i][threadIdx.x];
+        red[0][threadIdx.x] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float pol = red[0][0] * scale, val = red[0][1] * scale;
+        float frac = (float)B * scale;  // share of the global minibatch held by this shard
+        float loss = pol + value_coef * val - entropy_coef * ent * frac;
+        for (int a = 0; a < A; ++a) dlog_std[a] = red[0][4 + a] - entropy_coef * frac;
+        if (metrics) {
+            metrics[0] += loss; metrics[1] += pol; metrics[2] += val; metrics[3] += ent * frac;
+            metrics[4] += red[0][2] * scale; metrics[5] += red[0][3] * scale; metrics[6] += frac;
+        }
+    }
+}
+
+// d(a1) = dmean Wa2 (.) (a1>0) and d(c1) = dvalue Wc2 (.) (c1>0): rank-A / rank-1 outer products
+__global__ void heads_backward_kernel(const float *__restrict__ dmean, const float *__restrict__ dvalue,
+                                      const float *__restrict__ wa2, const float *__restrict__ wc2,
+                                      const float *__restrict__ a1, const float *__restrict__ c1, long long B,
+                                      int H, int A, float *__restrict__ da1, float *__restrict__ dc1)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H) return;
+    long long b = i / H;
+    int k = (int)(i - b * H);
+    float s = 0.f;
+    for (int a = 0; a < A; ++a) s = fmaf(dmean[b * A + a], wa2[(size_t)a * H + k], s);
+    da1[i] = a1[i] > 0.f ? s : 0.f;
+    dc1[i] = c1[i] > 0.f ? dvalue[b] * wc2[k] : 0.f;
+}
+
+// PPOMemory.compute_advantages (agent.py:126-138): fp64 arithmetic, float32 store of every A_t
+__global__ void gae_kernel(const float *__restrict__ reward, const float *__restrict__ value,
+                           const uint8_t *__restrict__ done, const float *__restrict__ last_value, long long T,
+                           long long E, double gamma, double lam, float *__restrict__ adv,
+                           float *__restrict__ ret)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    double next_v = last_value ? (double)last_value[e] : 0.0;
+    float last_adv = 0.f;
+    for (long long t = T - 1; t >= 0; --t) {
+        size_t o = (size_t)t * E + e;
+        double nd = 1.0 - (double)(done[o] != 0);
+        double v = (double)value[o];
+        double delta = (double)reward[o] + gamma * next_v * nd - v;
+        float a = (float)(delta + gamma * lam * nd * (double)last_adv);
+        adv[o] = a;
+        ret[o] = a + value[o];
+        last_adv = a;
+        next_v = v;
+    }
+}
+
+// sum, sum of squares, count of the local advantages (fp64), deterministic two-stage
+__global__ void __launch_bounds__(256)
+adv_stats_kernel(const float *__restrict__ adv, long long n, double *__restrict__ part)
+{
+    __shared__ double red[2][8];
+    double s = 0.0, q = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double a = adv[i];
+        s += a; q += a * a;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { s += __shfl_xor_sync(HRP_FULL, s, d); q += __shfl_xor_sync(HRP_FULL, q, d); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tq = 0.0;
+        for (int i = 0; i < 8; ++i) { ts += red[0][i]; tq += red[1][i]; }
+        part[2 * blockIdx.x] = ts; part[2 * blockIdx.x + 1] = tq;
+    }
+}
+__global__ void adv_stats_final_kernel(const double *__restrict__ part, int nblocks, long long n,
+                                       double *__restrict__ stats)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0, q = 0.0;
+        for (int i = 0; i < nblocks; ++i) { s += part[2 * i]; q += part[2 * i + 1]; }
+        stats[0] = s; stats[1] = q; stats[2] = (double)n;
+    }
+}
+__global__ void adv_normalize_kernel(float *__restrict__ adv, long long n, const double *__restrict__ stats)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double cnt = stats[2], mean = stats[0] / cnt;
+    double var = (stats[1] - cnt * mean * mean) / (cnt - 1.0);  // torch.std: unbiased
+    float m = (float)mean, sd = (float)sqrt(fmax(var, 0.0));
+    adv[i] = (adv[i] - m) / (sd + 1e-8f);
+}
+
+// clip_grad_norm_ + Adam (agent.py:249-252), two launches: partial sums of squares, then update
+__global__ void __launch_bounds__(256)
+gradnorm_kernel(const float *__restrict__ g, long long n, float *__restrict__ part)
+{
+    __shared__ float red[8];
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s = fmaf(g[i], g[i], s);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(HRP_FULL, s, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        part[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                 float *__restrict__ v, const int32_t *__restrict__ step, long long n, double lr, double beta1,
+                 double beta2, double eps, float max_norm, const float *__restrict__ part, int nparts)
+{
+    // torch.optim.Adam forms its scalars in Python doubles and hands float32 values to the kernels
+    __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < nparts; ++i) t += part[i];
+        float total_norm = sqrtf(t);
+        float c = max_norm / (total_norm + 1e-6f);
+        s_coef = max_norm > 0.f ? fminf(c, 1.f) : 1.f;
+        int k = step[0] + 1;
+        double bc1 = 1.0 - pow(beta1, (double)k), bc2 = 1.0 - pow(beta2, (double)k);
+        s_step_size = (float)(lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), ep = (float)eps;
+    float gi = g[i] * s_coef;
+    float mi = m[i] + w1 * (gi - m[i]);  // exp_avg.lerp_(grad, 1 - beta1)
+    float vi = v[i] * b2 + w2 * gi * gi;  // mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / s_bc2_sqrt + ep;
+    p[i] = p[i] - s_step_size * (mi / denom);
+}
+__global__ void bump_step_kernel(int32_t *step) { step[0] += 1; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+struct hrp_ppo {
+    Layout L;
+    long long max_batch;
+    int device;
+    float *ws;  // one arena
+    float *x, *z, *olp, *adv, *ret;          // gathered minibatch
+    float *h1, *h2, *a1, *c1;                // activations [B,H]
+    float *mean, *value, *dmean, *dvalue;    // heads and their gradients
+    float *d1, *d2;                          // activation gradients [B,H]
+    float *part;                             // split-K partials
+    int splits_cap;
+};
+
+static int gemm(bool AT, bool BT, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C,
+                int ldc, const float *bias, int relu, const float *mask, int ldm, int accumulate, int splits,
+                cudaStream_t s)
+{
+    int k_chunk = K;
+    if (splits > 1) {
+        k_chunk = ((K + splits - 1) / splits + GK - 1) / GK * GK;
+        splits = (K + k_chunk - 1) / k_chunk;
+    }
+    dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM, splits), blk(256);
+    if (!AT && BT) sgemm_kernel<false, true><<<grid, blk, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    else if (!AT && !BT) sgemm_kernel<false, false><<<grid, blk, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    else if (AT && !BT) sgemm_kernel<true, false><<<grid, blk, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    else sgemm_kernel<true, true><<<grid, blk, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    HRP_CUDA_OK(cudaGetLastError());
+    return splits;
+}
+
+// weight gradient dW[N,K] = dY[B,N]^T X[B,K], split over B, deterministic
+static int wgrad(hrp_ppo *h, int N, int K, long long B, const float *dY, const float *X, float *dW, cudaStream_t s)
+{
+    int splits = (int)((B + 511) / 512);
+    if (splits > h->splits_cap) splits = h->splits_cap;
+    if (splits <= 1) {
+        int rc = gemm(true, false, N, K, (int)B, dY, N, X, K, dW, K, nullptr, 0, nullptr, 0, 0, 1, s);
+        return rc < 0 ? rc : 0;
+    }
+    int used = gemm(true, false, N, K, (int)B, dY, N, X, K, h->part, K, nullptr, 0, nullptr, 0, 0, splits, s);
+    if (used < 0) return used;
+    long long n = (long long)N * K;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->part, dW, n, used);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int forward_impl(hrp_ppo *h, const float *params, const float *x, long long B, float *mean, float *value,
+                        cudaStream_t s)
+{
+    const Layout &L = h->L;
+    int H = L.H, S = L.S, A = L.A, Bi = (int)B;
+    if (gemm(false, true, Bi, H, S, x, S, params + L.w1, S, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+    if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+    if (gemm(false, true, Bi, H, H, h->h2, H, params + L.wa1, H, h->a1, H, params + L.ba1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+    if (gemm(false, true, Bi, H, H, h->h2, H, params + L.wc1, H, h->c1, H, params + L.bc1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+    heads_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(h->a1, h->c1, params + L.wa2, params + L.ba2, params + L.wc2,
+                                                        params + L.bc2, B, H, A, mean, value);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int64_t hrp_ppo_param_count(int32_t state_dim, int32_t action_dim, int32_t hidden_dim)
+{
+    return make_layout(state_dim, action_dim, hidden_dim).total;
+}
+
+int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, int64_t max_batch, int32_t device,
+                   hrp_ppo **out)
+{
+    if (!out || state_dim < 1 || hidden_dim < 1 || action_dim < 1 || action_dim > 4 || max_batch < 1) {
+        hrp_set_error("hrp_ppo_create: bad arguments (action_dim must be 1..4)");
+        return -1;
+    }
+    int ndev = hrp_device_count();
+    if (ndev <= 0) { hrp_set_error("no CUDA device: this library has no CPU path"); return -3; }
+    if (device < 0 || device >= ndev) { hrp_set_error("device %d not in [0, %d)", device, ndev); return -1; }
+    HRP_CUDA_OK(cudaSetDevice(device));
+    hrp_ppo *h = new hrp_ppo();
+    h->L = make_layout(state_dim, action_dim, hidden_dim);
+    h->max_batch = max_batch; h->device = device;
+    h->splits_cap = 32;
+    size_t B = (size_t)max_batch, H = hidden_dim, S = state_dim, A = action_dim;
+    size_t big = H * (H > S ? H : S);
+    size_t n = B * S + B * A + 3 * B + 4 * B * H + 2 * B * A + 2 * B + 2 * B * H + (size_t)h->splits_cap * big;
+    cudaError_t ce = cudaMalloc(&h->ws, n * sizeof(float));
+    if (ce != cudaSuccess) { hrp_set_error("cudaMalloc(%zu): %s", n * sizeof(float), cudaGetErrorString(ce)); delete h; return -2; }
+    float *p = h->ws;
+    h->x = p; p += B * S; h->z = p; p += B * A; h->olp = p; p += B; h->adv = p; p += B; h->ret = p; p += B;
+    h->h1 = p; p += B * H; h->h2 = p; p += B * H; h->a1 = p; p += B * H; h->c1 = p; p += B * H;
+    h->mean = p; p += B * A; h->dmean = p; p += B * A; h->value = p; p += B; h->dvalue = p; p += B;
+    h->d1 = p; p += B * H; h->d2 = p; p += B * H;
+    h->part = p;
+    *out = h;
+    return 0;
+}
+
+int hrp_ppo_destroy(hrp_ppo *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->ws);
+    delete h;
+    return 0;
+}
+
+int hrp_ppo_forward(hrp_ppo *h, const float *params, const float *states, int64_t batch, float *mean, float *value,
+                    void *stream)
+{
+    if (!h || !params || !states || !mean || !value) { hrp_set_error("hrp_ppo_forward: null argument"); return -1; }
+    if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
+    return forward_impl(h, params, states, batch, mean, value, (cudaStream_t)stream);
+}
+
+int hrp_ppo_act(hrp_ppo *h, const float *params, const float *states, const float *noise, int64_t batch,
+                float *action, float *pre_tanh, float *log_prob, float *value, void *stream)
+{
+    if (!h || !params || !states || !action || !pre_tanh || !value) { hrp_set_error("hrp_ppo_act: null argument"); return -1; }
+    if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = forward_impl(h, params, states, batch, h->mean, value, s)) return rc;
+    act_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(h->mean, params + h->L.log_std, noise, batch, h->L.A,
+                                                              action, pre_tanh, log_prob);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int hrp_gae(const float *reward, const float *value, const uint8_t *done, const float *last_value, int64_t T,
+            int64_t E, float gamma, float lam, float *adv, float *ret, void *stream)
+{
+    if (!reward || !value || !done || !adv || !ret || T < 1 || E < 1) { hrp_set_error("hrp_gae: bad arguments"); return -1; }
+    gae_kernel<<<(unsigned)((E + 127) / 128), 128, 0, (cudaStream_t)stream>>>(reward, value, done, last_value, T, E,
+                                                                            (double)gamma, (double)lam, adv, ret);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int hrp_adv_stats(const float *adv, int64_t n, double *stats, void *stream)
+{
+    if (!adv || !stats || n < 1) { hrp_set_error("hrp_adv_stats: bad arguments"); return -1; }
+    // stats_dev must hold 3 + 2*256 doubles: (sum, sumsq, n) followed by the block partials
+    const int nb = 256;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > nb) blocks = nb;
+    adv_stats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(adv, n, stats + 3);
+    adv_stats_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats + 3, blocks, n, stats);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int hrp_adv_normalize(float *adv, int64_t n, const double *stats, void *stream)
+{
+    if (!adv || !stats || n < 1) { hrp_set_error("hrp_adv_normalize: bad arguments"); return -1; }
+    adv_normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(adv, n, stats);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, const float *pre_tanh,
+                      const float *old_log_prob, const float *adv, const float *ret, const int64_t *idx, int64_t batch,
+                      float eps_clip, float value_coef, float entropy_coef, float loss_scale, float *grad,
+                      float *metrics, void *stream)
+{
+    if (!h || !params || !states || !pre_tanh || !old_log_prob || !adv || !ret || !grad) {
+        hrp_set_error("hrp_ppo_loss_grad: null argument");
+        return -1;
+    }
+    if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const Layout &L = h->L;
+    const int H = L.H, S = L.S, A = L.A, Bi = (int)batch;
+    const long long B = batch;
+    const float *x = states, *z = pre_tanh, *olp = old_log_prob, *ad = adv, *rt = ret;
+    if (idx) {
+        const long long *ix = (const long long *)idx;
+        gather_rows_kernel<<<(unsigned)((B * S + 255) / 256), 256, 0, s>>>(states, ix, h->x, B, S);
+        gather_rows_kernel<<<(unsigned)((B * A + 255) / 256), 256, 0, s>>>(pre_tanh, ix, h->z, B, A);
+        gather_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(old_log_prob, ix, h->olp, B, 1);
+        gather_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(adv, ix, h->adv, B, 1);
+        gather_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(ret, ix, h->ret, B, 1);
+        HRP_CUDA_OK(cudaGetLastError());
+        x = h->x; z = h->z; olp = h->olp; ad = h->adv; rt = h->ret;
+    }
+    if (int rc = forward_impl(h, params, x, B, h->mean, h->value, s)) return rc;
+    ppo_loss_kernel<<<1, 1024, 0, s>>>(h->mean, h->value, params + L.log_std, z, olp, ad, rt, B, A, eps_clip, value_coef,
+                                       entropy_coef, loss_scale, h->dmean, h->dvalue, grad + L.log_std, metrics);
+    HRP_CUDA_OK(cudaGetLastError());
+    // heads: dWa2 = dmean^T a1, dba2 = colsum(dmean); dWc2 = dvalue^T c1, dbc2 = sum(dvalue)
+    if (wgrad(h, A, H, B, h->dmean, h->a1, grad + L.wa2, s)) return -2;
+    if (wgrad(h, 1, H, B, h->dvalue, h->c1, grad + L.wc2, s)) return -2;
+    colsum_kernel<<<(A + 31) / 32, 256, 0, s>>>(h->dmean, A, B, A, grad + L.ba2);
+    colsum_kernel<<<1, 256, 0, s>>>(h->dvalue, 1, B, 1, grad + L.bc2);
+    // d(a1), d(c1) into d1, d2 (ReLU masks applied)
+    heads_backward_kernel<<<(unsigned)((B * H + 255) / 256), 256, 0, s>>>(h->dmean, h->dvalue, params + L.wa2,
+                                                                        params + L.wc2, h->a1, h->c1, B, H, A, h->d1, h->d2);
+    HRP_CUDA_OK(cudaGetLastError());
+    if (wgrad(h, H, H, B, h->d1, h->h2, grad + L.wa1, s)) return -2;
+    if (wgrad(h, H, H, B, h->d2, h->h2, grad + L.wc1, s)) return -2;
+    colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(h->d1, H, B, H, grad + L.ba1);
+    colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(h->d2, H, B, H, grad + L.bc1);
+    // d(h2) = (d(a1) Wa1 + d(c1) Wc1) (.) (h2>0) -> reuse a1 as the destination
+    float *dh2 = h->a1;
+    if (gemm(false, false, Bi, H, H, h->d1, H, params + L.wa1, H, dh2, H, nullptr, 0, nullptr, 0, 0, 1, s) < 0) return -2;
+    if (gemm(false, false, Bi, H, H, h->d2, H, params + L.wc1, H, dh2, H, nullptr, 0, h->h2, H, 1, 1, s) < 0) return -2;
+    if (wgrad(h, H, H, B, dh2, h->h1, grad + L.w2, s)) return -2;
+    colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(dh2, H, B, H, grad + L.b2);
+    // d(h1) = d(h2) W2 (.) (h1>0) -> c1
+    float *dh1 = h->c1;
+    if (gemm(false, false, Bi, H, H, dh2, H, params + L.w2, H, dh1, H, nullptr, 0, h->h1, H, 0, 1, s) < 0) return -2;
+    if (wgrad(h, H, S, B, dh1, x, grad + L.w1, s)) return -2;
+    colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(dh1, H, B, H, grad + L.b1);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int hrp_clip_adam_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int32_t *step, int64_t n,
+                       double lr, double beta1, double beta2, double eps, float max_grad_norm, float *scratch,
+                       void *stream)
+{
+    if (!params || !grad || !exp_avg || !exp_avg_sq || !step || !scratch || n < 1) {
+        hrp_set_error("hrp_clip_adam_step: bad arguments");
+        return -1;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int nparts = (int)((n + 255) / 256);
+    if (nparts > 128) nparts = 128;  // scratch_dev holds >= 128 floats
+    gradnorm_kernel<<<nparts, 256, 0, s>>>(grad, n, scratch);
+    clip_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params, grad, exp_avg, exp_avg_sq, step, n, lr, beta1,
+                                                                beta2, eps, max_grad_norm, scratch, nparts);
+    bump_step_kernel<<<1, 1, 0, s>>>(step);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,517 @@
+"""PPO agent on the C-ABI kernels (reference: ``ppo/agent.py:12-327``).
+
+Same classes, constructor arguments, method names, return types, metrics keys and checkpoint
+format as the reference; the arithmetic runs in ``libhrp_b200.so``:
+
+* ``ActorCritic`` keeps every parameter in ONE flat fp32 device buffer laid out in
+  ``ActorCritic.parameters()`` order (``log_std``, ``shared.0.*``, ``shared.2.*``,
+  ``actor_mean.0.*``, ``actor_mean.2.*``, ``critic.0.*``, ``critic.2.*``); the per-layer tensors
+  of ``state_dict()`` are views into it, so gradients, Adam moments and the multi-GPU all-reduce
+  all touch one contiguous range.
+* ``PPOMemory`` keeps the list-based ``store`` API of the reference loop and adds a device-resident
+  [T, E] rollout for the vectorised loop.
+* ``PPOAgent.update`` = GAE kernel -> advantage normalisation -> for every epoch and minibatch:
+  fused evaluate + loss + backward (``hrp_ppo_loss_grad``), optional NCCL all-reduce of the flat
+  gradient, fused clip-grad-norm + Adam (``hrp_clip_adam_step``).  Metrics are accumulated on the
+  device and read back once per update (the reference syncs five times per minibatch,
+  ``agent.py:230,257-262``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from collections import OrderedDict
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+_PARAM_ORDER = ("log_std", "shared.0.weight", "shared.0.bias", "shared.2.weight", "shared.2.bias",
+                "actor_mean.0.weight", "actor_mean.0.bias", "actor_mean.2.weight", "actor_mean.2.bias",
+                "critic.0.weight", "critic.0.bias", "critic.2.weight", "critic.2.bias")
+
+
+def _param_shapes(S: int, A: int, H: int) -> "OrderedDict[str, tuple]":
+    return OrderedDict([
+        ("log_std", (A,)),
+        ("shared.0.weight", (H, S)), ("shared.0.bias", (H,)),
+        ("shared.2.weight", (H, H)), ("shared.2.bias", (H,)),
+        ("actor_mean.0.weight", (H, H)), ("actor_mean.0.bias", (H,)),
+        ("actor_mean.2.weight", (A, H)), ("actor_mean.2.bias", (A,)),
+        ("critic.0.weight", (H, H)), ("critic.0.bias", (H,)),
+        ("critic.2.weight", (1, H)), ("critic.2.bias", (1,)),
+    ])
+
+
+def _cuda_device(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.HrpError(f"device {device} is not a CUDA device: highway-rope-ppo_b200 has no CPU path")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return torch.device("cuda", idx)
+
+
+class ActorCritic:
+    """Shared 2x(Linear+ReLU) trunk, actor head -> mean, state-independent ``log_std``, critic head.
+
+    Weight initialisation builds the reference's ``nn.Linear`` stack on the CPU in the reference's
+    construction order (``agent.py:22-42``), so a seeded run starts from the same parameters.
+    """
+
+    def __init__(self, state_dim: int, action_dim: int, hidden_dim: int = 128,
+                 device: Any = "cuda", max_batch: int = 4096):
+        self._lib = _lib.load()
+        _lib.require_device()
+        self.device = _cuda_device(device)
+        self.state_dim, self.action_dim, self.hidden_dim = int(state_dim), int(action_dim), int(hidden_dim)
+        S, A, H = self.state_dim, self.action_dim, self.hidden_dim
+        shared = nn.Sequential(nn.Linear(S, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU())
+        actor_mean = nn.Sequential(nn.Linear(H, H), nn.ReLU(), nn.Linear(H, A))
+        log_std = torch.zeros(A)
+        critic = nn.Sequential(nn.Linear(H, H), nn.ReLU(), nn.Linear(H, 1))
+        init = {"log_std": log_std}
+        for prefix, seq in (("shared", shared), ("actor_mean", actor_mean), ("critic", critic)):
+            for k, v in seq.state_dict().items():
+                init[f"{prefix}.{k}"] = v
+        self.shapes = _param_shapes(S, A, H)
+        self.num_params = int(self._lib.hrp_ppo_param_count(S, A, H))
+        assert self.num_params == sum(int(np.prod(s)) for s in self.shapes.values())
+        self.flat = torch.empty(self.num_params, dtype=torch.float32, device=self.device)
+        self._views: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        off = 0
+        for name, shape in self.shapes.items():
+            n = int(np.prod(shape))
+            view = self.flat[off:off + n].view(shape)
+            view.copy_(init[name].detach().to(torch.float32))
+            self._views[name] = view
+            off += n
+        self._h = C.c_void_p()
+        self.max_batch = 0
+        self._ensure_workspace(max_batch)
+
+    def _ensure_workspace(self, batch: int) -> None:
+        if batch <= self.max_batch:
+            return
+        if self._h:
+            torch.cuda.synchronize(self.device)
+            self._lib.hrp_ppo_destroy(self._h)
+            self._h = C.c_void_p()
+        _lib.check(self._lib.hrp_ppo_create(self.state_dim, self.action_dim, self.hidden_dim, int(batch),
+                                            self.device.index, C.byref(self._h)), "hrp_ppo_create")
+        self.max_batch = int(batch)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            if self._h:
+                self._lib.hrp_ppo_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- nn.Module-like surface ----------------------------------------------------------------
+    def parameters(self) -> List[torch.Tensor]:
+        return list(self._views.values())
+
+    def named_parameters(self):
+        return list(self._views.items())
+
+    def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        return OrderedDict((k, v.detach().clone()) for k, v in self._views.items())
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        missing = [k for k in self._views if k not in sd]
+        unexpected = [k for k in sd if k not in self._views]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict for ActorCritic: missing {missing}, "
+                               f"unexpected {unexpected}")
+        for k, v in self._views.items():
+            if k in sd:
+                if tuple(sd[k].shape) != tuple(v.shape):
+                    raise RuntimeError(f"size mismatch for {k}: {tuple(sd[k].shape)} vs {tuple(v.shape)}")
+                v.copy_(sd[k].to(device=self.device, dtype=torch.float32))
+
+    @property
+    def log_std(self) -> torch.Tensor:
+        return self._views["log_std"]
+
+    def to(self, device):
+        return self
+
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = True):
+        return self
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _as_states(self, x) -> torch.Tensor:
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        x = x.to(device=self.device, dtype=torch.float32)
+        return x.contiguous()
+
+    # -- ActorCritic.forward (agent.py:46-54) --------------------------------------------------
+    def forward(self, x):
+        x = self._as_states(x)
+        single = x.dim() == 1
+        xb = x.view(1, -1) if single else x.reshape(-1, x.shape[-1])
+        B = xb.shape[0]
+        if xb.shape[1] != self.state_dim:
+            raise ValueError(f"expected states of width {self.state_dim}, got {xb.shape[1]}")
+        self._ensure_workspace(B)
+        mean = torch.empty((B, self.action_dim), dtype=torch.float32, device=self.device)
+        value = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.hrp_ppo_forward(self._h, self.flat.data_ptr(), xb.data_ptr(), B, mean.data_ptr(),
+                                             value.data_ptr(), self._stream()), "hrp_ppo_forward")
+        std = self.log_std.exp()
+        if single:
+            return mean[0], std, value[0]
+        return mean, std, value
+
+    __call__ = forward
+
+    # -- batched get_action: everything stays on the device -------------------------------------
+    def act(self, states: torch.Tensor, noise: Optional[torch.Tensor] = None, deterministic: bool = False,
+            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """``get_action`` for [B, S] states -> dict(action, pre_tanh [B, A]; log_prob, value [B])."""
+        states = self._as_states(states)
+        B = states.shape[0]
+        self._ensure_workspace(B)
+        A = self.action_dim
+        if out is None:
+            out = {"action": torch.empty((B, A), dtype=torch.float32, device=self.device),
+                   "pre_tanh": torch.empty((B, A), dtype=torch.float32, device=self.device),
+                   "log_prob": torch.empty(B, dtype=torch.float32, device=self.device),
+                   "value": torch.empty(B, dtype=torch.float32, device=self.device)}
+        if not deterministic and noise is None:
+            noise = torch.randn((B, A), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.hrp_ppo_act(self._h, self.flat.data_ptr(), states.data_ptr(),
+                                         None if deterministic else noise.data_ptr(), B,
+                                         out["action"].data_ptr(), out["pre_tanh"].data_ptr(),
+                                         out["log_prob"].data_ptr(), out["value"].data_ptr(), self._stream()),
+                   "hrp_ppo_act")
+        return out
+
+    # -- ActorCritic.get_action (agent.py:56-74): one state, numpy results -----------------------
+    def get_action(self, state, deterministic: bool = False):
+        x = self._as_states(state).view(1, -1)
+        A = self.action_dim
+        buf = torch.empty(2 * A + 2, dtype=torch.float32, device=self.device)
+        out = {"action": buf[0:A], "pre_tanh": buf[A:2 * A], "log_prob": buf[2 * A:2 * A + 1],
+               "value": buf[2 * A + 1:2 * A + 2]}
+        self.act(x, deterministic=deterministic, out=out)
+        host = buf.cpu().numpy()  # one D2H for the four results
+        action, pre_tanh = host[0:A].copy(), host[A:2 * A].copy()
+        log_prob = None if deterministic else float(host[2 * A])
+        return action, pre_tanh, log_prob, np.float32(host[2 * A + 1])
+
+    # -- ActorCritic.evaluate (agent.py:76-84): values only, no autograd graph --------------------
+    def evaluate(self, states, actions, pre_tanh_actions):
+        mean, std, value = self.forward(states)
+        z = self._as_states(pre_tanh_actions)
+        var = std * std
+        logp = -((z - mean) ** 2) / (2 * var) - self.log_std - 0.5 * float(np.log(2 * np.pi))
+        logp = logp - torch.log1p(-torch.tanh(z).pow(2) + 1e-6)
+        entropy = (0.5 + 0.5 * float(np.log(2 * np.pi)) + self.log_std).sum().expand(mean.shape[0])
+        return logp.sum(dim=-1), value, entropy
+
+
+class PPOMemory:
+    """Rollout storage.  ``store`` / ``clear`` / ``compute_advantages`` / ``get_batches`` /
+    ``get_tensors`` keep the reference's list-based protocol (``agent.py:87-154``); the vectorised
+    loop writes straight into device tensors via ``begin_rollout`` / ``slot``."""
+
+    def __init__(self, batch_size: int = 64, device: Any = "cuda"):
+        self.batch_size = batch_size
+        self.device = _cuda_device(device)
+        self.clear()
+        self.rollout: Optional[Dict[str, torch.Tensor]] = None
+
+    def store(self, state, action, pre_tanh_action, reward, next_state, log_prob, done, value):
+        # next_state is accepted and dropped: nothing in the reference ever reads it back
+        self.states.append(state)
+        self.actions.append(action)
+        self.pre_tanh_actions.append(pre_tanh_action)
+        self.rewards.append(reward)
+        self.log_probs.append(log_prob)
+        self.dones.append(done)
+        self.values.append(value)
+
+    def clear(self):
+        self.states: List[Any] = []
+        self.actions: List[Any] = []
+        self.pre_tanh_actions: List[Any] = []
+        self.rewards: List[float] = []
+        self.next_states: List[Any] = []
+        self.log_probs: List[float] = []
+        self.dones: List[bool] = []
+        self.values: List[float] = []
+        self.rollout = None
+
+    def __len__(self):
+        if self.rollout is not None:
+            return int(self.rollout["reward"].numel())
+        return len(self.states)
+
+    # -- device-resident [T, E] rollout -----------------------------------------------------------
+    def begin_rollout(self, T: int, E: int, state_dim: int, action_dim: int) -> Dict[str, torch.Tensor]:
+        """Allocate (or reuse) time-major buffers: states [T+1,E,S] (slot T holds the bootstrap
+        observation), pre_tanh/action [T,E,A], log_prob/value/reward [T,E], done [T,E] uint8."""
+        r = self.rollout
+        if r is None or r["reward"].shape != (T, E) or r["states"].shape[2] != state_dim:
+            d = self.device
+            r = {"states": torch.empty((T + 1, E, state_dim), dtype=torch.float32, device=d),
+                 "action": torch.empty((T, E, action_dim), dtype=torch.float32, device=d),
+                 "pre_tanh": torch.empty((T, E, action_dim), dtype=torch.float32, device=d),
+                 "log_prob": torch.empty((T, E), dtype=torch.float32, device=d),
+                 "value": torch.empty((T, E), dtype=torch.float32, device=d),
+                 "reward": torch.empty((T, E), dtype=torch.float32, device=d),
+                 "done": torch.empty((T, E), dtype=torch.uint8, device=d)}
+        self.rollout = r
+        return r
+
+    def _from_lists(self) -> Dict[str, torch.Tensor]:
+        """The list protocol, moved to the device as a [T, 1] rollout in ONE staging copy per field."""
+        d = self.device
+        T = len(self.states)
+        f32 = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(d)
+        return {"states": f32(np.array(self.states)).view(T, 1, -1),
+                "action": f32(np.array(self.actions)).view(T, 1, -1),
+                "pre_tanh": f32(np.array(self.pre_tanh_actions)).view(T, 1, -1),
+                "log_prob": f32(self.log_probs).view(T, 1),
+                "value": f32(self.values).view(T, 1),
+                "reward": f32(self.rewards).view(T, 1),
+                "done": torch.from_numpy(np.asarray(self.dones, dtype=np.uint8)).to(d).view(T, 1)}
+
+    def as_rollout(self) -> Dict[str, torch.Tensor]:
+        return self.rollout if self.rollout is not None else self._from_lists()
+
+    # -- reference protocol -------------------------------------------------------------------------
+    def compute_advantages(self, gamma: float, lam: float, last_value):
+        """GAE (``agent.py:126-138``) on the device; returns (advantages, returns) as numpy arrays
+        of shape [T] for a list-built memory, [T, E] for a device rollout."""
+        r = self.as_rollout()
+        adv, ret = gae(r["reward"], r["value"], r["done"], last_value, gamma, lam)
+        if self.rollout is None:
+            return adv.view(-1).cpu().numpy(), ret.view(-1).cpu().numpy()
+        return adv.cpu().numpy(), ret.cpu().numpy()
+
+    def get_batches(self):
+        n = len(self)
+        indices = np.arange(n, dtype=np.int64)
+        np.random.shuffle(indices)
+        return [indices[i:i + self.batch_size] for i in range(0, n, self.batch_size)]
+
+    def get_tensors(self):
+        r = self.as_rollout()
+        S, A = r["states"].shape[-1], r["action"].shape[-1]
+        n = r["reward"].numel()
+        return (r["states"].reshape(-1, S)[:n], r["action"].reshape(-1, A), r["pre_tanh"].reshape(-1, A),
+                r["log_prob"].reshape(-1))
+
+
+def gae(reward: torch.Tensor, value: torch.Tensor, done: torch.Tensor, last_value, gamma: float, lam: float):
+    """``PPOMemory.compute_advantages`` over time-major [T, E] tensors (reverse scan kernel)."""
+    lib = _lib.load()
+    T, E = reward.shape
+    dev = reward.device
+    if not torch.is_tensor(last_value):
+        last_value = torch.full((E,), float(last_value), dtype=torch.float32, device=dev)
+    last_value = last_value.to(device=dev, dtype=torch.float32).reshape(E).contiguous()
+    adv = torch.empty((T, E), dtype=torch.float32, device=dev)
+    ret = torch.empty((T, E), dtype=torch.float32, device=dev)
+    done = done.to(torch.uint8).contiguous()
+    _lib.check(lib.hrp_gae(reward.contiguous().data_ptr(), value.contiguous().data_ptr(), done.data_ptr(),
+                           last_value.data_ptr(), T, E, float(gamma), float(lam), adv.data_ptr(), ret.data_ptr(),
+                           torch.cuda.current_stream(dev).cuda_stream), "hrp_gae")
+    return adv, ret
+
+
+class _AdamState:
+    """``optim.Adam(params, lr)`` as flat moment buffers + a device step counter."""
+
+    def __init__(self, ac: ActorCritic, lr: float):
+        self.ac = ac
+        self.lr, self.betas, self.eps = float(lr), (0.9, 0.999), 1e-8
+        d = ac.device
+        self.exp_avg = torch.zeros(ac.num_params, dtype=torch.float32, device=d)
+        self.exp_avg_sq = torch.zeros(ac.num_params, dtype=torch.float32, device=d)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=d)
+        self.scratch = torch.zeros(128, dtype=torch.float32, device=d)
+        self.param_groups = [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0,
+                              "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                              "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                              "params": list(range(len(ac.shapes)))}]
+
+    def state_dict(self) -> Dict[str, Any]:
+        """Same structure as ``torch.optim.Adam.state_dict()`` over ``ActorCritic.parameters()``."""
+        step = int(self.step_dev.item())
+        state: Dict[int, Any] = {}
+        if step > 0:
+            off = 0
+            for i, shape in enumerate(self.ac.shapes.values()):
+                n = int(np.prod(shape))
+                state[i] = {"step": torch.tensor(float(step)),
+                            "exp_avg": self.exp_avg[off:off + n].view(shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view(shape).clone()}
+                off += n
+        groups = [dict(g) for g in self.param_groups]
+        groups[0]["lr"] = self.lr
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        state = sd.get("state", {})
+        off, step = 0, 0
+        for i, shape in enumerate(self.ac.shapes.values()):
+            n = int(np.prod(shape))
+            s = state.get(i, state.get(str(i)))
+            if s is not None:
+                self.exp_avg[off:off + n].copy_(s["exp_avg"].reshape(-1).to(self.exp_avg))
+                self.exp_avg_sq[off:off + n].copy_(s["exp_avg_sq"].reshape(-1).to(self.exp_avg_sq))
+                step = int(float(s["step"]))
+            off += n
+        self.step_dev.fill_(step)
+        groups = sd.get("param_groups") or []
+        if groups:
+            self.lr = float(groups[0].get("lr", self.lr))
+            self.betas = tuple(groups[0].get("betas", self.betas))
+            self.eps = float(groups[0].get("eps", self.eps))
+
+
+class PPOAgent:
+    def __init__(self, state_dim: int, action_dim: int, lr: float = 1e-4, gamma: float = 0.99, lam: float = 0.95,
+                 eps_clip: float = 0.2, value_coef: float = 0.5, entropy_coef: float = 0.005,
+                 max_grad_norm: float = 0.5, epochs: int = 6, batch_size: int = 64, hidden_dim: int = 128,
+                 logger: Optional[logging.Logger] = None, device: Any = "cuda"):
+        self._lib = _lib.load()
+        self.device = _cuda_device(device)
+        self.actor_critic = ActorCritic(state_dim, action_dim, hidden_dim, device=self.device,
+                                        max_batch=max(int(batch_size), 1))
+        self.optimizer = _AdamState(self.actor_critic, lr)
+        self.gamma, self.lam, self.eps_clip = gamma, lam, eps_clip
+        self.value_coef, self.entropy_coef, self.max_grad_norm = value_coef, entropy_coef, max_grad_norm
+        self.epochs = epochs
+        self.logger = logger or logging.getLogger(__name__)
+        self.memory = PPOMemory(batch_size=batch_size, device=self.device)
+        P = self.actor_critic.num_params
+        self.grad = torch.zeros(P, dtype=torch.float32, device=self.device)
+        self._metrics = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._stats = torch.zeros(3 + 512, dtype=torch.float64, device=self.device)
+        self.launches = 0  # hrp_* calls enqueued by this agent (each is >= 1 kernel of this library)
+
+    # -- acting ----------------------------------------------------------------------------------
+    def select_action(self, state, deterministic: bool = False):
+        self.launches += 1
+        return self.actor_critic.get_action(state, deterministic)
+
+    def act(self, states: torch.Tensor, deterministic: bool = False, noise: Optional[torch.Tensor] = None,
+            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        self.launches += 1
+        return self.actor_critic.act(states, noise=noise, deterministic=deterministic, out=out)
+
+    # -- distributed helpers ---------------------------------------------------------------------
+    @staticmethod
+    def _world() -> int:
+        import torch.distributed as dist
+
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _allreduce(self, t: torch.Tensor) -> None:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    # -- one optimizer step on minibatch ``idx`` (device int64) ----------------------------------
+    def _minibatch_step(self, flat: Dict[str, torch.Tensor], idx: Optional[torch.Tensor], B: int, world: int) -> None:
+        ac, opt, s = self.actor_critic, self.optimizer, self.actor_critic._stream()
+        _lib.check(self._lib.hrp_ppo_loss_grad(
+            ac._h, ac.flat.data_ptr(), flat["states"].data_ptr(), flat["pre_tanh"].data_ptr(),
+            flat["log_prob"].data_ptr(), flat["adv"].data_ptr(), flat["ret"].data_ptr(), _lib.ptr(idx), B,
+            float(self.eps_clip), float(self.value_coef), float(self.entropy_coef), 1.0 / (B * world),
+            self.grad.data_ptr(), self._metrics.data_ptr(), s), "hrp_ppo_loss_grad")
+        if world > 1:
+            self._allreduce(self.grad)
+        _lib.check(self._lib.hrp_clip_adam_step(
+            ac.flat.data_ptr(), self.grad.data_ptr(), opt.exp_avg.data_ptr(), opt.exp_avg_sq.data_ptr(),
+            opt.step_dev.data_ptr(), ac.num_params, opt.lr, opt.betas[0], opt.betas[1], opt.eps,
+            float(self.max_grad_norm), opt.scratch.data_ptr(), s), "hrp_clip_adam_step")
+        self.launches += 2
+
+    # -- PPOAgent.update (agent.py:196-308) --------------------------------------------------------
+    def update(self, last_value=0.0) -> Dict[str, float]:
+        mem, ac = self.memory, self.actor_critic
+        r = mem.as_rollout()
+        T, E = r["reward"].shape
+        n = T * E
+        S, A = ac.state_dim, ac.action_dim
+        world = self._world()
+        stream = ac._stream()
+        adv, ret = gae(r["reward"], r["value"], r["done"], last_value, self.gamma, self.lam)
+        # advantage normalisation over the whole (global) buffer, unbiased std (agent.py:204)
+        adv_n = adv.clone()
+        _lib.check(self._lib.hrp_adv_stats(adv_n.data_ptr(), n, self._stats.data_ptr(), stream), "hrp_adv_stats")
+        if world > 1:
+            self._allreduce(self._stats[:3])
+        _lib.check(self._lib.hrp_adv_normalize(adv_n.data_ptr(), n, self._stats.data_ptr(), stream),
+                   "hrp_adv_normalize")
+        self.launches += 3
+        flat = {"states": r["states"].reshape(-1, S)[:n].contiguous(), "pre_tanh": r["pre_tanh"].reshape(n, A),
+                "log_prob": r["log_prob"].reshape(n), "adv": adv_n.view(n), "ret": ret.view(n)}
+        # one permutation per update, reused by every epoch (agent.py:140-147,205)
+        perm = np.arange(n, dtype=np.int64)
+        np.random.shuffle(perm)
+        perm_dev = torch.from_numpy(perm).to(self.device)
+        bs = int(mem.batch_size)
+        ac._ensure_workspace(min(bs, n))
+        self._metrics.zero_()
+        for _ in range(self.epochs):
+            for start in range(0, n, bs):
+                B = min(bs, n - start)
+                self._minibatch_step(flat, perm_dev[start:start + B], B, world)
+        # explained variance of the value predictions (agent.py:276-285)
+        y_pred, y_true = r["value"].reshape(n), ret.view(n)
+        if world > 1:
+            # global variances from all-reduced moments
+            res = y_true - y_pred
+            mom = torch.stack([y_true.double().sum(), (y_true.double() ** 2).sum(), res.double().sum(),
+                               (res.double() ** 2).sum(), torch.tensor(float(n), dtype=torch.float64, device=self.device)])
+            self._allreduce(mom)
+            cnt = mom[4]
+            var_y = (mom[1] - mom[0] ** 2 / cnt) / (cnt - 1)
+            var_r = (mom[3] - mom[2] ** 2 / cnt) / (cnt - 1)
+            self._allreduce(self._metrics)
+        else:
+            var_y = torch.var(y_true) if n > 1 else torch.zeros((), device=self.device)
+            var_r = torch.var(y_true - y_pred) if n > 1 else torch.zeros((), device=self.device)
+        tail = torch.stack([var_y.float(), var_r.float()])
+        host = torch.cat([self._metrics, tail]).cpu().numpy()  # the update's single D2H
+        count = max(float(host[6]), 1.0)
+        explained = float(1.0 - host[9] / host[8]) if host[8] > 0 else 0.0
+        out = {"loss": float(host[0] / count), "policy_loss": float(host[1] / count),
+               "value_loss": float(host[2] / count), "entropy": float(host[3] / count),
+               "clip_fraction": float(host[4] / count), "approx_kl": float(host[5] / count),
+               "explained_variance": explained}
+        self.logger.info(
+            "update_complete loss=%.4f policy_loss=%.4f value_loss=%.4f entropy=%.4f clip_frac=%.3f kl=%.5f "
+            "explained_var=%.3f", out["loss"], out["policy_loss"], out["value_loss"], out["entropy"],
+            out["clip_fraction"], out["approx_kl"], out["explained_variance"])
+        mem.clear()
+        return out
+
+    # -- checkpoints (agent.py:310-327): same file format and key names ----------------------------
+    def save(self, path: str):
+        torch.save({"model": self.actor_critic.state_dict(), "optimizer": self.optimizer.state_dict()}, path)
+        self.logger.info(f"model_saved path={path}")
+
+    def load(self, path: str, load_optimizer: bool = True):
+        checkpoint = torch.load(path, map_location=self.device)
+        self.actor_critic.load_state_dict(checkpoint["model"])
+        if load_optimizer and "optimizer" in checkpoint:
+            self.optimizer.load_state_dict(checkpoint["optimizer"])
+        self.logger.info(f"model_loaded path={path}")
+        return checkpoint.get("config", {})

@@ -1,0 +1,204 @@
+/*
+ * hrp.h -- C ABI of the B200-native hot path of highway-rope-ppo.
+ *
+ * The reference (DhruvDh/highway-rope-ppo) is pure Python and has no FFI of its
+ * own; the boundary it exposes for this path is two Python protocols:
+ *   - the gymnasium env produced by experiments/wrappers.py:14-104 (make_env) and
+ *     stepped at training/routine.py:18,24,127,134, with the observation wrappers
+ *     experiments/rope_embed.py:64-74, dist_embed.py:76-96, rank_embed.py:45-51;
+ *   - ppo/agent.py:157-327 (PPOAgent.select_action / memory / update).
+ * Each entry point below names the reference interface it replaces.  The Python
+ * host (highway-rope-ppo_b200/) binds this library with ctypes and mirrors the
+ * reference classes on top; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only.  "_dev" pointers are device memory
+ * owned by the caller (e.g. torch allocations), contiguous; "_host" pointers are
+ * host memory.  Every call returns 0 on success, <0 on error
+ * (hrp_last_error() gives the thread-local message).  Work is enqueued on the
+ * caller's stream (a cudaStream_t passed as void*), with no hidden
+ * synchronisation unless the entry point says "synchronous".  A handle is bound to
+ * one device and is not thread-safe.  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails.
+ */
+#ifndef HRP_H
+#define HRP_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRP_MAX_VEHICLES 64   /* vehicles per env incl. ego (one warp, two per lane) */
+#define HRP_MAX_OBS_ROWS 64
+#define HRP_MAX_FEATURES 8
+#define HRP_MAX_LANES 8
+#define HRP_MAX_EMBED 64
+#define HRP_MAX_EMBED_COLS 1024 /* F of hrp_embed_apply on caller-provided observations */
+
+/* Kinematics feature codes (highway-env Vehicle.to_dict keys used by
+ * config/base_config.py:9,11-19) */
+enum { HRP_F_PRESENCE = 0, HRP_F_X, HRP_F_Y, HRP_F_VX, HRP_F_VY, HRP_F_HEADING, HRP_F_COS_H, HRP_F_SIN_H };
+/* observation embedding fused behind the Kinematics observation */
+enum { HRP_EMBED_NONE = 0, HRP_EMBED_ROPE = 1, HRP_EMBED_DIST = 2, HRP_EMBED_RANK = 3 };
+
+/* highway-v0 config (config/base_config.py:5-39 over HighwayEnv.default_config) */
+typedef struct hrp_cfg {
+    int32_t lanes_count;
+    int32_t vehicles_count;        /* other vehicles; V = vehicles_count + 1 */
+    int32_t simulation_frequency;
+    int32_t policy_frequency;
+    int32_t initial_lane_id;       /* -1 == None */
+    int32_t ego_mode;              /* 0 ContinuousAction (base_config.py:23-27), 1 DiscreteMetaAction */
+    int32_t normalize_reward;
+    int32_t offroad_terminal;
+    double  duration;
+    double  ego_spacing;
+    double  vehicles_density;
+    double  collision_reward;
+    double  right_lane_reward;
+    double  high_speed_reward;
+    double  reward_speed_lo;
+    double  reward_speed_hi;
+    /* KinematicObservation */
+    int32_t obs_vehicles;          /* N rows */
+    int32_t obs_nfeat;             /* F */
+    int32_t obs_feat[HRP_MAX_FEATURES];
+    int32_t obs_has_range[HRP_MAX_FEATURES];
+    double  obs_lo[HRP_MAX_FEATURES];
+    double  obs_hi[HRP_MAX_FEATURES];
+    int32_t obs_normalize;
+    int32_t obs_clip;
+    int32_t obs_absolute;
+    int32_t obs_sorted;            /* 1 "sorted", 0 "shuffled" (wrappers.py:47-57) */
+    int32_t obs_see_behind;
+    /* embedding wrapper (rope_embed.py:14-42, dist_embed.py:10-66, rank_embed.py:10-37) */
+    int32_t embed_kind;            /* HRP_EMBED_* */
+    int32_t embed_dim;             /* rotate_dim (RoPE) or d_embed (Dist/Rank) */
+    int32_t embed_use_euclidean;   /* DistanceEmbedWrapper(use_euclidean=) */
+    double  embed_max_dist;        /* max_dist, utils/defaults.py:10-13 */
+    /* vec-env behaviour */
+    int32_t autoreset;             /* respawn inside the step that ended the episode */
+    int32_t embed_ego_idx;         /* ego_idx of the embed wrappers (row the distance refers to) */
+} hrp_cfg;
+
+/* Host-side SoA view of the simulator state, [num_envs * V] per vehicle field
+ * (ego = index 0 of every env), [num_envs] per env field.  Used for state
+ * injection (parity tests) and checkpointing. */
+typedef struct hrp_state {
+    double  *x, *y, *heading, *speed, *target_speed, *delta, *timer, *impact_x, *impact_y;
+    int32_t *lane, *target_lane, *crashed, *has_impact;
+    double  *time;      /* env.time */
+    uint32_t *episode;  /* spawn counter of every env */
+    uint32_t *obs_draw; /* shuffle counter of every env */
+} hrp_state;
+
+typedef struct hrp_env hrp_env;
+
+const char *hrp_last_error(void);
+int hrp_version(void);
+/* number of CUDA devices visible; <0 on driver error */
+int hrp_device_count(void);
+
+/* ---- simulator: replaces gym.make("highway-v0", config=cfg) + wrapper construction
+ *      (experiments/wrappers.py:80,100-104).  embed_table_host: RoPE inv_freq[rotate_dim/2]
+ *      (rope_embed.py:37-39), DistPE freqs[d/2] (dist_embed.py:48-52) or tanh(rank table)[N*d]
+ *      (rank_embed.py:21-22,48); copied.  env_id_base offsets the Philox counter so that
+ *      a shard owns envs [env_id_base, env_id_base+num_envs). */
+int hrp_env_create(const hrp_cfg *cfg, const float *embed_table_host, int64_t embed_table_len,
+                   int32_t num_envs, uint64_t env_id_base, int32_t device, hrp_env **out);
+int hrp_env_destroy(hrp_env *env);
+int hrp_env_obs_dim(const hrp_env *env, int32_t *rows, int32_t *cols);
+int hrp_env_num_vehicles(const hrp_env *env);
+
+/* env.reset(seed=...) (training/routine.py:18,127): counter-based spawn of every env whose
+ * mask byte is non-zero (mask_dev NULL: all), then the observation into obs_dev[E,N,F_out]. */
+int hrp_env_reset(hrp_env *env, uint64_t seed, const uint8_t *mask_dev, float *obs_dev, void *stream);
+
+/* env.step(action) (training/routine.py:24,134): 15 fused sub-steps + observation + embedding.
+ * actions_dev[E,2] float32 (ContinuousAction) or [E,2] with the meta-action id in column 0.
+ * perm_dev (nullable) [E,N-1] int32 injects the row shuffle; row_vehicle_dev (nullable)
+ * [E,N] int32 receives the vehicle index shown in each row (-1 padding). */
+int hrp_env_step(hrp_env *env, const float *actions_dev, float *obs_dev, float *reward_dev,
+                 uint8_t *terminated_dev, uint8_t *truncated_dev, const int32_t *perm_dev,
+                 int32_t *row_vehicle_dev, void *stream);
+
+/* observation_type.observe() + wrapper.observation() of the current state */
+int hrp_env_observe(hrp_env *env, float *obs_dev, const int32_t *perm_dev, int32_t *row_vehicle_dev,
+                    void *stream);
+
+/* the same step for callers with HOST buffers (what the reference's CPU loop would bind):
+ * pinned staging, H2D actions, kernel, D2H results; synchronous. */
+int hrp_env_step_host(hrp_env *env, const float *actions_host, float *obs_host, float *reward_host,
+                      uint8_t *terminated_host, uint8_t *truncated_host);
+int hrp_env_reset_host(hrp_env *env, uint64_t seed, float *obs_host);
+
+/* state injection / extraction; synchronous */
+int hrp_env_get_state(hrp_env *env, hrp_state *dst_host);
+int hrp_env_set_state(hrp_env *env, const hrp_state *src_host);
+
+/* the generator behind spawn and shuffle (known-answer test) */
+int hrp_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* ---- wrappers on caller-provided observations: RotaryEmbedWrapper.observation
+ *      (rope_embed.py:64-74), DistanceEmbedWrapper.observation (dist_embed.py:76-96),
+ *      RankEmbedWrapper.observation (rank_embed.py:45-51).  obs_dev[B,N,F] -> out_dev[B,N,F_out].
+ *      dist_override_dev (nullable) [B,N] replaces the computed normalised distance, which is
+ *      RotaryEmbedWrapper._apply_rope(obs, dist_norm) (rope_embed.py:44-62). */
+int hrp_embed_apply(int32_t kind, int32_t embed_dim, int32_t use_euclidean, int32_t ego_idx,
+                    float max_dist, const float *table_dev, const float *obs_dev, float *out_dev,
+                    int64_t batch, int32_t rows, int32_t cols, const float *dist_override_dev,
+                    void *stream);
+
+/* ---- PPO (ppo/agent.py).  Parameters live in ONE flat fp32 buffer, laid out in
+ *      ActorCritic.parameters() order (agent.py:12-44; the root module's own Parameter comes
+ *      first): log_std, shared.0.{weight,bias}, shared.2.{weight,bias}, actor_mean.0.*,
+ *      actor_mean.2.*, critic.0.*, critic.2.*; nn.Linear weights row-major [out,in].
+ *      hrp_ppo_param_count gives P. */
+int64_t hrp_ppo_param_count(int32_t state_dim, int32_t action_dim, int32_t hidden_dim);
+
+typedef struct hrp_ppo hrp_ppo;
+/* workspace for batches up to max_batch rows */
+int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, int64_t max_batch,
+                   int32_t device, hrp_ppo **out);
+int hrp_ppo_destroy(hrp_ppo *h);
+
+/* ActorCritic.forward (agent.py:46-54): states[B,S] -> mean[B,A], value[B] */
+int hrp_ppo_forward(hrp_ppo *h, const float *params_dev, const float *states_dev, int64_t batch,
+                    float *mean_dev, float *value_dev, void *stream);
+/* ActorCritic.get_action (agent.py:56-74) for a batch: noise_dev[B,A] standard normals
+ * (nullable => deterministic).  Outputs action=tanh(z), pre_tanh=z, log_prob[B], value[B]. */
+int hrp_ppo_act(hrp_ppo *h, const float *params_dev, const float *states_dev, const float *noise_dev,
+                int64_t batch, float *action_dev, float *pre_tanh_dev, float *log_prob_dev,
+                float *value_dev, void *stream);
+/* PPOMemory.compute_advantages (agent.py:126-138) over [T,E] (time-major), reverse scan.
+ * last_value_dev[E]; done as uint8.  Outputs advantages[T,E] (float32), returns[T,E]. */
+int hrp_gae(const float *reward_dev, const float *value_dev, const uint8_t *done_dev,
+            const float *last_value_dev, int64_t T, int64_t E, float gamma, float lam,
+            float *adv_dev, float *ret_dev, void *stream);
+/* advantage normalisation (agent.py:204): (a-mean)/(std_unbiased+1e-8), in place.
+ * hrp_adv_stats writes (sum, sum of squares, n) of the local shard to stats_dev[0..2] (fp64;
+ * stats_dev must hold 3 + 512 doubles, the tail is scratch); a sharded run all-reduces those
+ * three numbers before hrp_adv_normalize consumes them. */
+int hrp_adv_stats(const float *adv_dev, int64_t n, double *stats_dev, void *stream);
+int hrp_adv_normalize(float *adv_dev, int64_t n, const double *stats_dev, void *stream);
+/* one minibatch of PPOAgent.update (agent.py:218-245 + backward): evaluate, clipped surrogate,
+ * value MSE, entropy; writes d(loss)/d(params) into grad_dev[P] (overwritten) and
+ * metrics_dev[8] += (loss, policy_loss, value_loss, entropy, clip_fraction, approx_kl, 1, 0).
+ * idx_dev (nullable) [B] int64 gathers the minibatch rows out of the rollout tensors.
+ * loss_scale multiplies every per-sample term (1/B_global for sharded minibatches). */
+int hrp_ppo_loss_grad(hrp_ppo *h, const float *params_dev, const float *states_dev,
+                      const float *pre_tanh_dev, const float *old_log_prob_dev, const float *adv_dev,
+                      const float *ret_dev, const int64_t *idx_dev, int64_t batch, float eps_clip,
+                      float value_coef, float entropy_coef, float loss_scale, float *grad_dev,
+                      float *metrics_dev, void *stream);
+/* clip_grad_norm_ + Adam.step (agent.py:247-252) fused over the flat buffers.
+ * step_dev[1] int32 is incremented on device (bias correction). */
+int hrp_clip_adam_step(float *params_dev, const float *grad_dev, float *exp_avg_dev,
+                       float *exp_avg_sq_dev, int32_t *step_dev, int64_t n, double lr, double beta1,
+                       double beta2, double eps, float max_grad_norm, float *scratch_dev /* >=128 floats */,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

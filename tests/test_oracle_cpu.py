@@ -1,0 +1,284 @@
+"""The oracle against what pins it (CPU only).
+
+* embedding and PPO restatements vs tests/golden/*.npz, which tools/gen_golden.py produced by
+  running the reference's own classes (rope_embed.py, dist_embed.py, rank_embed.py, ppo/agent.py);
+* the simulator restatement (PARITY UNPINNED, see oracle/highway_oracle.h) vs known answers derived
+  by hand from the published formulas of highway-env 1.10.1;
+* Philox4x32-10 vs the Random123 known-answer vectors.
+"""
+import copy
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden
+from oracle import embed as oe
+from oracle import highway as oh
+from oracle import ppo_ref
+
+
+# ---------------------------------------------------------------- embedding vs reference fixtures
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "embed_rope_*.npz"))))
+def test_rope_oracle_matches_reference(path):
+    g = dict(np.load(path))
+    rd, md = int(g["rotate_dim"]), float(g["max_dist"])
+    assert np.array_equal(oe.rope_inv_freq(rd, md), g["inv_freq"])
+    for o, want, dn, want_dn in zip(g["obs"], g["out"], g["dist_norm"], g["out_dist_norm"]):
+        assert np.array_equal(oe.rope(o, rd, md), want)
+        assert np.array_equal(oe.apply_rope(o, dn, g["inv_freq"], rd), want_dn)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "embed_dist_*.npz"))))
+def test_dist_oracle_matches_reference(path):
+    g = dict(np.load(path))
+    d, md, eu = int(g["d_embed"]), float(g["max_dist"]), bool(g["use_euclidean"])
+    np.testing.assert_allclose(oe.dist_freqs(d, md), g["freqs"], rtol=2e-7)
+    for o, want in zip(g["obs"], g["out"]):
+        assert np.array_equal(oe.distpe(o, d, md, use_euclidean=eu, freqs=g["freqs"]), want)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "embed_rank_*.npz"))))
+def test_rank_oracle_matches_reference(path):
+    g = dict(np.load(path))
+    for o, want in zip(g["obs"], g["out"]):
+        assert np.array_equal(oe.rankpe(o, g["tag"]), want)
+    assert np.abs(g["tag"]).max() < math.tanh(0.05) + 1e-7
+
+
+def test_known_frequencies():
+    # F=4, rotate 4 -> inv_freq [1, 0.1]; DistPE d=16 -> 100^(-2k/16)
+    np.testing.assert_allclose(oe.rope_inv_freq(4, 100.0), [1.0, 0.1], rtol=1e-6)
+    np.testing.assert_allclose(oe.dist_freqs(16, 100.0),
+                               [1, .5623413, .3162278, .1778279, .1, .05623413, .03162278, .01778279], rtol=1e-5)
+
+
+# ---------------------------------------------------------------- PPO vs reference fixtures
+@pytest.mark.parametrize("name", ["s60_h256_b64", "s20_h32_b17", "s300_h64_b256"])
+def test_ppo_oracle_matches_reference_step(name):
+    g = golden(f"ppo_step_{name}.npz")
+    S, A, H, B, _ = (int(v) for v in g["dims"])
+    t = lambda k: torch.from_numpy(g[k])
+    flat = t("params0")
+    mean, log_std, value = ppo_ref.forward(flat, t("states"), S, A, H)
+    np.testing.assert_allclose(mean.numpy(), g["mean"], atol=1e-6)
+    np.testing.assert_allclose(value.numpy(), g["value"], atol=1e-6)
+    logp, _, ent = ppo_ref.evaluate(flat, t("states"), t("pre_tanh"), S, A, H)
+    np.testing.assert_allclose(logp.numpy(), g["logp"], atol=2e-5, rtol=1e-6)
+    np.testing.assert_allclose(ent.numpy(), g["entropy"], atol=1e-6)
+    r = ppo_ref.loss_and_grad(flat, t("states"), t("pre_tanh"), t("old_logp"), t("adv"), t("ret"), S, A, H)
+    assert abs(r["loss"] - float(g["loss"])) < 1e-5
+    assert abs(r["actor"] - float(g["actor_loss"])) < 1e-5
+    assert abs(r["critic"] - float(g["critic_loss"])) < 1e-5
+    assert abs(r["clip_fraction"] - float(g["clip_fraction"])) < 1e-7
+    np.testing.assert_allclose(r["grad"].numpy(), g["grads"], atol=2e-6, rtol=1e-4)
+    p1, m, v, total = ppo_ref.clip_adam(flat, r["grad"], torch.zeros_like(flat), torch.zeros_like(flat), 1)
+    assert abs(total - float(g["total_norm"])) < 1e-4 * max(1.0, total)
+    np.testing.assert_allclose(p1.numpy(), g["params1"], atol=2e-7)
+    r2 = ppo_ref.loss_and_grad(p1, t("states"), t("pre_tanh"), t("old_logp"), t("adv"), t("ret"), S, A, H)
+    p2, _, _, _ = ppo_ref.clip_adam(p1, r2["grad"], m, v, 2)
+    np.testing.assert_allclose(p2.numpy(), g["params2"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["t50", "t2048"])
+def test_gae_oracle_matches_reference(name):
+    g = golden(f"ppo_gae_{name}.npz")
+    adv, ret = ppo_ref.gae(g["reward"], g["value"], g["done"], float(g["last_value"]))
+    assert np.array_equal(adv, g["adv"])
+    assert np.array_equal(ret, g["ret"])
+
+
+# ---------------------------------------------------------------- Philox known answers (Random123 kat_vectors)
+@pytest.mark.parametrize("ctr,key,want", [
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+])
+def test_philox_known_answers(ctr, key, want):
+    assert tuple(int(x) for x in oh.philox4x32_10(ctr, key)) == want
+
+
+# ---------------------------------------------------------------- simulator restatement: hand-derived known answers
+def _state(env, **over):
+    st = env.get_state()
+    for k, v in over.items():
+        st[k] = np.asarray(v, dtype=st[k].dtype) if not np.isscalar(v) else v
+    return st
+
+
+def _lone_ego_cfg(cfg, vehicles=0):
+    c = copy.deepcopy(cfg)
+    c["vehicles_count"] = vehicles
+    return c
+
+
+def test_sim_ego_bicycle_known_answer(highway_config):
+    """One vehicle, zero steering, a0 = 0.5 -> acc 2.5 m/s^2: explicit Euler over 15 frames of 1/15 s."""
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config))
+    env.reset(1)
+    st = env.get_state()
+    st["x"][0], st["y"][0], st["speed"][0], st["heading"][0] = 100.0, 4.0, 20.0, 0.0
+    st["lane"][0] = st["target_lane"][0] = 1
+    env.set_state(st)
+    r, term, trunc = env.step([0.5, 0.0])
+    x, v = 100.0, 20.0
+    for _ in range(15):
+        x += v / 15.0
+        v += 2.5 / 15.0
+    s1 = env.get_state()
+    assert abs(s1["x"][0] - x) < 1e-9 and abs(s1["speed"][0] - v) < 1e-9
+    assert s1["y"][0] == 4.0 and s1["lane"][0] == 1 and not term and not trunc
+    # reward: lane 1 of 4 -> 0.1 * 1/3; speed 22.5 -> 0.4 * 0.25; normalised by [-1, 0.5]
+    want = (0.1 / 3 + 0.4 * (v - 20.0) / 10.0 + 1.0) / 1.5
+    assert abs(r - want) < 1e-12
+
+
+def test_sim_steering_known_answer(highway_config):
+    """a1 = 1 -> steering pi/4: beta = atan(tan(pi/4)/2); one frame checked by hand, then lane re-assignment."""
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config))
+    env.reset(1)
+    st = env.get_state()
+    st["x"][0], st["y"][0], st["speed"][0], st["heading"][0] = 50.0, 0.0, 15.0, 0.0
+    st["lane"][0] = st["target_lane"][0] = 0
+    env.set_state(st)
+    env.step([0.0, 1.0])
+    # ContinuousAction.get_action maps the np.float32 action in float32 (lmap keeps the dtype)
+    q = np.float32(math.pi / 4)
+    steer = float(-q + (np.float32(1.0) + np.float32(1.0)) * np.float32(math.pi / 4 + math.pi / 4) / np.float32(2.0))
+    beta = math.atan(0.5 * math.tan(steer))
+    y = h = 0.0
+    x, v = 50.0, 15.0
+    for _ in range(15):
+        x += v * math.cos(h + beta) / 15.0
+        y += v * math.sin(h + beta) / 15.0
+        h += v * math.sin(beta) / 2.5 / 15.0
+    s1 = env.get_state()
+    assert abs(s1["x"][0] - x) < 1e-9 and abs(s1["y"][0] - y) < 1e-9 and abs(s1["heading"][0] - h) < 1e-12
+    assert s1["lane"][0] == min(3, int(round(y / 4.0)))
+
+
+def test_sim_truncation_and_offroad(highway_config):
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config))
+    env.reset(3)
+    st = env.get_state()
+    st["time"] = 39.0
+    st["y"][0] = 20.0  # far right of lane 3 (y = 12): off road -> reward 0, not terminal (offroad_terminal False)
+    st["lane"][0] = st["target_lane"][0] = 3
+    env.set_state(st)
+    r, term, trunc = env.step([0.0, 0.0])
+    assert r == 0.0 and not term and trunc
+
+
+def test_sim_idm_free_road_and_following(highway_config):
+    """IDM known answers on frame 1: free road a = 3 (1 - (v/v0)^delta); with a leader the interaction term."""
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config, vehicles=2))
+    env.reset(5)
+    st = env.get_state()
+    # ego far behind on lane 3; follower (1) and leader (2) on lane 0, 30 m apart
+    st["x"][:] = [0.0, 200.0, 230.0]
+    st["y"][:] = [12.0, 0.0, 0.0]
+    st["lane"][:] = st["target_lane"][:] = [3, 0, 0]
+    st["speed"][:] = [10.0, 24.0, 20.0]
+    st["target_speed"][:] = [10.0, 30.0, 20.0]
+    st["delta"][:] = [4.0, 4.0, 4.0]
+    st["timer"][:] = [0.0, 0.0, 0.0]
+    st["heading"][:] = 0.0
+    env.set_state(st)
+    env.step([0.0, 0.0])
+    # replay the two IDM vehicles by hand (no lane change can fire: timer < 1 for the whole step)
+    x = [200.0, 230.0]; v = [24.0, 20.0]; v0 = [30.0, 20.0]
+    for _ in range(15):
+        gap = 10.0 + v[0] * 1.5 + v[0] * (v[0] - v[1]) / (2 * math.sqrt(15.0))
+        a0 = 3 * (1 - (v[0] / v0[0]) ** 4) - 3 * (gap / (x[1] - x[0])) ** 2
+        a1 = 3 * (1 - (v[1] / v0[1]) ** 4)
+        a0, a1 = max(-6, min(6, a0)), max(-6, min(6, a1))
+        x = [x[0] + v[0] / 15.0, x[1] + v[1] / 15.0]
+        v = [v[0] + a0 / 15.0, v[1] + a1 / 15.0]
+    s1 = env.get_state()
+    np.testing.assert_allclose(s1["x"][1:], x, atol=1e-9)
+    np.testing.assert_allclose(s1["speed"][1:], v, atol=1e-9)
+
+
+def test_sim_lane_change_timer_fires_on_frame_16(highway_config):
+    """15 x (1/15) in fp64 is 0.9999999999999999 < 1: a timer reset to 0 fires on the 16th frame (A.6)."""
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config, vehicles=2))
+    env.reset(5)
+    st = env.get_state()
+    # vehicle 1 is stuck behind a slow leader on lane 1, lane 0 and 2 are free -> MOBIL wants out
+    st["x"][:] = [0.0, 200.0, 240.0]
+    st["y"][:] = [12.0, 4.0, 4.0]
+    st["lane"][:] = st["target_lane"][:] = [3, 1, 1]
+    st["speed"][:] = [0.0, 25.0, 18.0]
+    st["target_speed"][:] = [0.0, 30.0, 18.0]
+    st["timer"][:] = [0.0, 0.0, 0.0]
+    st["heading"][:] = 0.0
+    env.set_state(st)
+    env.step([0.0, 0.0])
+    assert env.get_state()["target_lane"][1] == 1  # 15 frames: 1.0 < timer never true
+    env.step([0.0, 0.0])
+    # fired on the first frame of the second step; lane 2 (the later candidate) overwrites lane 0
+    assert env.get_state()["target_lane"][1] == 2
+
+
+def test_sim_collision_sets_crashed_and_terminates(highway_config):
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config, vehicles=1))
+    env.reset(5)
+    st = env.get_state()
+    st["x"][:] = [100.0, 108.0]
+    st["y"][:] = [0.0, 0.0]
+    st["lane"][:] = st["target_lane"][:] = [0, 0]
+    st["speed"][:] = [30.0, 0.0]
+    st["target_speed"][:] = [30.0, 0.0]
+    st["heading"][:] = 0.0
+    env.set_state(st)
+    r, term, trunc = env.step([1.0, 0.0])
+    s1 = env.get_state()
+    assert term and s1["crashed"][0] == 1 and s1["crashed"][1] == 1
+    assert abs(r - (0.4 * min(max((s1["speed"][0] - 20) / 10, 0), 1) - 1 + 1) / 1.5) < 1e-9
+
+
+def test_sim_spawn_layout(highway_config):
+    """A.3: ego first and rear-most at speed 25, others 21..24 m/s on lane centres, x increasing in list order."""
+    env = oh.OracleEnv(highway_config)
+    for seed in range(20):
+        env.reset(seed, env_id=seed * 7, episode=seed % 3)
+        st = env.get_state()
+        assert st["speed"][0] == 25.0 and np.all((st["speed"][1:] >= 21) & (st["speed"][1:] < 24))
+        assert np.all(np.diff(st["x"]) > 0) and 3 * 44.88 * 0.9 < st["x"][0] - 0 < 4.1 * 44.89
+        assert np.all(st["y"] == 4.0 * st["lane"]) and st["lane"].min() >= 0 and st["lane"].max() <= 3
+        gaps = np.diff(st["x"])  # others: offset = 0.5 (12 + v) exp(-0.5) U(0.9, 1.1)
+        off = 0.5 * (12 + st["speed"][1:]) * math.exp(-0.5)
+        assert np.all(gaps >= 0.9 * off - 1e-9) and np.all(gaps <= 1.1 * off + 1e-9)
+        assert np.all((st["delta"][1:] >= 3.5) & (st["delta"][1:] < 4.5))
+        np.testing.assert_allclose(st["timer"][1:], ((st["x"][1:] + st["y"][1:]) * math.pi) % 1.0, atol=1e-12)
+
+
+def test_sim_observation_sorted_and_shuffled(highway_config):
+    env = oh.OracleEnv(highway_config)
+    env.reset(11)
+    st = env.get_state()
+    obs, rows = env.observe(with_rows=True)
+    assert obs.shape == (15, 4) and rows[0] == 0
+    # ego row absolute and clipped; others relative, sorted by |dx| among those within 200 m and not > 10 m behind
+    assert obs[0, 0] == 1.0 and abs(obs[0, 1] - st["y"][0] / 100) < 1e-7 and abs(obs[0, 2] - 25 / 30) < 1e-7
+    dx = st["x"][1:] - st["x"][0]
+    near = 1 + np.argsort(np.abs(dx), kind="stable")[:14]
+    assert list(rows[1:]) == list(near)
+    np.testing.assert_allclose(obs[1:, 0], np.clip((st["x"][near] - st["x"][0]) / 100, -1, 1), atol=1e-7)
+    np.testing.assert_allclose(obs[1:, 2], (st["speed"][near] - 25.0) / 30, atol=1e-7)
+    # shuffled: first N-1 candidates in LIST order (not the nearest), scattered by the permutation
+    c = copy.deepcopy(highway_config)
+    c["observation"]["order"] = "shuffled"
+    env2 = oh.OracleEnv(c)
+    env2.set_state(st)
+    perm = np.random.default_rng(0).permutation(14).astype(np.int32)
+    obs2, rows2 = env2.observe(perm=perm, with_rows=True)
+    assert rows2[0] == 0
+    for k in range(14):
+        assert rows2[1 + perm[k]] == 1 + k
+    p = oh.shuffle_perm(3, 5, 2, 14)
+    assert sorted(p) == list(range(14))

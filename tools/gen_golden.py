@@ -1,0 +1,240 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference code from /root/reference.
+
+Run once in the build container (the reference tree does not exist on the GPU box):
+
+    python tools/gen_golden.py
+
+* ``embed_*.npz``: outputs of the reference's RotaryEmbedWrapper / DistanceEmbedWrapper
+  (``experiments/rope_embed.py``, ``experiments/dist_embed.py``) on seeded observations.  The
+  wrappers import ``gymnasium``, which is absent here, so a ~25-line stand-in providing only
+  ``ObservationWrapper``/``Env``/``spaces.Box`` is put on ``sys.modules`` first; the wrapper code
+  itself is the reference's.  RankEmbedWrapper.observation() raises at HEAD, so its
+  fixture holds ``tanh(table).detach()`` computed from the reference-constructed table.
+* ``ppo_*.npz``: ``ppo/agent.py`` imported as is: initial parameters for a seed, one evaluate +
+  loss + backward + clip + Adam step on a seeded minibatch, GAE on a seeded trajectory, and a
+  full ``PPOAgent.update`` (all metrics + final parameters).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def install_gymnasium_stub():
+    gym = types.ModuleType("gymnasium")
+    spaces = types.ModuleType("gymnasium.spaces")
+
+    class Box:
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            shape = tuple(shape if shape is not None else np.shape(low))
+            self.shape, self.dtype = shape, np.dtype(dtype)
+            self.low = np.broadcast_to(np.asarray(low, dtype=dtype), shape).copy()
+            self.high = np.broadcast_to(np.asarray(high, dtype=dtype), shape).copy()
+
+    class Env:
+        def __init__(self):
+            pass
+
+    class Wrapper(Env):
+        def __init__(self, env):
+            self.env = env
+            self.observation_space = env.observation_space
+            self.action_space = getattr(env, "action_space", None)
+
+    class ObservationWrapper(Wrapper):
+        pass
+
+    spaces.Box = Box
+    gym.spaces, gym.Env, gym.Wrapper, gym.ObservationWrapper = spaces, Env, Wrapper, ObservationWrapper
+    sys.modules["gymnasium"] = gym
+    sys.modules["gymnasium.spaces"] = spaces
+    return gym
+
+
+def dummy_env(gym, shape):
+    e = gym.Env()
+    e.observation_space = gym.spaces.Box(-np.inf, np.inf, shape, np.float32)
+    e.action_space = gym.spaces.Box(-1.0, 1.0, (2,), np.float32)
+    return e
+
+
+def highway_like_obs(rng, N, F, n_real):
+    """Observation with the statistics of the normalised Kinematics table."""
+    obs = np.zeros((N, F), dtype=np.float32)
+    obs[0, 0] = 1.0
+    obs[0, 1] = rng.choice([0.0, 0.04, 0.08, 0.12])
+    obs[0, 2:4] = [rng.uniform(0.6, 1.0), rng.uniform(-0.05, 0.05)]
+    for r in range(1, n_real):
+        obs[r, 0] = rng.uniform(-0.1, 1.0)
+        obs[r, 1] = rng.uniform(-0.12, 0.12)
+        obs[r, 2] = rng.uniform(-0.3, 0.1)
+        obs[r, 3] = rng.uniform(-0.05, 0.05)
+        if F > 4:
+            obs[r, 4:] = rng.uniform(-1, 1, F - 4)
+    perm = rng.permutation(N - 1)
+    obs[1:] = obs[1:][perm]
+    return obs
+
+
+def gen_embed(gym):
+    sys.path.insert(0, REF)
+    from experiments.dist_embed import DistanceEmbedWrapper
+    from experiments.rank_embed import RankEmbedWrapper
+    from experiments.rope_embed import RotaryEmbedWrapper
+
+    rng = np.random.default_rng(20261018)
+    cases = {}
+    # RoPE: the make_env-reachable shape (N=15, F=4, rotate 4), generic shapes incl. rotate_dim 16
+    for name, (N, F, rd, md) in {"rope_n15_f4_r4": (15, 4, 4, 100.0), "rope_n15_f4_r2": (15, 4, 2, 100.0),
+                                 "rope_n30_f7_r6": (30, 7, 6, 100.0), "rope_n5_f16_r16": (5, 16, 16, 10.0),
+                                 "rope_n8_f20_r16": (8, 20, 16, 1.0)}.items():
+        w = RotaryEmbedWrapper(dummy_env(gym, (N, F)), rotate_dim=rd, max_dist=md)
+        B = 16
+        if F in (4, 7):
+            obs = np.stack([highway_like_obs(rng, N, F, int(rng.integers(1, N + 1))) for _ in range(B)])
+        else:
+            obs = rng.standard_normal((B, N, F)).astype(np.float32)
+        out = np.stack([w.observation(o) for o in obs])
+        dn = rng.random((B, N)).astype(np.float32)
+        out_dn = np.stack([w._apply_rope(o.copy(), d) for o, d in zip(obs, dn)])
+        cases[name] = dict(obs=obs, out=out, dist_norm=dn, out_dist_norm=out_dn, inv_freq=w.inv_freq,
+                           rotate_dim=rd, max_dist=md)
+    for name, (N, F, d, md, eu) in {"dist_n15_f4_d4": (15, 4, 4, 100.0, True), "dist_n15_f4_d16": (15, 4, 16, 100.0, True),
+                                    "dist_n30_f4_d8": (30, 4, 8, 100.0, True), "dist_n15_f4_d8_abs": (15, 4, 8, 100.0, False),
+                                    "dist_n6_f5_d6_md1": (6, 5, 6, 1.0, True)}.items():
+        w = DistanceEmbedWrapper(dummy_env(gym, (N, F)), d_embed=d, max_dist=md, use_euclidean=eu)
+        B = 16
+        if md == 100.0:
+            obs = np.stack([highway_like_obs(rng, N, F, int(rng.integers(1, N + 1))) for _ in range(B)])
+        else:
+            obs = rng.standard_normal((B, N, F)).astype(np.float32)
+        out = np.stack([w.observation(o) for o in obs])
+        cases[name] = dict(obs=obs, out=out, freqs=w._freqs_np, d_embed=d, max_dist=md, use_euclidean=int(eu))
+    for name, (N, F, d, seed) in {"rank_n15_f4_d4": (15, 4, 4, 42), "rank_n30_f4_d16": (30, 4, 16, 1042)}.items():
+        torch.manual_seed(seed)
+        w = RankEmbedWrapper(dummy_env(gym, (N, F)), d_embed=d)
+        tag = torch.tanh(w.table.weight).detach().numpy()  # intended value of rank_embed.py:48
+        obs = np.stack([highway_like_obs(rng, N, F, int(rng.integers(1, N + 1))) for _ in range(4)])
+        out = np.concatenate([obs, np.broadcast_to(tag, (4,) + tag.shape)], axis=-1).astype(np.float32)
+        cases[name] = dict(obs=obs, out=out, tag=tag, d_embed=d, seed=seed)
+    for name, arrs in cases.items():
+        np.savez_compressed(os.path.join(OUT, f"embed_{name}.npz"), **arrs)
+    print("embed fixtures:", sorted(cases))
+
+
+def flat_params(ac):
+    return np.concatenate([p.detach().cpu().numpy().reshape(-1) for p in ac.parameters()])
+
+
+def gen_ppo():
+    sys.path.insert(0, REF)
+    from ppo.agent import PPOAgent
+    import torch.nn as nn
+    import torch.nn.functional as Fn
+
+    torch.set_num_threads(1)
+    for name, (S, A, H, B, seed) in {"s60_h256_b64": (60, 2, 256, 64, 42), "s20_h32_b17": (20, 2, 32, 17, 7),
+                                     "s300_h64_b256": (300, 2, 64, 256, 3)}.items():
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        agent = PPOAgent(S, A, lr=3e-4, hidden_dim=H, batch_size=B, epochs=2)
+        ac = agent.actor_critic
+        names = [n for n, _ in ac.named_parameters()]
+        p0 = flat_params(ac)
+        g = torch.Generator().manual_seed(seed + 1)
+        states = torch.randn(B, S, generator=g) * 0.5
+        mean, std, value = ac.forward(states)
+        noise = torch.randn(B, A, generator=g)
+        z = (mean + std * noise).detach()
+        z[0, 0] = 4.0  # saturated tanh exercises the 1e-6 guard of the log-prob correction
+        logp, v, ent = ac.evaluate(states, torch.tanh(z), z)
+        old_logp = (logp + 0.3 * torch.randn(B, generator=g)).detach()  # spread ratios across the clip range
+        adv = torch.randn(B, generator=g)
+        ret = torch.randn(B, generator=g)
+        # one minibatch of PPOAgent.update (agent.py:218-252)
+        new_logp, sv, entropy = ac.evaluate(states, torch.tanh(z), z)
+        ratios = torch.exp(new_logp - old_logp)
+        surr1 = ratios * adv
+        surr2 = torch.clamp(ratios, 1 - agent.eps_clip, 1 + agent.eps_clip) * adv
+        actor_loss = -torch.min(surr1, surr2).mean()
+        critic_loss = Fn.mse_loss(sv.squeeze(-1), ret)
+        loss = actor_loss + agent.value_coef * critic_loss - agent.entropy_coef * entropy.mean()
+        agent.optimizer.zero_grad()
+        loss.backward()
+        grads = np.concatenate([p.grad.detach().numpy().reshape(-1) for p in ac.parameters()])
+        total_norm = float(nn.utils.clip_grad_norm_(ac.parameters(), agent.max_grad_norm))
+        agent.optimizer.step()
+        p1 = flat_params(ac)
+        # a second step (bias correction with step = 2)
+        new_logp, sv, entropy = ac.evaluate(states, torch.tanh(z), z)
+        ratios2 = torch.exp(new_logp - old_logp)
+        loss2 = (-torch.min(ratios2 * adv, torch.clamp(ratios2, 0.8, 1.2) * adv).mean()
+                 + 0.5 * Fn.mse_loss(sv.squeeze(-1), ret) - 0.005 * entropy.mean())
+        agent.optimizer.zero_grad()
+        loss2.backward()
+        nn.utils.clip_grad_norm_(ac.parameters(), agent.max_grad_norm)
+        agent.optimizer.step()
+        p2 = flat_params(ac)
+        kl = float(((ratios - 1) - (new_logp * 0 + torch.log(ratios))).mean())
+        np.savez_compressed(
+            os.path.join(OUT, f"ppo_step_{name}.npz"), names=np.array(names), params0=p0, states=states.numpy(),
+            mean=mean.detach().numpy(), value=value.detach().numpy(), pre_tanh=z.numpy(), logp=logp.detach().numpy(),
+            entropy=ent.detach().numpy(), old_logp=old_logp.numpy(), adv=adv.numpy(), ret=ret.numpy(),
+            loss=float(loss), actor_loss=float(actor_loss), critic_loss=float(critic_loss),
+            clip_fraction=float((torch.abs(ratios - 1) > agent.eps_clip).float().mean()), approx_kl=kl,
+            grads=grads, total_norm=total_norm, params1=p1, params2=p2, loss2=float(loss2),
+            dims=np.array([S, A, H, B, seed]))
+    # GAE (agent.py:126-138) on seeded trajectories with episode boundaries
+    from ppo.agent import PPOMemory
+    rng = np.random.default_rng(5)
+    for name, T in {"t50": 50, "t2048": 2048}.items():
+        mem = PPOMemory()
+        mem.rewards = [float(x) for x in rng.random(T)]
+        mem.values = [np.float32(x) for x in rng.standard_normal(T)]
+        mem.dones = [bool(x) for x in (rng.random(T) < 0.05)]
+        last_value = 0.37
+        adv, ret = mem.compute_advantages(0.99, 0.95, last_value)
+        np.savez_compressed(os.path.join(OUT, f"ppo_gae_{name}.npz"), reward=np.array(mem.rewards, dtype=np.float64),
+                            value=np.array(mem.values, dtype=np.float32), done=np.array(mem.dones),
+                            last_value=last_value, adv=adv, ret=ret)
+    # a full update(): 2048 stored transitions, bs 64, 2 epochs (the reference's loop shape)
+    for name, (S, H, n, bs, epochs, seed) in {"s60_h256_n2048": (60, 256, 2048, 64, 2, 42),
+                                              "s12_h16_n100": (12, 16, 100, 32, 3, 9)}.items():
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        agent = PPOAgent(S, 2, lr=3e-4, hidden_dim=H, batch_size=bs, epochs=epochs)
+        p0 = flat_params(agent.actor_critic)
+        rng = np.random.default_rng(seed)
+        st = (rng.standard_normal((n, S)) * 0.5).astype(np.float32)
+        rew = rng.random(n)
+        done = rng.random(n) < 0.03
+        stored = {k: [] for k in ("action", "pre_tanh", "logp", "value")}
+        for t in range(n):
+            a, z, lp, v = agent.select_action(st[t])
+            agent.memory.store(st[t], a, z, float(rew[t]), st[t], lp, bool(done[t]), v)
+            for k, x in zip(("action", "pre_tanh", "logp", "value"), (a, z, lp, v)):
+                stored[k].append(x)
+        np.random.seed(seed + 100)  # fixes the minibatch permutation of get_batches()
+        metrics = agent.update(last_value=0.25)
+        np.savez_compressed(
+            os.path.join(OUT, f"ppo_update_{name}.npz"), params0=p0, params1=flat_params(agent.actor_critic),
+            states=st, reward=rew, done=done, action=np.array(stored["action"], dtype=np.float32),
+            pre_tanh=np.array(stored["pre_tanh"], dtype=np.float32), logp=np.array(stored["logp"], dtype=np.float32),
+            value=np.array(stored["value"], dtype=np.float32), last_value=0.25,
+            metric_names=np.array(list(metrics)), metric_values=np.array([metrics[k] for k in metrics]),
+            dims=np.array([S, 2, H, n, bs, epochs, seed + 100]))
+    print("ppo fixtures written")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gym = install_gymnasium_stub()
+    gen_embed(gym)
+    gen_ppo()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
