@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- policy env-steps/s of the lock-step highway-v0 + PPO hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E]
+
+Workload (BASELINE.json configs[1]): shuffled Kinematics observation + RoPE, hidden_dim 256, 4096 lock-step envs
+per GPU, V = 51 vehicles, N = 15 rows, F = 4.  RoPE rotates rotate_dim = 4 features: the d_embed 16 of the config
+string is rejected by the reference at HEAD for F = 4, 4 is the only width `make_env` accepts.
+
+One "step" = one policy step of every env: the policy kernel chain (MLP forward + tanh-Gaussian sampling,
+`hrp_ppo_act`) followed by the fused env kernel (`hrp_env_step`: 15 simulation frames, reward / termination,
+in-kernel respawn, shuffled observation, RoPE).  `value` is env-steps/s with everything resident in HBM; `e2e`
+is the same step through the host-buffer API (observations and actions cross PCIe every step, as in the
+reference's CPU loop); `roofline` is the env kernel against the measured HBM peak; `cpu_baseline` is the CPU
+oracle (C restatement, OpenMP over envs + torch CPU policy) timed on this box's host cores.
+
+Under torchrun each rank owns its own 4096 envs (weak scaling); the only collective on the path is the PPO
+gradient all-reduce inside `ppo_samples_per_s` (reported beside the headline).
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "policy env-steps/s (4096 envs/GPU)"
+UNIT = "env-steps/s"
+OVERRIDE = {"observation": {"order": "shuffled"}}
+KERNELS_PER_ACT = 6   # 4 x sgemm (trunk 2, actor 1, critic 1) + heads + act
+KERNELS_PER_ENV_STEP = 1
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=400)
+    p.add_argument("--warmup", type=int, default=40)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    p.add_argument("--hidden", type=int, default=256)
+    p.add_argument("--rollout", type=int, default=32, help="T of the PPO iteration measured beside the headline")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-ppo", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    return p.parse_args()
+
+
+def workload_config(args):
+    return {"workload": "highway-v0 shuffled obs + RoPE(rotate_dim 4; d_embed 16 invalid at F=4, SURVEY F4), "
+                        f"hidden_dim {args.hidden}, {args.envs} lock-step envs/GPU, V=51, N=15, F=4, 15 substeps/step",
+            "envs_per_gpu": args.envs, "hidden_dim": args.hidden,
+            "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)"}
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons of one GPU while the timed region runs (NVML, 20 ms period)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes_per_env_step(V=51, N=15, Fout=4):
+    """state read once + written once per POLICY step (the 15 substeps stay on chip).
+    Per vehicle: read x(8) timer(8) y,heading,speed,target_speed,delta,impx,impy (7x4) flags(4) = 48 B, write
+    the same minus the two per-episode constants (target_speed, delta) = 40 B; per env: action 8, time 8+8,
+    episode/draw counters 16, obs 4 N Fout, reward 4, flags 2."""
+    return 88 * V + 4 * N * Fout + 46
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_policy_env_steps(args, seconds, n_envs, steps=None, warmup=1):
+    """Oracle arm: C restatement of highway-v0 (OpenMP over envs, all host cores) + torch CPU MLP policy."""
+    import numpy as np
+    import torch
+
+    from highway_rope_ppo_b200.config.base_config import HIGHWAY_CONFIG
+    from oracle import embed as oe
+    from oracle import highway as oh
+    from oracle import ppo_ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = copy.deepcopy(HIGHWAY_CONFIG)
+    cfg["observation"]["order"] = "shuffled"
+    vec = oh.OracleVecEnv(cfg, n_envs, seed=42, nthreads=cores)
+    S, A, H = 60, 2, args.hidden
+    torch.manual_seed(0)
+    import torch.nn as nn
+
+    flat = torch.cat([torch.zeros(A)] + [p.detach().reshape(-1) for layer in
+                                         (nn.Linear(S, H), nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, A),
+                                          nn.Linear(H, H), nn.Linear(H, 1)) for p in layer.parameters()])
+    inv = oe.rope_inv_freq(4, 100.0)
+    obs = np.zeros((n_envs, 15, 4), dtype=np.float32)
+
+    def one_step(obs):
+        # RoPE wrapper (vectorised numpy restatement of rope_embed.py:64-74) + policy forward + env step
+        rel = obs[:, :, :2] - obs[:, :1, :2]
+        dn = np.clip(np.linalg.norm(rel, axis=-1) / 100.0, 0.0, 1.0).astype(np.float32)
+        theta = (2 * np.pi * dn[..., None] * inv[None, None, :]).astype(np.float32)
+        s, c = np.sin(theta), np.cos(theta)
+        pair = obs.reshape(n_envs, 15, 2, 2)
+        rot = np.stack([pair[..., 0] * c - pair[..., 1] * s, pair[..., 0] * s + pair[..., 1] * c], axis=-1)
+        x = torch.from_numpy(rot.reshape(n_envs, S).astype(np.float32))
+        with torch.no_grad():
+            mean, log_std, value = ppo_ref.forward(flat, x, S, A, H)
+            act = torch.tanh(mean + log_std.exp() * torch.randn_like(mean))
+        return vec.step(act.numpy())[0]
+
+    t_env = 0.0
+    for _ in range(warmup):
+        obs = one_step(obs)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        obs = one_step(obs)
+        n += 1
+        el = time.perf_counter() - t0
+        if steps is not None:
+            if n >= steps:
+                break
+        elif el >= seconds and n >= 3:
+            break
+    return {"value": n * n_envs / el, "steps": n, "envs": n_envs, "seconds": el, "cores": cores}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference path on the host cores.  The simulator the reference calls
+    (highway-env 1.10.1) is a third-party package absent from this image, so this arm times the oracle's
+    C restatement of it (kind "port") with every host thread, plus a torch CPU policy forward."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 150.0  # seconds for the whole --steps/--warmup run
+    probe = cpu_policy_env_steps(args, 2.0, 256, steps=2, warmup=1)
+    per_env_step = 1.0 / probe["value"]
+    total = max(1, args.steps + args.warmup)
+    n_envs = int(min(args.envs, max(64, budget / (total * per_env_step))))
+    res = cpu_policy_env_steps(args, 0.0, n_envs, steps=args.steps, warmup=max(1, args.warmup))
+    cfg = workload_config(args)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / res["steps"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg, "gpu_launches": 0,
+            "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                             "sample": f"{res['envs']} envs x {res['steps']} policy steps, oracle C restatement "
+                                       "(OpenMP) + torch CPU policy forward"},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from highway_rope_ppo_b200 import _lib
+    from highway_rope_ppo_b200.config.base_config import HIGHWAY_CONFIG
+    from highway_rope_ppo_b200.experiments.config import Condition
+    from highway_rope_ppo_b200.experiments.wrappers import make_vec_env
+    from highway_rope_ppo_b200.ppo.agent import PPOAgent
+    from highway_rope_ppo_b200.training.routine import rollout_and_update
+    from highway_rope_ppo_b200.utils.reproducibility import set_random_seeds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_device()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    E, S, A, H = args.envs, 60, 2, args.hidden
+    set_random_seeds(42)
+    env = make_vec_env(Condition.SHUFFLED_ROPE, HIGHWAY_CONFIG, 4, OVERRIDE, num_envs=E, device=dev, seed=42,
+                       env_id_base=rank * E)
+    agent = PPOAgent(S, A, lr=3e-4, hidden_dim=H, batch_size=4096, epochs=8, device=dev)
+    obs = env.reset(42).view(E, S)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {"action": torch.empty((E, A), device=dev), "pre_tanh": torch.empty((E, A), device=dev),
+           "log_prob": torch.empty(E, device=dev), "value": torch.empty(E, device=dev)}
+
+    def policy_env_step():
+        agent.act(obs, out=out)
+        env.step(out["action"])  # writes env.obs, which `obs` views
+
+    for _ in range(args.warmup):
+        policy_env_step()
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()                       # evict the (L2-sized) working set between timed iterations
+        ev[k][0].record()
+        agent.act(obs, out=out)
+        ev[k][1].record()
+        env.step(out["action"])
+        ev[k][2].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.result()
+    act_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
+    env_ms = sum(e[1].elapsed_time(e[2]) for e in ev)
+    total_ms = act_ms + env_ms
+    t = torch.tensor([total_ms, env_ms, act_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, env_ms, act_ms = (float(x) for x in t.cpu())
+    value = world * E * K / (total_ms * 1e-3)
+
+    # back-to-back (no flush, one event pair around all K steps): what a training loop actually sees
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        policy_env_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    warm_value = world * E * K / (float(t.cpu()) * 1e-3)
+
+    # env kernel alone, random actions resident in HBM (the "env-step-only" sweep point of BASELINE configs[4])
+    acts = torch.rand((E, 2), device=dev) * 2 - 1
+    barrier()
+    e0.record()
+    for k in range(K):
+        env.step(acts)
+    e1.record()
+    barrier()
+    env_only = world * E * K / (e0.elapsed_time(e1) * 1e-3)
+
+    # roofline of the dominant kernel (the fused env step), from the flushed per-step events
+    peak, peak_src = measured_peak()
+    bytes_per_launch = algorithmic_bytes_per_env_step() * E
+    env_kernel_s = env_ms * 1e-3 / K
+    achieved = bytes_per_launch / env_kernel_s / 1e9
+    roofline = {"bound": "hbm", "kernel": "hrp_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_us": env_kernel_s * 1e6,
+                "share_of_step": env_ms / total_ms,
+                "note": "compute/latency-bound kernel (15 fused substeps per launch); see DESIGN.md"}
+
+    # e2e: the same step through the host-buffer API (pinned host obs -> policy -> host actions -> env -> host obs)
+    e2e = None
+    if not args.no_e2e:
+        Ke = min(K, 200)
+        obs_h = torch.zeros((E, 15, 4), dtype=torch.float32).pin_memory()
+        act_h = torch.zeros((E, 2), dtype=torch.float32).pin_memory()
+        rew_h = np.zeros(E, dtype=np.float32)
+        te_h, tr_h = np.zeros(E, dtype=np.uint8), np.zeros(E, dtype=np.uint8)
+        obs_np, act_np = obs_h.numpy(), act_h.numpy()
+        env.reset_host(42, obs_np)
+        obs_d = torch.empty((E, S), device=dev)
+
+        def host_step():
+            obs_d.copy_(obs_h.view(E, S), non_blocking=True)          # H2D observation
+            agent.act(obs_d, out=out)
+            act_h.copy_(out["action"], non_blocking=True)             # D2H action
+            torch.cuda.current_stream().synchronize()
+            env.step_host(act_np, obs_np, rew_h, te_h, tr_h)          # H2D action, kernel, D2H obs/reward/flags
+
+        for _ in range(5):
+            host_step()
+        barrier()
+        e0.record()
+        w0 = time.perf_counter()
+        for _ in range(Ke):
+            host_step()
+        e1.record()
+        barrier()
+        w = time.perf_counter() - w0
+        t = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, w)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * E * Ke / float(t.cpu()), "unit": UNIT,
+               "h2d_bytes_per_step": E * S * 4 + E * 2 * 4, "d2h_bytes_per_step": E * 2 * 4 + E * S * 4 + E * 4 + 2 * E,
+               "steps": Ke, "api": "PPOAgent.act on a pinned-host observation + hrp_env_step_host"}
+
+    # PPO iteration (rollout of T steps + update: 8 epochs of 4096-sample minibatches, gradient all-reduce if N > 1)
+    ppo = None
+    if not args.no_ppo:
+        T = args.rollout
+        o = env.reset(42)
+        _, o = rollout_and_update(env, agent, T, obs=o)  # warm-up
+        barrier()
+        e0.record()
+        iters = 2
+        for _ in range(iters):
+            m, o = rollout_and_update(env, agent, T, obs=o)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ppo = {"value": world * E * T * iters / (float(t.cpu()) * 1e-3), "unit": "samples/s", "rollout_T": T,
+               "epochs": 8, "minibatch": 4096, "last_loss": m["loss"],
+               "definition": "T policy+env steps then PPOAgent.update (GAE, 8 epochs, clip+Adam), amortised"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_policy_env_steps(args, args.cpu_seconds, 1024)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"{r['envs']} envs x {r['steps']} policy steps ({r['seconds']:.1f} s), oracle C restatement of "
+                         "highway-env 1.10.1 (OpenMP over envs) + torch CPU policy forward"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (x, lane-change timer f64)", "data": "synthetic", "config": workload_config(args),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": K * (KERNELS_PER_ACT + KERNELS_PER_ENV_STEP),
+                "roofline": roofline, "cpu_baseline": cpu,
+                "value_back_to_back_l2_warm": warm_value, "env_only_steps_per_s": env_only,
+                "policy_ms_per_step": act_ms / K, "env_ms_per_step": env_ms / K, "ppo_samples_per_s": ppo,
+                "wall_s_timed_region": wall}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,7 +84,7 @@ SIGNATURES: Dict[str, Any] = {
     "hrp_ppo_destroy": (C.c_int, [_vp]),
     "hrp_ppo_forward": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "hrp_ppo_act": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "hrp_gae": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp, _vp]),
+    "hrp_gae": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _vp, _vp, _vp]),
     "hrp_adv_stats": (C.c_int, [_vp, _i64, _vp, _vp]),
     "hrp_adv_normalize": (C.c_int, [_vp, _i64, _vp, _vp]),
     "hrp_ppo_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp,

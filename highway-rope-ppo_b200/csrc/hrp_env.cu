@@ -70,13 +70,11 @@ __device__ __forceinline__ int slot_rear(ull mask, int p)
 }
 __device__ __forceinline__ int closest_lane(float y, int lanes)
 {
-    float best = fabsf(y);
-    int arg = 0;
-    for (int i = 1; i < lanes; ++i) {
-        float d = fabsf(y - kLaneW * i);
-        if (d < best) { best = d; arg = i; }
-    }
-    return arg;
+    // argmin_i |y - 4 i| with the first minimum winning a tie (RoadNetwork.get_closest_lane_index):
+    // ceil(y / 4 - 1/2), clamped.  y / 4 and the subtraction of 0.5 are exact in binary floating point
+    // wherever the result can change the answer.
+    int i = (int)ceilf(y * 0.25f - 0.5f);
+    return max(0, min(lanes - 1, i));
 }
 
 // IDMVehicle.desired_gap: e follows f
@@ -144,6 +142,16 @@ __device__ int collide_pair(const WarpS &S, int i, int j, float dt, float &tx, f
     float uax = S.ch[i], uay = S.sh[i], ubx = S.ch[j], uby = S.sh[j];
     float cax = S.xr[i], cay = S.y[i], cbx = S.xr[j], cby = S.y[j];
     float rdx = (S.v[i] * uax - S.v[j] * ubx) * dt, rdy = (S.v[i] * uay - S.v[j] * uby) * dt;
+    {
+        // cheap exit for the common near miss (vehicles side by side on adjacent lanes): if a's lateral
+        // axis separates the rectangles now AND after the displacement, both flags end up false whatever
+        // the other axes say, which is the reference's "no contact" result
+        float nx = -uay, ny = uax;
+        float pa = cax * nx + cay * ny, pb = cbx * nx + cby * ny;
+        float rb = 2.5f * fabsf(ubx * nx + uby * ny) + fabsf(-uby * nx + ubx * ny);
+        float gap = fabsf(pa - pb) - (1.f + rb);
+        if (gap > 0.f && gap - fabsf(nx * rdx + ny * rdy) > 0.f) return 0;
+    }
     bool inter = true, will = true;
     float mind = INFINITY, ax = 0.f, ay = 0.f;
     float dneg[2], nnx[2], nny[2], ddn[2];
@@ -622,10 +630,12 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
         // ControlledVehicle.steering_control(target_lane) -> tan(beta) without leaving the tangent
         float lat = w.y - kLaneW * w.tlane;
         float lsc = -(1.f / 0.6f) * lat;
-        float hc = asinf(clipf(lsc / nzf(w.v), -1.f, 1.f));
+        float rv = 1.f / nzf(w.v);
+        // clip(asin(clip(c, -1, 1)), -pi/4, pi/4) == asin(clip(c, -sin(pi/4), sin(pi/4))): asin is monotone
+        float hc = asinf(clipf(lsc * rv, -0.70710678118654752f, 0.70710678118654752f));
         float href = clipf(hc, -kPi / 4.f, kPi / 4.f);
         float hrc = 5.f * wrap_to_pi(href - w.h);
-        float ss = clipf(2.5f / nzf(w.v) * hrc, -1.f, 1.f);  // sin(slip)
+        float ss = clipf(2.5f * rv * hrc, -1.f, 1.f);  // sin(slip)
         float tslip = ss * rsqrtf(fmaxf(1.f - ss * ss, 0.f));  // tan(slip); +-inf at |ss| == 1
         w.tb = clipf(tslip, -kTanBetaMax, kTanBetaMax);  // tan(beta) = clip(2 tan slip, +-tan(pi/3)) / 2
         if (k > 0) {
@@ -735,7 +745,7 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
 }
 
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * HRP_WARPS_PER_CTA)
+__global__ void __launch_bounds__(32 * HRP_WARPS_PER_CTA, HRP_STEP_CTAS_PER_SM)
 hrp_step_kernel(const EnvDev P, const float *__restrict__ actions, float *__restrict__ obs,
                 float *__restrict__ reward, uint8_t *__restrict__ term, uint8_t *__restrict__ trunc,
                 const int32_t *__restrict__ perm, int32_t *__restrict__ row_vehicle)

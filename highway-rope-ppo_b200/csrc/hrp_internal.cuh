@@ -7,6 +7,7 @@
 
 #define HRP_VS 64            // vehicle slots per env in every SoA array (two per lane)
 #define HRP_WARPS_PER_CTA 4  // envs per CTA (one warp each)
+#define HRP_STEP_CTAS_PER_SM 7  // 28 envs per SM: 4096 envs fill 148 SMs in one wave (<= 72 registers)
 #define HRP_FULL 0xffffffffu
 
 typedef unsigned long long ull;

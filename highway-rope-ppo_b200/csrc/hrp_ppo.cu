@@ -552,11 +552,11 @@ int hrp_ppo_act(hrp_ppo *h, const float *params, const float *states, const floa
 }
 
 int hrp_gae(const float *reward, const float *value, const uint8_t *done, const float *last_value, int64_t T,
-            int64_t E, float gamma, float lam, float *adv, float *ret, void *stream)
+            int64_t E, double gamma, double lam, float *adv, float *ret, void *stream)
 {
     if (!reward || !value || !done || !adv || !ret || T < 1 || E < 1) { hrp_set_error("hrp_gae: bad arguments"); return -1; }
     gae_kernel<<<(unsigned)((E + 127) / 128), 128, 0, (cudaStream_t)stream>>>(reward, value, done, last_value, T, E,
-                                                                            (double)gamma, (double)lam, adv, ret);
+                                                                            gamma, lam, adv, ret);
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }

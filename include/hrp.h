@@ -173,7 +173,7 @@ int hrp_ppo_act(hrp_ppo *h, const float *params_dev, const float *states_dev, co
 /* PPOMemory.compute_advantages (agent.py:126-138) over [T,E] (time-major), reverse scan.
  * last_value_dev[E]; done as uint8.  Outputs advantages[T,E] (float32), returns[T,E]. */
 int hrp_gae(const float *reward_dev, const float *value_dev, const uint8_t *done_dev,
-            const float *last_value_dev, int64_t T, int64_t E, float gamma, float lam,
+            const float *last_value_dev, int64_t T, int64_t E, double gamma, double lam,
             float *adv_dev, float *ret_dev, void *stream);
 /* advantage normalisation (agent.py:204): (a-mean)/(std_unbiased+1e-8), in place.
  * hrp_adv_stats writes (sum, sum of squares, n) of the local shard to stats_dev[0..2] (fp64;

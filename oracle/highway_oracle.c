@@ -183,8 +183,12 @@ static double idm_acceleration(const veh_t *self, const veh_t *ego, const veh_t 
 }
 
 /* ---- ControlledVehicle.steering_control / speed_control (A.5) ------------ */
-static double steering_control(const veh_t *v, int target_lane)
+static double steering_control(hw_env *e, const veh_t *v, int target_lane)
 {
+    mg(e, fabs(v->speed) - 1e-2); mg(e, v->speed); /* not_zero(speed): eps switch and sign */
+    /* test aid: below 0.5 m/s the two divisions by the speed amplify a 1e-6 rounding of y by > 1e3
+     * (the controller is ill-conditioned as v -> 0): such steps are reported as marginal */
+    if (fabs(v->speed) < 0.5) mg(e, 0.0);
     double lat = v->y - LANE_WIDTH * target_lane;
     double lateral_speed_command = -(1.0 / TAU_LATERAL) * lat;
     double heading_command = asin(clipd(lateral_speed_command / not_zero(v->speed), -1, 1));
@@ -264,7 +268,7 @@ static void idm_act(hw_env *e, int self)
     veh_t *me = &e->v[self];
     if (me->crashed) return;
     change_lane_policy(e, self);
-    double steer = steering_control(me, me->target_lane);
+    double steer = steering_control(e, me, me->target_lane);
     steer = clipd(steer, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
     int f, r;
     neighbours(e, self, me->lane, &f, &r);
@@ -298,7 +302,7 @@ static void controlled_act(hw_env *e, int self, int action)
         int t = (int)clipd(me->target_lane + (action == 2 ? 1 : -1), 0, e->cfg.lanes_count - 1);
         if (is_reachable_from(e, me->x, me->y, t)) me->target_lane = t;
     }
-    double steer = steering_control(me, me->target_lane);
+    double steer = steering_control(e, me, me->target_lane);
     me->act_steer = clipd(steer, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
     me->act_acc = speed_control(me, me->target_speed);
 }
@@ -309,6 +313,7 @@ static void vehicle_step(hw_env *e, int idx, double dt)
     veh_t *v = &e->v[idx];
     if (v->is_idm) v->timer += dt;
     if (v->crashed) { v->act_steer = 0; v->act_acc = -1.0 * v->speed; }
+    mg(e, v->speed - MAX_SPEED); mg(e, v->speed - MIN_SPEED);
     if (v->speed > MAX_SPEED) v->act_acc = fmin(v->act_acc, 1.0 * (MAX_SPEED - v->speed));
     else if (v->speed < MIN_SPEED) v->act_acc = fmax(v->act_acc, 1.0 * (MIN_SPEED - v->speed));
     double beta = atan(1.0 / 2 * tan(v->act_steer));
@@ -364,6 +369,8 @@ static void handle_collisions(hw_env *e, int ia, int ib, double dt)
     double db[2] = {B->speed * cos(B->heading) * dt, B->speed * sin(B->heading) * dt};
     int intersecting = 1, will_intersect = 1;
     double min_distance = INFINITY, axis[2] = {0, 0};
+    double seen_d[8], seen_ax[8][2];
+    int nseen = 0;
     for (int poly = 0; poly < 2; ++poly) {
         const double(*P)[2] = poly == 0 ? a : b;
         for (int k = 0; k < 4; ++k) {
@@ -382,17 +389,24 @@ static void handle_collisions(hw_env *e, int ia, int ib, double dt)
             mg(e, distance);
             if (distance > 0) will_intersect = 0;
             if (!intersecting && !will_intersect) break;
-            if (fabs(distance) < min_distance) {
-                min_distance = fabs(distance);
+            {
                 double cx = 0, cy = 0;
                 for (int q = 0; q < 4; ++q) { cx += a[q][0] - b[q][0]; cy += a[q][1] - b[q][1]; }
                 double dd = (cx / 4) * n[0] + (cy / 4) * n[1];
-                if (dd > 0) { axis[0] = n[0]; axis[1] = n[1]; }
-                else { axis[0] = -n[0]; axis[1] = -n[1]; }
+                double sx = dd > 0 ? n[0] : -n[0], sy = dd > 0 ? n[1] : -n[1];
+                seen_d[nseen] = fabs(distance); seen_ax[nseen][0] = sx; seen_ax[nseen][1] = sy; ++nseen;
+                if (fabs(distance) < min_distance) {
+                    min_distance = fabs(distance);
+                    axis[0] = sx; axis[1] = sy;
+                }
             }
         }
     }
     if (will_intersect) {
+        /* test aid: how close another edge came to winning the min-|distance| choice of the
+         * translation axis (a different axis means a different impact vector) */
+        for (int q = 0; q < nseen; ++q)
+            if (fabs(seen_ax[q][0] - axis[0]) + fabs(seen_ax[q][1] - axis[1]) > 1e-6) mg(e, seen_d[q] - min_distance);
         double tx = min_distance * axis[0], ty = min_distance * axis[1];
         A->impact_x = tx / 2; A->impact_y = ty / 2; A->has_impact = 1;
         B->impact_x = -tx / 2; B->impact_y = -ty / 2; B->has_impact = 1;

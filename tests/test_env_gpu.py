@@ -1,0 +1,304 @@
+"""GPU parity of the simulator kernels (hrp_env_step / observe / reset through the C-ABI) against the
+CPU oracle (oracle/highway_oracle.c), by STATE INJECTION: every step the oracle's fp64 state is
+injected into the GPU handle, both sides step once on the same action, and the results are compared.
+
+Tolerances (stated here, used below).  The kernel integrates in fp32 with x and the lane-change
+timer in fp64; the oracle is fp64 throughout.
+  * discrete results -- lane and target-lane indices, crashed / pending-impact flags, terminated /
+    truncated, and the vehicle index shown in every observation row -- must be EXACT whenever the
+    oracle reports that no discrete decision of that step was taken within MARGIN of its threshold
+    (hw_last_min_margin); steps closer than that -- and steps where a controlled vehicle crawls below 0.5 m/s,
+    where the controller's divisions by the speed amplify rounding by > 1e3 -- are counted and must stay a minority;
+  * x, y: 1e-3 m;  speed: 2e-4 m/s;  heading: 1e-4 rad;  reward: 2e-5;  observation entries: 2e-5
+    (normalised units);  IDM timer: 1e-9.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import highway as oh
+
+pytestmark = pytest.mark.gpu
+
+MARGIN = 1e-3
+TOL = dict(x=1e-3, y=1e-3, speed=2e-4, heading=1e-4, impact_x=1e-3, impact_y=1e-3, timer=1e-9, target_speed=1e-5)
+DISCRETE = ("lane", "target_lane", "crashed", "has_impact")
+
+
+def _vec(cfg, E, **kw):
+    from highway_rope_ppo_b200.envs.highway_vec import HighwayVecEnv
+
+    return HighwayVecEnv(cfg, E, device="cuda:0", **kw)
+
+
+def _stack_states(envs):
+    sts = [e.get_state() for e in envs]
+    out = {k: np.stack([s[k] for s in sts]) for k in oh.STATE_F64 + oh.STATE_I32}
+    out["time"] = np.array([s["time"] for s in sts])
+    return out
+
+
+def _cfg(base, **over):
+    c = copy.deepcopy(base)
+    for k, v in over.items():
+        if isinstance(v, dict):
+            c[k].update(v)
+        else:
+            c[k] = v
+    return c
+
+
+def test_philox_matches_oracle():
+    from highway_rope_ppo_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for _ in range(64):
+        ctr = rng.integers(0, 2**32, 4, dtype=np.uint64).astype(np.uint32)
+        key = rng.integers(0, 2**32, 2, dtype=np.uint64).astype(np.uint32)
+        out = np.zeros(4, dtype=np.uint32)
+        lib.hrp_philox4x32_10(ctr.ctypes.data, key.ctypes.data, out.ctypes.data)
+        assert np.array_equal(out, oh.philox4x32_10(ctr, key))
+
+
+@pytest.mark.parametrize("seed,base", [(0, 0), (42, 0), (2**40 + 7, 1000)])
+def test_reset_matches_oracle(highway_config, seed, base):
+    E = 96
+    env = _vec(highway_config, E, env_id_base=base)
+    env.reset(seed)
+    st = env.get_state()
+    o = oh.OracleEnv(highway_config)
+    for e in range(E):
+        o.reset(seed, env_id=base + e, episode=0)
+        ref = o.get_state()
+        for k in DISCRETE:
+            assert np.array_equal(st[k][e], ref[k]), k
+        np.testing.assert_allclose(st["x"][e], ref["x"], atol=1e-9)
+        np.testing.assert_allclose(st["timer"][e], ref["timer"], atol=1e-8)
+        for k in ("y", "speed", "target_speed", "delta", "heading"):
+            np.testing.assert_allclose(st[k][e], ref[k], rtol=2e-7, atol=1e-7, err_msg=k)
+        assert st["time"][e] == 0.0 and st["episode"][e] == 0
+    env.close()
+
+
+def _injected_parity(cfg, E, steps, seed, action_fn, sorted_obs=True):
+    """Returns (#env-steps compared exactly, #env-steps skipped as marginal, max abs errors)."""
+    N = cfg["observation"]["vehicles_count"]
+    env = _vec(cfg, E, autoreset=False)
+    oracles = [oh.OracleEnv(cfg) for _ in range(E)]
+    for e, o in enumerate(oracles):
+        o.reset(seed, env_id=e, episode=0)
+    rng = np.random.default_rng(seed)
+    rows = torch.zeros((E, N), dtype=torch.int32, device="cuda:0")
+    compared = skipped = 0
+    worst = {k: 0.0 for k in list(TOL) + ["reward", "obs"]}
+    for t in range(steps):
+        st = _stack_states(oracles)
+        env.set_state(st)
+        actions = action_fn(rng, E, t).astype(np.float32)
+        perm = None
+        if not sorted_obs:
+            perm = np.stack([rng.permutation(N - 1) for _ in range(E)]).astype(np.int32)
+        obs, rew, term, trunc = env.step(torch.from_numpy(actions).cuda(),
+                                         perm=None if perm is None else torch.from_numpy(perm).cuda(),
+                                         row_vehicle=rows)
+        got = env.get_state()
+        obs, rew, term, trunc, rv = (x.cpu().numpy() for x in (obs, rew, term, trunc, rows))
+        for e, o in enumerate(oracles):
+            r, te, tr = o.step(actions[e])
+            margin = o.min_margin()
+            ref = o.get_state()
+            want_obs, want_rows = o.observe(perm=None if perm is None else perm[e], with_rows=True)
+            margin = min(margin, o.min_margin())
+            if margin < MARGIN:
+                skipped += 1
+            else:
+                compared += 1
+                for k in DISCRETE:
+                    assert np.array_equal(got[k][e], ref[k]), (k, t, e, got[k][e], ref[k])
+                assert bool(term[e]) == te and bool(trunc[e]) == tr, (t, e)
+                assert np.array_equal(rv[e], want_rows), (t, e, rv[e], want_rows)
+                for k, tol in TOL.items():
+                    err = float(np.max(np.abs(got[k][e] - ref[k])))
+                    worst[k] = max(worst[k], err)
+                    assert err <= tol, (k, t, e, err)
+                worst["reward"] = max(worst["reward"], abs(float(rew[e]) - r))
+                assert abs(float(rew[e]) - r) <= 2e-5, (t, e, rew[e], r)
+                err = float(np.max(np.abs(obs[e] - want_obs)))
+                worst["obs"] = max(worst["obs"], err)
+                assert err <= 2e-5, (t, e, err)
+            if te or tr:  # reference loop: reset right after done
+                o.reset(seed, env_id=e, episode=1 + t)
+    env.close()
+    return compared, skipped, worst
+
+
+def _random_actions(rng, E, t):
+    return rng.uniform(-1, 1, (E, 2))
+
+
+def _gentle_actions(rng, E, t):
+    a = rng.uniform(-1, 1, (E, 2))
+    a[:, 1] *= 0.08  # small steering: long episodes in traffic, lane changes of the IDM vehicles dominate
+    return a
+
+
+def test_step_parity_random_actions(highway_config):
+    """>= 1000 injected-state env-steps with uniformly random actions (crashes, off-road, respawns)."""
+    compared, skipped, worst = _injected_parity(highway_config, E=48, steps=25, seed=1, action_fn=_random_actions)
+    print("random actions: compared", compared, "marginal", skipped, "max abs err", worst)
+    assert compared >= 1000 and skipped <= 0.3 * (compared + skipped)
+
+
+def test_step_parity_gentle_actions(highway_config):
+    """Long episodes (40 steps, truncation) where IDM / MOBIL traffic interaction is the bulk of the work."""
+    compared, skipped, worst = _injected_parity(highway_config, E=32, steps=42, seed=2, action_fn=_gentle_actions)
+    print("gentle actions: compared", compared, "marginal", skipped, "max abs err", worst)
+    assert compared >= 1000 and skipped <= 0.3 * (compared + skipped)
+
+
+def test_step_parity_shuffled_30_rows_7_features(highway_config):
+    """BASELINE config 3 shape: N = 30 observed vehicles, all 7 features, shuffled with an injected permutation."""
+    cfg = _cfg(highway_config, observation=dict(vehicles_count=30, order="shuffled",
+                                               features=["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"]))
+    compared, skipped, worst = _injected_parity(cfg, E=16, steps=20, seed=3, action_fn=_random_actions,
+                                                sorted_obs=False)
+    print("shuffled N=30 F=7: compared", compared, "marginal", skipped, "max abs err", worst)
+    assert compared >= 250 and skipped <= 0.3 * (compared + skipped)
+
+
+def test_step_parity_dense_small_road(highway_config):
+    """Edge sizes: 2 lanes, 12 vehicles at density 3 (frequent contacts), 5 observed rows, see_behind."""
+    cfg = _cfg(highway_config, lanes_count=2, vehicles_count=12, vehicles_density=3,
+               observation=dict(vehicles_count=5, see_behind=True))
+    compared, skipped, worst = _injected_parity(cfg, E=32, steps=30, seed=4, action_fn=_random_actions)
+    print("dense 2-lane: compared", compared, "marginal", skipped, "max abs err", worst)
+    assert compared >= 600 and skipped <= 0.4 * (compared + skipped)
+
+
+def test_step_parity_meta_action_ego(highway_config):
+    """DiscreteMetaAction / MDPVehicle ego (north_star; unreachable through the reference runner)."""
+    cfg = _cfg(highway_config)
+    cfg["action"] = {"type": "DiscreteMetaAction"}
+
+    def act(rng, E, t):
+        a = np.zeros((E, 2))
+        a[:, 0] = rng.integers(0, 5, E)
+        return a
+
+    compared, skipped, worst = _injected_parity(cfg, E=24, steps=40, seed=5, action_fn=act)
+    print("meta-action ego: compared", compared, "marginal", skipped, "max abs err", worst)
+    # LANE_LEFT/RIGHT reachability tests |y - 4 lane| <= 8 sit exactly on the threshold for a centred ego
+    assert compared >= 600 and skipped <= 0.4 * (compared + skipped)
+
+
+def test_single_vehicle_and_max_vehicles(highway_config):
+    """Edge sizes: an empty road (ego only: every observation row but the first is padding) and V = 64."""
+    for vc, n in ((0, 15), (63, 15)):
+        cfg = _cfg(highway_config, vehicles_count=vc)
+        compared, skipped, _ = _injected_parity(cfg, E=8, steps=12, seed=6 + vc, action_fn=_gentle_actions)
+        assert compared >= 80
+
+
+def test_shuffle_draw_matches_oracle_permutation(highway_config):
+    """Without an injected permutation the kernel draws it from Philox(seed, env id, draw counter)."""
+    cfg = _cfg(highway_config, observation=dict(order="shuffled"))
+    E, N, seed, base = 40, 15, 99, 500
+    env = _vec(cfg, E, env_id_base=base, autoreset=False)
+    env.reset(seed)
+    rows = torch.zeros((E, N), dtype=torch.int32, device="cuda:0")
+    st0 = env.get_state()
+    env.observe(row_vehicle=rows)
+    rv = rows.cpu().numpy()
+    o = oh.OracleEnv(cfg)
+    for e in range(E):
+        o.reset(seed, env_id=base + e, episode=0)
+        perm = oh.shuffle_perm(seed, base + e, int(st0["obs_draw"][e]), N - 1)
+        _, want = o.observe(perm=perm, with_rows=True)
+        assert np.array_equal(rv[e], want)
+    assert np.all(env.get_state()["obs_draw"] == st0["obs_draw"] + 1)
+    env.close()
+
+
+def test_autoreset_respawns_inside_the_step(highway_config):
+    """A finished env is respawned by the same launch: episode counter +1, time 0, fresh spawn == oracle's."""
+    E, seed = 64, 7
+    env = _vec(highway_config, E, autoreset=True)
+    env.reset(seed)
+    st = env.get_state()
+    st["time"][::2] = 39.0  # every other env truncates on this step
+    env.set_state(st)
+    a = torch.zeros((E, 2), device="cuda:0")
+    obs, rew, term, trunc = env.step(a)
+    trunc = trunc.cpu().numpy().astype(bool)
+    assert trunc[::2].all() and not trunc[1::2].any()
+    got = env.get_state()
+    o = oh.OracleEnv(highway_config)
+    for e in range(0, E, 2):
+        o.reset(seed, env_id=e, episode=1)
+        ref = o.get_state()
+        assert got["episode"][e] == 1 and got["time"][e] == 0.0
+        np.testing.assert_allclose(got["x"][e], ref["x"], atol=1e-9)
+        assert np.array_equal(got["lane"][e], ref["lane"])
+        np.testing.assert_allclose(obs[e].cpu().numpy(), o.observe(), atol=2e-6)
+    # envs that did not finish (no truncation, no crash in this step) keep their episode and advance time
+    alive = ~(trunc | term.cpu().numpy().astype(bool))
+    assert alive[1::2].sum() > E // 4
+    assert np.all(got["episode"][alive] == 0) and np.all(got["time"][alive] == 1.0)
+    assert np.all(got["episode"][~alive] == 1) and np.all(got["time"][~alive] == 0.0)
+    env.close()
+
+
+def test_full_size_invariants(highway_config):
+    """BASELINE size (4096 envs): size-independent properties after 45 free-running steps with autoreset."""
+    E = 4096
+    env = _vec(highway_config, E, autoreset=True)
+    env.reset(123)
+    g = torch.Generator(device="cuda:0").manual_seed(42)
+    ep_done = torch.zeros(E, dtype=torch.int64, device="cuda:0")
+    for t in range(45):
+        a = torch.rand((E, 2), generator=g, device="cuda:0") * 2 - 1
+        a[:, 1] *= 0.1
+        obs, rew, term, trunc = env.step(a)
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert (rew >= 0).all() and (rew <= 1.0 + 1e-6).all()
+        assert (obs.abs() <= 1.0 + 1e-6).all()
+        ep_done += (term | trunc).long()
+    st = env.get_state()
+    assert np.all(st["time"] <= 40.0) and np.all(st["time"] >= 0.0)
+    assert np.all(st["episode"] == ep_done.cpu().numpy())   # every done respawned exactly once
+    assert np.all((st["lane"] >= 0) & (st["lane"] < 4))
+    assert np.all(np.isfinite(st["x"])) and np.all(np.isfinite(st["speed"]))
+    # ego row is absolute: x / 100 clipped to 1 (a forward-driving ego is always beyond x = 100)
+    o = obs.cpu().numpy()
+    np.testing.assert_allclose(o[:, 0, 0], np.clip(st["x"][:, 0] / 100.0, -1, 1), atol=1e-6)
+    np.testing.assert_allclose(o[:, 0, 1], np.clip(st["y"][:, 0] / 100.0, -1, 1), atol=1e-6)
+    assert (o[:, 0, 0] == 1.0).mean() > 0.95
+    # sorted observation: |dx| non-decreasing over the non-padding rows
+    o = obs.cpu().numpy()
+    dx = np.abs(o[:, 1:, 0])
+    present = np.any(o[:, 1:, :] != 0, axis=-1)
+    for e in range(0, E, 37):
+        k = int(present[e].sum())
+        assert np.all(np.diff(dx[e, :k]) >= -1e-7)
+    env.close()
+
+
+def test_host_buffer_entry_points_match_device_path(highway_config):
+    E = 32
+    a_env, b_env = _vec(highway_config, E), _vec(highway_config, E)
+    obs_h = np.zeros((E, 15, 4), dtype=np.float32)
+    a_env.reset_host(5, obs_h)
+    obs_d = b_env.reset(5)
+    assert np.array_equal(obs_h, obs_d.cpu().numpy())
+    rew, te, tr = np.zeros(E, np.float32), np.zeros(E, np.uint8), np.zeros(E, np.uint8)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        act = rng.uniform(-1, 1, (E, 2)).astype(np.float32)
+        a_env.step_host(act, obs_h, rew, te, tr)
+        o, r, t1, t2 = b_env.step(torch.from_numpy(act).cuda())
+        assert np.array_equal(obs_h, o.cpu().numpy()) and np.array_equal(rew, r.cpu().numpy())
+        assert np.array_equal(te, t1.cpu().numpy()) and np.array_equal(tr, t2.cpu().numpy())
+    a_env.close(); b_env.close()

@@ -1,0 +1,223 @@
+"""GPU parity of the PPO kernels against the reference agent (tests/golden/ppo_*.npz, produced by
+/root/reference/ppo/agent.py through tools/gen_golden.py) and the torch fp32 oracle (oracle/ppo_ref.py).
+
+Tolerances (fp32 kernels, different summation order than ATen):
+  forward mean/value 2e-5 abs;  log-prob 5e-5;  loss terms 2e-5;  gradients 1e-4 relative to the gradient's
+  max-abs (plus 2e-6 abs);  parameters after Adam 5e-6 abs for one step (Adam's first steps move every weight
+  by ~lr = 3e-4 regardless of the gradient's size, so sign-level agreement of tiny gradients is what matters);
+  GAE: advantages 2e-6 abs (fp64 scan, fp32 store, same as the reference).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import ppo_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _agent(S, A, H, B, **kw):
+    from highway_rope_ppo_b200.ppo.agent import PPOAgent
+
+    return PPOAgent(S, A, lr=3e-4, hidden_dim=H, batch_size=B, device="cuda:0", **kw)
+
+
+def _load_flat(agent, flat):
+    agent.actor_critic.flat.copy_(torch.from_numpy(flat).cuda())
+
+
+@pytest.mark.parametrize("name", ["s60_h256_b64", "s20_h32_b17", "s300_h64_b256"])
+def test_init_matches_reference_for_the_same_seed(name):
+    """Same torch seed -> same nn.Linear initialisation stream as the reference's ActorCritic."""
+    g = golden(f"ppo_step_{name}.npz")
+    S, A, H, B, seed = (int(v) for v in g["dims"])
+    torch.manual_seed(seed)
+    agent = _agent(S, A, H, B)
+    assert [n for n, _ in agent.actor_critic.named_parameters()] == [str(n) for n in g["names"]]
+    assert np.array_equal(agent.actor_critic.flat.cpu().numpy(), g["params0"])
+
+
+@pytest.mark.parametrize("name", ["s60_h256_b64", "s20_h32_b17", "s300_h64_b256"])
+def test_forward_loss_grad_adam_match_reference(name):
+    from highway_rope_ppo_b200 import _lib
+
+    g = golden(f"ppo_step_{name}.npz")
+    S, A, H, B, _ = (int(v) for v in g["dims"])
+    agent = _agent(S, A, H, B)
+    _load_flat(agent, g["params0"])
+    ac = agent.actor_critic
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    mean, std, value = ac.forward(cu("states"))
+    np.testing.assert_allclose(mean.cpu().numpy(), g["mean"], atol=2e-5)
+    np.testing.assert_allclose(value.cpu().numpy(), g["value"], atol=2e-5)
+    logp, v, ent = ac.evaluate(cu("states"), None, cu("pre_tanh"))
+    np.testing.assert_allclose(logp.cpu().numpy(), g["logp"], atol=5e-5, rtol=1e-5)
+    np.testing.assert_allclose(ent.cpu().numpy(), g["entropy"], atol=1e-6)
+    # act kernel: deterministic noise reproduces pre_tanh -> log-prob of the reference's evaluate()
+    noise = (cu("pre_tanh") - mean) / std
+    out = ac.act(cu("states"), noise=noise.contiguous())
+    np.testing.assert_allclose(out["pre_tanh"].cpu().numpy(), g["pre_tanh"], atol=1e-5)
+    np.testing.assert_allclose(out["log_prob"].cpu().numpy(), g["logp"], atol=1e-4, rtol=1e-5)
+    np.testing.assert_allclose(out["action"].cpu().numpy(), np.tanh(g["pre_tanh"]), atol=1e-6)
+    np.testing.assert_allclose(out["value"].cpu().numpy(), g["value"][:, 0], atol=2e-5)
+    # one minibatch: loss, gradient, clip + Adam
+    flat = {"states": cu("states"), "pre_tanh": cu("pre_tanh"), "log_prob": cu("old_logp"), "adv": cu("adv"),
+            "ret": cu("ret")}
+    agent._metrics.zero_()
+    agent._minibatch_step(flat, None, B, 1)
+    m = agent._metrics.cpu().numpy()
+    assert abs(m[0] - float(g["loss"])) < 2e-5 and abs(m[1] - float(g["actor_loss"])) < 2e-5
+    assert abs(m[2] - float(g["critic_loss"])) < 2e-5 * max(1.0, float(g["critic_loss"]))
+    assert abs(m[4] - float(g["clip_fraction"])) < 1e-6 and abs(m[5] - float(g["approx_kl"])) < 2e-5
+    assert m[6] == 1.0
+    grad = agent.grad.cpu().numpy()
+    scale = np.abs(g["grads"]).max()
+    np.testing.assert_allclose(grad, g["grads"], atol=1e-4 * scale + 2e-6)
+    np.testing.assert_allclose(ac.flat.cpu().numpy(), g["params1"], atol=5e-6)
+    # gathered minibatch (idx) gives the same step: run step 2 through an identity-permuted gather
+    idx = torch.arange(B, device="cuda:0", dtype=torch.int64)
+    agent._minibatch_step(flat, idx, B, 1)
+    np.testing.assert_allclose(ac.flat.cpu().numpy(), g["params2"], atol=2e-5)
+    assert int(agent.optimizer.step_dev.item()) == 2
+
+
+@pytest.mark.parametrize("name", ["t50", "t2048"])
+def test_gae_matches_reference(name):
+    from highway_rope_ppo_b200.ppo.agent import gae
+
+    g = golden(f"ppo_gae_{name}.npz")
+    T = len(g["reward"])
+    adv, ret = gae(torch.from_numpy(g["reward"].astype(np.float32)).cuda().view(T, 1),
+                   torch.from_numpy(g["value"]).cuda().view(T, 1),
+                   torch.from_numpy(g["done"].astype(np.uint8)).cuda().view(T, 1), float(g["last_value"]), 0.99, 0.95)
+    # rewards are float32 on the device (float64 python floats in the reference): 2e-6 covers the input rounding
+    np.testing.assert_allclose(adv.cpu().numpy()[:, 0], g["adv"], atol=2e-6, rtol=2e-6)
+    np.testing.assert_allclose(ret.cpu().numpy()[:, 0], g["ret"], atol=2e-6, rtol=2e-6)
+
+
+def test_gae_batched_matches_oracle():
+    from highway_rope_ppo_b200.ppo.agent import gae
+
+    rng = np.random.default_rng(0)
+    T, E = 64, 300
+    rew = rng.random((T, E)).astype(np.float32)
+    val = rng.standard_normal((T, E)).astype(np.float32)
+    done = (rng.random((T, E)) < 0.1)
+    last = rng.standard_normal(E).astype(np.float32)
+    adv, ret = gae(torch.from_numpy(rew).cuda(), torch.from_numpy(val).cuda(),
+                   torch.from_numpy(done.astype(np.uint8)).cuda(), torch.from_numpy(last).cuda(), 0.99, 0.95)
+    adv, ret = adv.cpu().numpy(), ret.cpu().numpy()
+    for e in range(0, E, 17):
+        a, r = ppo_ref.gae(rew[:, e], val[:, e], done[:, e], last[e])
+        assert np.array_equal(adv[:, e], a) and np.array_equal(ret[:, e], r)
+
+
+def test_adv_normalize_matches_torch():
+    from highway_rope_ppo_b200 import _lib
+
+    lib = _lib.load()
+    a = torch.randn(100_003, device="cuda:0") * 3 + 1.5
+    want = ((a - a.mean()) / (a.std() + 1e-8)).cpu().numpy()
+    stats = torch.zeros(3 + 512, dtype=torch.float64, device="cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.hrp_adv_stats(a.data_ptr(), a.numel(), stats.data_ptr(), s))
+    _lib.check(lib.hrp_adv_normalize(a.data_ptr(), a.numel(), stats.data_ptr(), s))
+    np.testing.assert_allclose(a.cpu().numpy(), want, atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["s12_h16_n100", "s60_h256_n2048"])
+def test_full_update_matches_reference(name):
+    """PPOAgent.update on the reference's stored rollout with the reference's minibatch permutation."""
+    g = golden(f"ppo_update_{name}.npz")
+    S, A, H, n, bs, epochs, np_seed = (int(v) for v in g["dims"])
+    agent = _agent(S, A, H, bs, epochs=epochs)
+    _load_flat(agent, g["params0"])
+    for t in range(n):
+        agent.memory.store(g["states"][t], g["action"][t], g["pre_tanh"][t], float(g["reward"][t]), None,
+                           float(g["logp"][t]), bool(g["done"][t]), np.float32(g["value"][t]))
+    np.random.seed(np_seed)
+    metrics = agent.update(last_value=float(g["last_value"]))
+    want = dict(zip((str(k) for k in g["metric_names"]), g["metric_values"]))
+    print({k: (metrics[k], float(want[k])) for k in want})
+    # hundreds of optimizer steps amplify fp32 summation-order differences: compare at 2e-3 relative
+    for k in ("loss", "policy_loss", "value_loss", "entropy", "explained_variance"):
+        assert abs(metrics[k] - want[k]) <= 2e-3 * max(1.0, abs(want[k])), (k, metrics[k], want[k])
+    assert abs(metrics["clip_fraction"] - want["clip_fraction"]) <= 0.01
+    assert abs(metrics["approx_kl"] - want["approx_kl"]) <= 2e-3 * max(1e-2, abs(want["approx_kl"]))
+    p1 = agent.actor_critic.flat.cpu().numpy()
+    moved = np.abs(g["params1"] - g["params0"]).max()
+    assert np.abs(p1 - g["params1"]).max() <= 0.05 * moved + 1e-5
+    assert len(agent.memory) == 0
+
+
+def test_loss_grad_large_batch_matches_oracle():
+    """BASELINE-size minibatch (4096 x S=60, H=256): gradient vs the torch fp32 oracle (split-K wgrad path)."""
+    S, A, H, B = 60, 2, 256, 4096
+    torch.manual_seed(1)
+    agent = _agent(S, A, H, B)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, S, generator=g) * 0.5
+    flat = agent.actor_critic.flat.cpu()
+    mean, log_std, _ = ppo_ref.forward(flat, x, S, A, H)
+    z = mean + torch.randn(B, A, generator=g)
+    logp, _, _ = ppo_ref.evaluate(flat, x, z, S, A, H)
+    old = logp + 0.2 * torch.randn(B, generator=g)
+    adv, ret = torch.randn(B, generator=g), torch.randn(B, generator=g)
+    r = ppo_ref.loss_and_grad(flat, x, z, old, adv, ret, S, A, H)
+    dev = {"states": x.cuda(), "pre_tanh": z.cuda(), "log_prob": old.cuda(), "adv": adv.cuda(), "ret": ret.cuda()}
+    agent._metrics.zero_()
+    agent._minibatch_step(dev, None, B, 1)
+    m = agent._metrics.cpu().numpy()
+    assert abs(m[0] - r["loss"]) < 5e-5 and abs(m[4] - r["clip_fraction"]) < 1e-3
+    want = r["grad"].numpy()
+    np.testing.assert_allclose(agent.grad.cpu().numpy(), want, atol=2e-4 * np.abs(want).max() + 1e-6)
+
+
+def test_checkpoint_roundtrip_and_reference_key_names(tmp_path):
+    torch.manual_seed(0)
+    a = _agent(60, 2, 64, 32)
+    flat = {"states": torch.randn(32, 60).cuda(), "pre_tanh": torch.randn(32, 2).cuda(),
+            "log_prob": torch.randn(32).cuda() - 2, "adv": torch.randn(32).cuda(), "ret": torch.randn(32).cuda()}
+    a._minibatch_step(flat, None, 32, 1)
+    path = str(tmp_path / "ck.pth")
+    a.save(path)
+    ck = torch.load(path, map_location="cpu")
+    assert list(ck["model"]) == ["log_std", "shared.0.weight", "shared.0.bias", "shared.2.weight", "shared.2.bias",
+                                 "actor_mean.0.weight", "actor_mean.0.bias", "actor_mean.2.weight",
+                                 "actor_mean.2.bias", "critic.0.weight", "critic.0.bias", "critic.2.weight",
+                                 "critic.2.bias"]
+    # visualize.py:54-57 infers the dimensions from these two tensors
+    assert ck["model"]["shared.0.weight"].shape == (64, 60) and ck["model"]["actor_mean.2.weight"].shape == (2, 64)
+    assert set(ck["optimizer"]) == {"state", "param_groups"} and len(ck["optimizer"]["state"]) == 13
+    b = _agent(60, 2, 64, 32)
+    b.load(path)
+    assert torch.equal(a.actor_critic.flat, b.actor_critic.flat)
+    assert torch.equal(a.optimizer.exp_avg, b.optimizer.exp_avg) and int(b.optimizer.step_dev.item()) == 1
+    # the checkpoint loads into a plain torch module with the reference's layout
+    import torch.nn as nn
+
+    class Ref(nn.Module):
+        def __init__(s):
+            super().__init__()
+            s.shared = nn.Sequential(nn.Linear(60, 64), nn.ReLU(), nn.Linear(64, 64), nn.ReLU())
+            s.actor_mean = nn.Sequential(nn.Linear(64, 64), nn.ReLU(), nn.Linear(64, 2))
+            s.log_std = nn.Parameter(torch.zeros(2))
+            s.critic = nn.Sequential(nn.Linear(64, 64), nn.ReLU(), nn.Linear(64, 1))
+
+    Ref().load_state_dict(ck["model"])
+    opt = torch.optim.Adam(Ref().parameters(), lr=1e-4)
+    opt.load_state_dict(ck["optimizer"])
+
+
+def test_select_action_protocol():
+    a = _agent(60, 2, 64, 32)
+    s = np.random.randn(60).astype(np.float32)
+    action, pre, lp, v = a.select_action(s)
+    assert action.shape == (2,) and pre.shape == (2,) and isinstance(lp, float) and v.dtype == np.float32
+    assert np.allclose(action, np.tanh(pre), atol=1e-6) and np.all(np.abs(action) <= 1)
+    action, pre, lp, v = a.select_action(s, deterministic=True)
+    assert lp is None
+    mean, std, value = a.actor_critic.forward(s)
+    assert mean.shape == (2,) and std.shape == (2,) and value.shape == (1,)
+    assert np.allclose(pre, mean.cpu().numpy(), atol=1e-6)
