@@ -80,6 +80,9 @@ SIGNATURES: Dict[str, Any] = {
     "hrp_philox4x32_10": (C.c_int, [_vp, _vp, _vp]),
     "hrp_embed_apply": (C.c_int, [_i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "hrp_ppo_param_count": (_i64, [_i32, _i32, _i32]),
+    "hrp_ppo_set_math": (C.c_int, [_i32]),
+    "hrp_ppo_get_math": (C.c_int, []),
+    "hrp_gemm_strided": (C.c_int, [_i32, _i32, _i32, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _i32, _vp]),
     "hrp_ppo_create": (C.c_int, [_i32, _i32, _i32, _i64, _i32, C.POINTER(_vp)]),
     "hrp_ppo_destroy": (C.c_int, [_vp]),
     "hrp_ppo_forward": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),

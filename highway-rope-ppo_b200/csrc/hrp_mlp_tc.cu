@@ -1,0 +1,328 @@
+// hrp_mlp_tc.cu -- tcgen05 (5th-gen tensor core) GEMM for the policy/value MLP of ppo/agent.py:12-84.
+//
+//   C[M,N] (+)= sum_k A(m,k) * B(n,k)      A(m,k) = A[m*sam + k*sak],  B(n,k) = B[n*sbn + k*sbk]
+//
+// with the same fused epilogue as the SIMT kernel in hrp_ppo.cu (+C, +bias[n], ReLU, ReLU-mask) and the same
+// deterministic split-K (gridDim.z partial tiles).  Arbitrary element strides cover every GEMM of the
+// forward and backward pass without transposed copies: nn.Linear forward (A = activations [B,K], B = weight
+// [N,K], both K-contiguous), dX = dY W (B = weight read with n-stride 1), dW = dY^T X (both operands
+// batch-major, i.e. "MN-contiguous").
+//
+// Structure (one CTA = one 128 x 128 output tile, 256 threads):
+//   * operands are fp32 in HBM and are multiplied as TF32 on the tensor cores (kind::tf32); in the default
+//     3xTF32 mode every operand is split into hi = tf32(x) and lo = x - hi while it is staged, and
+//     D += Ahi*Bhi + Ahi*Blo + Alo*Bhi is accumulated in fp32 in TMEM, which recovers fp32-level accuracy
+//     (the dropped Alo*Blo term is ~2^-22 relative) -- the MMA time is negligible for these shapes;
+//   * tiles are staged global -> registers -> shared memory in the canonical K-major SWIZZLE_128B layout
+//     (8-row x 128-byte atoms, 16-byte chunk index XOR row%8), software-pipelined one K-block ahead,
+//     3 shared-memory stages recycled through mbarriers signalled by tcgen05.commit;
+//   * one elected thread issues the tcgen05.mma instructions (UMMA 128 x 128 x 8); the accumulator lives in
+//     128 TMEM columns; the epilogue reads it with tcgen05.ld (32 lanes x 32 columns per warp).
+// Plain ld.global staging (no TMA) is deliberate: the weight matrices live at 8-byte-aligned offsets of the
+// flat parameter buffer and half of the backward operands are MN-contiguous, neither of which a 128B-swizzled
+// tensor map accepts without extra copies.  The matrices are small (<= 4 MB) and L2-resident.
+#include "hrp_internal.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 32;                  // BK * 4 B = 128 B = one swizzle row; BN is 64 or 128
+constexpr int TC_THREADS = 256;
+constexpr int A_TILE_BYTES = BM * BK * 4;         // 16 KB per part of the A tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B (one 8-row atom), version 1 (Blackwell), layout 2
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (2 at bits 7-9, 10-12), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// byte offset of element (row, k) inside a [rows x 32 fp32] K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz(int r, int k)
+{
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + ((k & 3) << 2));
+}
+
+// A tile element this thread stages at step i: K-contiguous operands walk k fastest (coalesced 128 B rows),
+// MN-contiguous operands walk the row fastest.
+template <bool KCONTIG, int ROWS>
+__device__ __forceinline__ void tile_coord(int i, int tid, int &r, int &k)
+{
+    int idx = tid + i * TC_THREADS;
+    if (KCONTIG) { r = idx >> 5; k = idx & 31; }
+    else { r = idx & (ROWS - 1); k = idx / ROWS; }
+}
+
+template <bool A_KC, bool B_KC, int NSPLIT, int BN>
+__global__ void __launch_bounds__(TC_THREADS)
+tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, long long sak,
+               const float *__restrict__ B, long long sbn, long long sbk, float *__restrict__ C, int ldc,
+               const float *__restrict__ bias, int relu, const float *__restrict__ mask, int ldm, int accumulate,
+               int k_chunk)
+{
+    constexpr int PARTS = NSPLIT == 3 ? 2 : 1;                  // hi (+ lo) copy of every operand tile
+    constexpr int B_TILE_BYTES = BN * BK * 4;
+    constexpr int STAGE_BYTES = PARTS * (A_TILE_BYTES + B_TILE_BYTES);
+    constexpr int STAGES = NSPLIT == 3 ? 3 : 4;
+    constexpr int B_ITERS = BN * BK / TC_THREADS;               // elements of B staged per thread and K-block
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar_empty[4], bar_done;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * k_chunk, kend = min(K, kbeg + k_chunk);
+    const int nkb = (kend - kbeg + BK - 1) / BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar_empty[s], 1);
+        mbar_init(&bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "n"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+    constexpr uint32_t idesc = make_idesc(BM, BN);
+
+    // register staging of the next K-block: 16 elements of A and BN/8 of B per thread
+    float ra[16], rb[B_ITERS];
+    auto fetch = [&](int kb) {
+        const int k0 = kbeg + kb * BK;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int r, k;
+            tile_coord<A_KC, BM>(i, tid, r, k);
+            int gm = m0 + r, gk = k0 + k;
+            ra[i] = (gm < M && gk < kend) ? __ldg(A + (long long)gm * sam + (long long)gk * sak) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < B_ITERS; ++i) {
+            int r, k;
+            tile_coord<B_KC, BN>(i, tid, r, k);
+            int gn = n0 + r, gk = k0 + k;
+            rb[i] = (gn < N && gk < kend) ? __ldg(B + (long long)gn * sbn + (long long)gk * sbk) : 0.f;
+        }
+    };
+    auto stash = [&](int s) {
+        uint8_t *a_hi = smem + s * STAGE_BYTES, *b_hi = a_hi + PARTS * A_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int r, k;
+            tile_coord<A_KC, BM>(i, tid, r, k);
+            uint32_t o = swz(r, k);
+            if (NSPLIT == 3) {
+                float hi = __uint_as_float(__float_as_uint(ra[i]) & 0xFFFFE000u);
+                *(float *)(a_hi + o) = hi;
+                *(float *)(a_hi + A_TILE_BYTES + o) = ra[i] - hi;
+            } else {
+                *(float *)(a_hi + o) = ra[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < B_ITERS; ++i) {
+            int r, k;
+            tile_coord<B_KC, BN>(i, tid, r, k);
+            uint32_t o = swz(r, k);
+            if (NSPLIT == 3) {
+                float hi = __uint_as_float(__float_as_uint(rb[i]) & 0xFFFFE000u);
+                *(float *)(b_hi + o) = hi;
+                *(float *)(b_hi + B_TILE_BYTES + o) = rb[i] - hi;
+            } else {
+                *(float *)(b_hi + o) = rb[i];
+            }
+        }
+    };
+
+    if (nkb > 0) fetch(0);
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        if (kb >= STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((kb / STAGES) - 1) & 1));  // MMAs of kb - STAGES retired
+        stash(s);
+        if (kb + 1 < nkb) fetch(kb + 1);                 // in flight while this block's MMAs are issued
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+        __syncthreads();
+        if (warp == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + PARTS * A_TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {       // UMMA_K = 8 tf32 = 32 bytes: advance the start address
+                    const uint32_t off = kk * 32;
+                    const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+                    if (NSPLIT == 3) {
+                        umma_tf32(tmem_d, make_desc(a_hi + A_TILE_BYTES + off), make_desc(b_hi + off), idesc, acc);
+                        umma_tf32(tmem_d, make_desc(a_hi + off), make_desc(b_hi + B_TILE_BYTES + off), idesc, 1u);
+                        umma_tf32(tmem_d, make_desc(a_hi + off), make_desc(b_hi + off), idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_d, make_desc(a_hi + off), make_desc(b_hi + off), idesc, acc);
+                    }
+                }
+                umma_commit(&bar_empty[s]);                 // frees the stage when these MMAs have read it
+                if (kb + 1 == nkb) umma_commit(&bar_done);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers -> shared (row-major, padded) -> coalesced global rows.
+    // Warp w reads TMEM lanes 32 (w % 4) .., columns (BN / 2) (w / 4) ..; the operand stages are free by now.
+    if (nkb > 0) mbar_wait(&bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    constexpr int LDS = BN + 1;                       // odd row pitch: conflict-free column writes
+    float *stage_c = (float *)smem;
+    {
+        const int trow = 32 * (warp & 3) + lane;
+#pragma unroll 1
+        for (int c0 = (BN / 2) * (warp >> 2); c0 < (BN / 2) * (warp >> 2) + BN / 2; c0 += 16) {
+            uint32_t v[16];
+            if (nkb > 0) {
+                uint32_t taddr = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                    "%13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) stage_c[trow * LDS + c0 + j] = __uint_as_float(v[j]);
+        }
+    }
+    __syncthreads();
+    float *Cz = C + (size_t)blockIdx.z * M * ldc;
+    for (int idx = tid; idx < BM * BN; idx += TC_THREADS) {
+        const int r = idx / BN, c = idx - r * BN;
+        const int gm = m0 + r, gn = n0 + c;
+        if (gm >= M || gn >= N) continue;
+        const size_t o = (size_t)gm * ldc + gn;
+        float x = stage_c[r * LDS + c];
+        if (accumulate) x += Cz[o];
+        if (bias) x += bias[gn];
+        if (relu) x = fmaxf(x, 0.f);
+        if (mask) x = mask[(size_t)gm * ldm + gn] > 0.f ? x : 0.f;
+        Cz[o] = x;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
+}
+
+template <bool A_KC, bool B_KC, int NSPLIT, int BN>
+int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
+           const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias, int relu,
+           const float *mask, int ldm, int accumulate, int k_chunk)
+{
+    constexpr int PARTS = NSPLIT == 3 ? 2 : 1;
+    constexpr int STAGES = NSPLIT == 3 ? 3 : 4;
+    constexpr int OPERANDS = STAGES * PARTS * (A_TILE_BYTES + BN * BK * 4);
+    constexpr int EPILOGUE = BM * (BN + 1) * 4;
+    constexpr int SMEM = (OPERANDS > EPILOGUE ? OPERANDS : EPILOGUE) + 1024;
+    static bool configured = false;
+    auto kern = tc_gemm_kernel<A_KC, B_KC, NSPLIT, BN>;
+    if (!configured) {
+        HRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    kern<<<grid, TC_THREADS, SMEM, s>>>(M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate,
+                                       k_chunk);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <bool A_KC, bool B_KC>
+int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
+             long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
+             int relu, const float *mask, int ldm, int accumulate, int k_chunk)
+{
+#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk
+    if (bn == 64) return nsplit == 3 ? launch<A_KC, B_KC, 3, 64>(HRP_TC_ARGS) : launch<A_KC, B_KC, 1, 64>(HRP_TC_ARGS);
+    return nsplit == 3 ? launch<A_KC, B_KC, 3, 128>(HRP_TC_ARGS) : launch<A_KC, B_KC, 1, 128>(HRP_TC_ARGS);
+#undef HRP_TC_ARGS
+}
+
+}  // namespace
+
+// Strided tcgen05 GEMM; returns the number of K splits actually used (partials at C + z*M*ldc), <0 on error.
+// nsplit: 3 = 3xTF32 (fp32-grade accuracy), 1 = single TF32 pass.
+int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
+                long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
+                int accumulate, int splits, int nsplit, cudaStream_t s)
+{
+    int k_chunk = K;
+    if (splits > 1) {
+        k_chunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+        splits = (K + k_chunk - 1) / k_chunk;
+    } else {
+        splits = 1;
+    }
+    // 64-wide N tiles when 128-wide ones would leave most of the 148 SMs idle
+    const int mt = (M + BM - 1) / BM;
+    const int bn = (N <= 64 || mt * ((N + 127) / 128) * splits < 120) ? 64 : 128;
+    dim3 grid((N + bn - 1) / bn, mt, splits);
+    const bool akc = sak == 1, bkc = sbk == 1;
+    int rc;
+    if (akc && bkc) rc = dispatch<true, true>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    else if (akc) rc = dispatch<true, false>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    else if (bkc) rc = dispatch<false, true>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    else rc = dispatch<false, false>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    return rc < 0 ? rc : splits;
+}

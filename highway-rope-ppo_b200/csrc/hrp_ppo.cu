@@ -130,36 +130,101 @@ __global__ void reduce_partials_kernel(const float *__restrict__ part, float *__
     out[i] = s;
 }
 
-// column sums of G[B, N] -> out[N] (bias gradients); one warp per 32 columns, deterministic
+// column sums, stage 1: block (x, y) reduces rows [y*rows_per, ...) of 32 columns -> part[y][N]
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float *__restrict__ G, int ldg, long long B, int N, float *__restrict__ out)
+colsum_partial_kernel(const float *__restrict__ G, int ldg, long long B, int N, int rows_per, float *__restrict__ part)
 {
     __shared__ float red[8][33];
-    int col = blockIdx.x * 32 + (threadIdx.x & 31);
-    int w = threadIdx.x >> 5;
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + l;
+    const long long r0 = (long long)blockIdx.y * rows_per, r1 = min(B, r0 + rows_per);
     float s = 0.f;
     if (col < N)
-        for (long long b = w; b < B; b += 8) s += G[(size_t)b * ldg + col];
-    red[w][threadIdx.x & 31] = s;
+        for (long long b = r0 + w; b < r1; b += 8) s += G[(size_t)b * ldg + col];
+    red[w][l] = s;
     __syncthreads();
     if (w == 0 && col < N) {
         float t = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-        out[col] = t;
+        for (int i = 0; i < 8; ++i) t += red[i][l];
+        part[(size_t)blockIdx.y * N + col] = t;
     }
 }
 
-// gather minibatch rows: dst[b, :] = src[idx[b], :]
-__global__ void gather_rows_kernel(const float *__restrict__ src, const long long *__restrict__ idx,
-                                   float *__restrict__ dst, long long B, int cols)
+// head weight/bias gradients, stage 1 (agent.py actor_mean.2 / critic.2): for a chunk of rows,
+//   dWa2[a,h] = sum_b dmean[b,a] a1[b,h], dba2[a] = sum_b dmean[b,a], dWc2[h] = sum_b dvalue[b] c1[b,h], dbc2 = sum_b dvalue[b]
+// part[y] holds [A*H | A | H | 1] floats.
+__global__ void __launch_bounds__(256)
+heads_wgrad_partial_kernel(const float *__restrict__ dmean, const float *__restrict__ dvalue,
+                           const float *__restrict__ a1, const float *__restrict__ c1, long long B, int H, int A,
+                           int rows_per, float *__restrict__ part)
 {
+    __shared__ float red[8][6][33];
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int h = blockIdx.x * 32 + l;
+    const long long r0 = (long long)blockIdx.y * rows_per, r1 = min(B, r0 + rows_per);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accc = 0.f, accb = 0.f;
+    for (long long b = r0 + w; b < r1; b += 8) {
+        float dv = dvalue[b];
+        if (h < H) {
+            float av = a1[(size_t)b * H + h];
+            for (int a = 0; a < A; ++a) acc[a] = fmaf(dmean[b * A + a], av, acc[a]);
+            accc = fmaf(dv, c1[(size_t)b * H + h], accc);
+        }
+        if (blockIdx.x == 0 && l <= A) accb += l < A ? dmean[b * A + l] : dv;
+    }
+    for (int a = 0; a < 4; ++a) red[w][a][l] = acc[a];
+    red[w][4][l] = accc;
+    red[w][5][l] = accb;
+    __syncthreads();
+    if (w == 0) {
+        float *out = part + (size_t)blockIdx.y * ((size_t)A * H + A + H + 1);
+        float t[6];
+        for (int q = 0; q < 6; ++q) {
+            t[q] = 0.f;
+            for (int i = 0; i < 8; ++i) t[q] += red[i][q][l];
+        }
+        if (h < H) {
+            for (int a = 0; a < A; ++a) out[(size_t)a * H + h] = t[a];
+            out[(size_t)A * H + A + h] = t[4];
+        }
+        if (blockIdx.x == 0 && l <= A) {
+            if (l < A) out[(size_t)A * H + l] = t[5];
+            else out[(size_t)A * H + A + H] = t[5];
+        }
+    }
+}
+// stage 2: sum the chunks; [A*H + A] go to grad + wa2 (ba2 follows wa2), [H + 1] to grad + wc2 (bc2 follows wc2)
+__global__ void heads_wgrad_final_kernel(const float *__restrict__ part, int chunks, int H, int A,
+                                         float *__restrict__ g_wa2, float *__restrict__ g_wc2)
+{
+    int n = A * H + A + H + 1;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += part[(size_t)c * n + i];
+    if (i < A * H + A) g_wa2[i] = s;
+    else g_wc2[i - (A * H + A)] = s;
+}
+
+// gather the minibatch out of the rollout in one launch: states, pre_tanh, old log-prob, advantage, return
+__global__ void gather_batch_kernel(const float *__restrict__ states, const float *__restrict__ pre_tanh,
+                                    const float *__restrict__ olp, const float *__restrict__ adv,
+                                    const float *__restrict__ ret, const long long *__restrict__ idx, long long B, int S,
+                                    int A, float *__restrict__ x, float *__restrict__ z, float *__restrict__ o_olp,
+                                    float *__restrict__ o_adv, float *__restrict__ o_ret)
+{
+    const int W = S + A + 3;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = B * cols;
-    if (i >= total) return;
-    long long b = i / cols;
-    int c = (int)(i - b * cols);
-    dst[i] = src[(size_t)idx[b] * cols + c];
+    if (i >= B * W) return;
+    long long b = i / W;
+    int c = (int)(i - b * W);
+    long long src = idx[b];
+    if (c < S) x[b * S + c] = states[(size_t)src * S + c];
+    else if (c < S + A) z[b * A + (c - S)] = pre_tanh[(size_t)src * A + (c - S)];
+    else if (c == S + A) o_olp[b] = olp[src];
+    else if (c == S + A + 1) o_adv[b] = adv[src];
+    else o_ret[b] = ret[src];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -431,13 +496,25 @@ struct hrp_ppo {
     float *mean, *value, *dmean, *dvalue;    // heads and their gradients
     float *d1, *d2;                          // activation gradients [B,H]
     float *part;                             // split-K partials
+    float *part2;                            // column-sum / head-gradient partials (32 chunks)
     int splits_cap;
 };
+
+// tensor-core path (hrp_mlp_tc.cu)
+int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
+                long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
+                int accumulate, int splits, int nsplit, cudaStream_t s);
+
+// math mode of the hidden-layer GEMMs: 0 = fp32 SIMT, 1 = TF32 tcgen05, 3 = 3xTF32 tcgen05 (default)
+static int g_math_mode = 3;
 
 static int gemm(bool AT, bool BT, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C,
                 int ldc, const float *bias, int relu, const float *mask, int ldm, int accumulate, int splits,
                 cudaStream_t s)
 {
+    if (g_math_mode != 0 && N >= 32 && M >= 32)
+        return hrp_tc_gemm(M, N, K, A, AT ? 1 : lda, AT ? lda : 1, B, BT ? ldb : 1, BT ? 1 : ldb, C, ldc, bias, relu,
+                           mask, ldm, accumulate, splits, g_math_mode == 1 ? 1 : 3, s);
     int k_chunk = K;
     if (splits > 1) {
         k_chunk = ((K + splits - 1) / splits + GK - 1) / GK * GK;
@@ -469,6 +546,20 @@ static int wgrad(hrp_ppo *h, int N, int K, long long B, const float *dY, const f
     return 0;
 }
 
+// bias gradient db[N] = column sums of G[B, N], deterministic two-stage
+static int colsum(hrp_ppo *h, const float *G, int ldg, long long B, int N, float *out, cudaStream_t s)
+{
+    int chunks = (int)((B + 255) / 256);
+    if (chunks > 32) chunks = 32;
+    if (chunks < 1) chunks = 1;
+    int rows_per = (int)((B + chunks - 1) / chunks);
+    dim3 grid((N + 31) / 32, chunks);
+    colsum_partial_kernel<<<grid, 256, 0, s>>>(G, ldg, B, N, rows_per, h->part2);
+    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, s>>>(h->part2, out, N, chunks);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static int forward_impl(hrp_ppo *h, const float *params, const float *x, long long B, float *mean, float *value,
                         cudaStream_t s)
 {
@@ -485,6 +576,25 @@ static int forward_impl(hrp_ppo *h, const float *params, const float *x, long lo
 }
 
 extern "C" {
+
+int hrp_ppo_set_math(int32_t mode)
+{
+    if (mode != 0 && mode != 1 && mode != 3) { hrp_set_error("hrp_ppo_set_math: mode must be 0, 1 or 3"); return -1; }
+    g_math_mode = mode;
+    return 0;
+}
+int hrp_ppo_get_math(void) { return g_math_mode; }
+
+int hrp_gemm_strided(int32_t M, int32_t N, int32_t K, const float *A, int64_t sam, int64_t sak, const float *B,
+                     int64_t sbn, int64_t sbk, float *C, int32_t ldc, const float *bias, int32_t relu, int32_t mode,
+                     void *stream)
+{
+    if (!A || !B || !C || M < 1 || N < 1 || K < 1 || ldc < N) { hrp_set_error("hrp_gemm_strided: bad arguments"); return -1; }
+    if (mode != 1 && mode != 3) { hrp_set_error("hrp_gemm_strided: mode must be 1 (TF32) or 3 (3xTF32)"); return -1; }
+    int rc = hrp_tc_gemm(M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, nullptr, 0, 0, 1, mode,
+                         (cudaStream_t)stream);
+    return rc < 0 ? rc : 0;
+}
 
 int64_t hrp_ppo_param_count(int32_t state_dim, int32_t action_dim, int32_t hidden_dim)
 {
@@ -508,7 +618,8 @@ int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, in
     h->splits_cap = 32;
     size_t B = (size_t)max_batch, H = hidden_dim, S = state_dim, A = action_dim;
     size_t big = H * (H > S ? H : S);
-    size_t n = B * S + B * A + 3 * B + 4 * B * H + 2 * B * A + 2 * B + 2 * B * H + (size_t)h->splits_cap * big;
+    size_t part2 = 32 * ((A + 1) * H + A + 1 > H ? (A + 1) * H + A + 1 : H);
+    size_t n = B * S + B * A + 3 * B + 4 * B * H + 2 * B * A + 2 * B + 2 * B * H + (size_t)h->splits_cap * big + part2;
     cudaError_t ce = cudaMalloc(&h->ws, n * sizeof(float));
     if (ce != cudaSuccess) { hrp_set_error("cudaMalloc(%zu): %s", n * sizeof(float), cudaGetErrorString(ce)); delete h; return -2; }
     float *p = h->ws;
@@ -516,7 +627,8 @@ int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, in
     h->h1 = p; p += B * H; h->h2 = p; p += B * H; h->a1 = p; p += B * H; h->c1 = p; p += B * H;
     h->mean = p; p += B * A; h->dmean = p; p += B * A; h->value = p; p += B; h->dvalue = p; p += B;
     h->d1 = p; p += B * H; h->d2 = p; p += B * H;
-    h->part = p;
+    h->part = p; p += (size_t)h->splits_cap * big;
+    h->part2 = p;
     *out = h;
     return 0;
 }
@@ -599,11 +711,9 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
     const float *x = states, *z = pre_tanh, *olp = old_log_prob, *ad = adv, *rt = ret;
     if (idx) {
         const long long *ix = (const long long *)idx;
-        gather_rows_kernel<<<(unsigned)((B * S + 255) / 256), 256, 0, s>>>(states, ix, h->x, B, S);
-        gather_rows_kernel<<<(unsigned)((B * A + 255) / 256), 256, 0, s>>>(pre_tanh, ix, h->z, B, A);
-        gather_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(old_log_prob, ix, h->olp, B, 1);
-        gather_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(adv, ix, h->adv, B, 1);
-        gather_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(ret, ix, h->ret, B, 1);
+        long long tot = B * (S + A + 3);
+        gather_batch_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(states, pre_tanh, old_log_prob, adv, ret, ix, B,
+                                                                         S, A, h->x, h->z, h->olp, h->adv, h->ret);
         HRP_CUDA_OK(cudaGetLastError());
         x = h->x; z = h->z; olp = h->olp; ad = h->adv; rt = h->ret;
     }
@@ -612,29 +722,35 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
                                        entropy_coef, loss_scale, h->dmean, h->dvalue, grad + L.log_std, metrics);
     HRP_CUDA_OK(cudaGetLastError());
     // heads: dWa2 = dmean^T a1, dba2 = colsum(dmean); dWc2 = dvalue^T c1, dbc2 = sum(dvalue)
-    if (wgrad(h, A, H, B, h->dmean, h->a1, grad + L.wa2, s)) return -2;
-    if (wgrad(h, 1, H, B, h->dvalue, h->c1, grad + L.wc2, s)) return -2;
-    colsum_kernel<<<(A + 31) / 32, 256, 0, s>>>(h->dmean, A, B, A, grad + L.ba2);
-    colsum_kernel<<<1, 256, 0, s>>>(h->dvalue, 1, B, 1, grad + L.bc2);
+    {
+        int chunks = (int)((B + 255) / 256);
+        if (chunks > 32) chunks = 32;
+        int rows_per = (int)((B + chunks - 1) / chunks);
+        dim3 grid((H + 31) / 32, chunks);
+        heads_wgrad_partial_kernel<<<grid, 256, 0, s>>>(h->dmean, h->dvalue, h->a1, h->c1, B, H, A, rows_per, h->part2);
+        int n = A * H + A + H + 1;
+        heads_wgrad_final_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->part2, chunks, H, A, grad + L.wa2, grad + L.wc2);
+        HRP_CUDA_OK(cudaGetLastError());
+    }
     // d(a1), d(c1) into d1, d2 (ReLU masks applied)
     heads_backward_kernel<<<(unsigned)((B * H + 255) / 256), 256, 0, s>>>(h->dmean, h->dvalue, params + L.wa2,
                                                                         params + L.wc2, h->a1, h->c1, B, H, A, h->d1, h->d2);
     HRP_CUDA_OK(cudaGetLastError());
     if (wgrad(h, H, H, B, h->d1, h->h2, grad + L.wa1, s)) return -2;
     if (wgrad(h, H, H, B, h->d2, h->h2, grad + L.wc1, s)) return -2;
-    colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(h->d1, H, B, H, grad + L.ba1);
-    colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(h->d2, H, B, H, grad + L.bc1);
+    if (colsum(h, h->d1, H, B, H, grad + L.ba1, s)) return -2;
+    if (colsum(h, h->d2, H, B, H, grad + L.bc1, s)) return -2;
     // d(h2) = (d(a1) Wa1 + d(c1) Wc1) (.) (h2>0) -> reuse a1 as the destination
     float *dh2 = h->a1;
     if (gemm(false, false, Bi, H, H, h->d1, H, params + L.wa1, H, dh2, H, nullptr, 0, nullptr, 0, 0, 1, s) < 0) return -2;
     if (gemm(false, false, Bi, H, H, h->d2, H, params + L.wc1, H, dh2, H, nullptr, 0, h->h2, H, 1, 1, s) < 0) return -2;
     if (wgrad(h, H, H, B, dh2, h->h1, grad + L.w2, s)) return -2;
-    colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(dh2, H, B, H, grad + L.b2);
+    if (colsum(h, dh2, H, B, H, grad + L.b2, s)) return -2;
     // d(h1) = d(h2) W2 (.) (h1>0) -> c1
     float *dh1 = h->c1;
     if (gemm(false, false, Bi, H, H, dh2, H, params + L.w2, H, dh1, H, nullptr, 0, h->h1, H, 0, 1, s) < 0) return -2;
     if (wgrad(h, H, S, B, dh1, x, grad + L.w1, s)) return -2;
-    colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(dh1, H, B, H, grad + L.b1);
+    if (colsum(h, dh1, H, B, H, grad + L.b1, s)) return -2;
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }

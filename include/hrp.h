@@ -155,6 +155,16 @@ int hrp_embed_apply(int32_t kind, int32_t embed_dim, int32_t use_euclidean, int3
  *      actor_mean.2.*, critic.0.*, critic.2.*; nn.Linear weights row-major [out,in].
  *      hrp_ppo_param_count gives P. */
 int64_t hrp_ppo_param_count(int32_t state_dim, int32_t action_dim, int32_t hidden_dim);
+/* arithmetic of the hidden-layer GEMMs (process-wide): 3 = tcgen05 tensor cores, 3xTF32 split (fp32-grade
+ * accuracy; default), 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA-core GEMM.  torch's nn.Linear in the
+ * reference is fp32 (ppo/agent.py:22-42). */
+int hrp_ppo_set_math(int32_t mode);
+int hrp_ppo_get_math(void);
+/* the dense contraction behind every nn.Linear of the path, on the tcgen05 tensor cores:
+ * C[M,N] = act(sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] + bias[n]); mode 1 = TF32, 3 = 3xTF32. */
+int hrp_gemm_strided(int32_t M, int32_t N, int32_t K, const float *A_dev, int64_t sam, int64_t sak,
+                     const float *B_dev, int64_t sbn, int64_t sbk, float *C_dev, int32_t ldc,
+                     const float *bias_dev, int32_t relu, int32_t mode, void *stream);
 
 typedef struct hrp_ppo hrp_ppo;
 /* workspace for batches up to max_batch rows */
