@@ -15,7 +15,8 @@
 //     (the dropped Alo*Blo term is ~2^-22 relative) -- the MMA time is negligible for these shapes;
 //   * tiles are staged global -> registers -> shared memory in the canonical K-major SWIZZLE_128B layout
 //     (8-row x 128-byte atoms, 16-byte chunk index XOR row%8), software-pipelined one K-block ahead,
-//     3 shared-memory stages recycled through mbarriers signalled by tcgen05.commit;
+//     2 (3xTF32) or 4 (TF32) shared-memory stages recycled through mbarriers signalled by tcgen05.commit,
+//     sized so that two CTAs are resident per SM and overlap each other's load and MMA phases;
 //   * one elected thread issues the tcgen05.mma instructions (UMMA 128 x 128 x 8); the accumulator lives in
 //     128 TMEM columns; the epilogue reads it with tcgen05.ld (32 lanes x 32 columns per warp).
 // Plain ld.global staging (no TMA) is deliberate: the weight matrices live at 8-byte-aligned offsets of the
@@ -108,7 +109,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;                  // hi (+ lo) copy of every operand tile
     constexpr int B_TILE_BYTES = BN * BK * 4;
     constexpr int STAGE_BYTES = PARTS * (A_TILE_BYTES + B_TILE_BYTES);
-    constexpr int STAGES = NSPLIT == 3 ? 3 : 4;
+    constexpr int STAGES = NSPLIT == 3 ? 2 : 4;                 // <= 96 KB per CTA: two CTAs share an SM
     constexpr int B_ITERS = BN * BK / TC_THREADS;               // elements of B staged per thread and K-block
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar_empty[4], bar_done;
@@ -272,7 +273,7 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
            const float *mask, int ldm, int accumulate, int k_chunk)
 {
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;
-    constexpr int STAGES = NSPLIT == 3 ? 3 : 4;
+    constexpr int STAGES = NSPLIT == 3 ? 2 : 4;
     constexpr int OPERANDS = STAGES * PARTS * (A_TILE_BYTES + BN * BK * 4);
     constexpr int EPILOGUE = BM * (BN + 1) * 4;
     constexpr int SMEM = (OPERANDS > EPILOGUE ? OPERANDS : EPILOGUE) + 1024;

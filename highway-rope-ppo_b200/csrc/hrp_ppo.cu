@@ -496,7 +496,7 @@ struct hrp_ppo {
     float *mean, *value, *dmean, *dvalue;    // heads and their gradients
     float *d1, *d2;                          // activation gradients [B,H]
     float *part;                             // split-K partials
-    float *part2;                            // column-sum / head-gradient partials (32 chunks)
+    float *part2;                            // column-sum / head-gradient partials (<= 64 chunks)
     int splits_cap;
 };
 
@@ -532,7 +532,7 @@ static int gemm(bool AT, bool BT, int M, int N, int K, const float *A, int lda, 
 // weight gradient dW[N,K] = dY[B,N]^T X[B,K], split over B, deterministic
 static int wgrad(hrp_ppo *h, int N, int K, long long B, const float *dY, const float *X, float *dW, cudaStream_t s)
 {
-    int splits = (int)((B + 511) / 512);
+    int splits = (int)((B + 255) / 256);
     if (splits > h->splits_cap) splits = h->splits_cap;
     if (splits <= 1) {
         int rc = gemm(true, false, N, K, (int)B, dY, N, X, K, dW, K, nullptr, 0, nullptr, 0, 0, 1, s);
@@ -549,8 +549,8 @@ static int wgrad(hrp_ppo *h, int N, int K, long long B, const float *dY, const f
 // bias gradient db[N] = column sums of G[B, N], deterministic two-stage
 static int colsum(hrp_ppo *h, const float *G, int ldg, long long B, int N, float *out, cudaStream_t s)
 {
-    int chunks = (int)((B + 255) / 256);
-    if (chunks > 32) chunks = 32;
+    int chunks = (int)((B + 63) / 64);
+    if (chunks > 64) chunks = 64;
     if (chunks < 1) chunks = 1;
     int rows_per = (int)((B + chunks - 1) / chunks);
     dim3 grid((N + 31) / 32, chunks);
@@ -618,7 +618,7 @@ int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, in
     h->splits_cap = 32;
     size_t B = (size_t)max_batch, H = hidden_dim, S = state_dim, A = action_dim;
     size_t big = H * (H > S ? H : S);
-    size_t part2 = 32 * ((A + 1) * H + A + 1 > H ? (A + 1) * H + A + 1 : H);
+    size_t part2 = 64 * ((A + 1) * H + A + 1 > H ? (A + 1) * H + A + 1 : H);
     size_t n = B * S + B * A + 3 * B + 4 * B * H + 2 * B * A + 2 * B + 2 * B * H + (size_t)h->splits_cap * big + part2;
     cudaError_t ce = cudaMalloc(&h->ws, n * sizeof(float));
     if (ce != cudaSuccess) { hrp_set_error("cudaMalloc(%zu): %s", n * sizeof(float), cudaGetErrorString(ce)); delete h; return -2; }
@@ -723,8 +723,8 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
     HRP_CUDA_OK(cudaGetLastError());
     // heads: dWa2 = dmean^T a1, dba2 = colsum(dmean); dWc2 = dvalue^T c1, dbc2 = sum(dvalue)
     {
-        int chunks = (int)((B + 255) / 256);
-        if (chunks > 32) chunks = 32;
+        int chunks = (int)((B + 63) / 64);
+        if (chunks > 64) chunks = 64;
         int rows_per = (int)((B + chunks - 1) / chunks);
         dim3 grid((H + 31) / 32, chunks);
         heads_wgrad_partial_kernel<<<grid, 256, 0, s>>>(h->dmean, h->dvalue, h->a1, h->c1, B, H, A, rows_per, h->part2);

@@ -28,6 +28,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
+from . import distributed
 
 _PARAM_ORDER = ("log_std", "shared.0.weight", "shared.0.bias", "shared.2.weight", "shared.2.bias",
                 "actor_mean.0.weight", "actor_mean.0.bias", "actor_mean.2.weight", "actor_mean.2.bias",
@@ -414,17 +415,13 @@ class PPOAgent:
         self.launches += 1
         return self.actor_critic.act(states, noise=noise, deterministic=deterministic, out=out)
 
-    # -- distributed helpers ---------------------------------------------------------------------
+    # -- distributed helpers (ppo/distributed.py) ---------------------------------------------------
     @staticmethod
     def _world() -> int:
-        import torch.distributed as dist
-
-        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        return distributed.world_size()
 
     def _allreduce(self, t: torch.Tensor) -> None:
-        import torch.distributed as dist
-
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        distributed.allreduce_sum_(t)
 
     # -- one optimizer step on minibatch ``idx`` (device int64) ----------------------------------
     def _minibatch_step(self, flat: Dict[str, torch.Tensor], idx: Optional[torch.Tensor], B: int, world: int) -> None:
@@ -432,7 +429,7 @@ class PPOAgent:
         _lib.check(self._lib.hrp_ppo_loss_grad(
             ac._h, ac.flat.data_ptr(), flat["states"].data_ptr(), flat["pre_tanh"].data_ptr(),
             flat["log_prob"].data_ptr(), flat["adv"].data_ptr(), flat["ret"].data_ptr(), _lib.ptr(idx), B,
-            float(self.eps_clip), float(self.value_coef), float(self.entropy_coef), 1.0 / (B * world),
+            float(self.eps_clip), float(self.value_coef), float(self.entropy_coef), distributed.loss_scale(B, world),
             self.grad.data_ptr(), self._metrics.data_ptr(), s), "hrp_ppo_loss_grad")
         if world > 1:
             self._allreduce(self.grad)
