@@ -89,17 +89,134 @@ __device__ __forceinline__ uint32_t swz(int r, int k)
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + ((k & 3) << 2));
 }
 
-// A tile element this thread stages at step i: K-contiguous operands walk k fastest (coalesced 128 B rows),
-// MN-contiguous operands walk the row fastest.
-template <bool KCONTIG, int ROWS>
-__device__ __forceinline__ void tile_coord(int i, int tid, int &r, int &k)
-{
-    int idx = tid + i * TC_THREADS;
-    if (KCONTIG) { r = idx >> 5; k = idx & 31; }
-    else { r = idx & (ROWS - 1); k = idx / ROWS; }
-}
+// ---- operand staging: global -> registers (fetch) -> swizzled shared tile(s) (stash) --------------------------
+// MODE 0: scalar, K-contiguous (a warp reads one 128-byte row)      1: scalar, MN-contiguous (32 rows at one k)
+// MODE 2: 16-byte vectors along K (needs 16 B alignment)           3: 8-byte vectors along K (flat-buffer weights)
+// MODE 4: 16-byte vectors along MN (4 rows at one k; batch-major operands of the weight gradient)
+enum { ST_K1 = 0, ST_MN1 = 1, ST_K4 = 2, ST_K2 = 3, ST_MN4 = 4 };
 
-template <bool A_KC, bool B_KC, int NSPLIT, int BN>
+template <int MODE, int ROWS>
+struct Stager {
+    static constexpr int ELEMS = ROWS * BK / TC_THREADS;   // fp32 values per thread and K-block
+    float v[ELEMS];
+
+    // P(row, k) = P[row * srow + k * sk]; rows >= nrows and k >= kend read as zero
+    __device__ __forceinline__ void fetch(const float *__restrict__ P, long long srow, long long sk, int row0,
+                                          int nrows, int k0, int kend, int tid)
+    {
+        if (MODE == ST_K1 || MODE == ST_MN1) {
+#pragma unroll
+            for (int i = 0; i < ELEMS; ++i) {
+                int idx = tid + i * TC_THREADS;
+                int r = MODE == ST_K1 ? idx >> 5 : idx & (ROWS - 1);
+                int k = MODE == ST_K1 ? idx & 31 : idx / ROWS;
+                int gr = row0 + r, gk = k0 + k;
+                v[i] = (gr < nrows && gk < kend) ? __ldg(P + (long long)gr * srow + (long long)gk * sk) : 0.f;
+            }
+        } else if (MODE == ST_K4) {
+#pragma unroll
+            for (int i = 0; i < ELEMS / 4; ++i) {
+                int idx = tid + i * TC_THREADS;
+                int r = idx >> 3, k = (idx & 7) * 4;
+                int gr = row0 + r, gk = k0 + k;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gr < nrows && gk < kend) t = __ldg(reinterpret_cast<const float4 *>(P + (long long)gr * srow + gk));
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
+        } else if (MODE == ST_K2) {
+#pragma unroll
+            for (int i = 0; i < ELEMS / 2; ++i) {
+                int idx = tid + i * TC_THREADS;
+                int r = idx >> 4, k = (idx & 15) * 2;
+                int gr = row0 + r, gk = k0 + k;
+                float2 t = make_float2(0.f, 0.f);
+                if (gr < nrows && gk < kend) t = __ldg(reinterpret_cast<const float2 *>(P + (long long)gr * srow + gk));
+                v[2 * i] = t.x; v[2 * i + 1] = t.y;
+            }
+        } else {  // ST_MN4
+#pragma unroll
+            for (int i = 0; i < ELEMS / 4; ++i) {
+                int idx = tid + i * TC_THREADS;
+                int r = (idx % (ROWS / 4)) * 4, k = idx / (ROWS / 4);
+                int gr = row0 + r, gk = k0 + k;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gr < nrows && gk < kend) t = __ldg(reinterpret_cast<const float4 *>(P + (long long)gk * sk + gr));
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
+        }
+    }
+
+    template <int NSPLIT>
+    __device__ __forceinline__ void put(uint8_t *hi_tile, int part_bytes, uint32_t o, float x) const
+    {
+        if (NSPLIT == 3) {
+            float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            *(float *)(hi_tile + o) = hi;
+            *(float *)(hi_tile + part_bytes + o) = x - hi;
+        } else {
+            *(float *)(hi_tile + o) = x;
+        }
+    }
+
+    // hi part at hi_tile, lo part (3xTF32) at hi_tile + part_bytes
+    template <int NSPLIT>
+    __device__ __forceinline__ void stash(uint8_t *hi_tile, int part_bytes, int tid) const
+    {
+        if (MODE == ST_K1 || MODE == ST_MN1) {
+#pragma unroll
+            for (int i = 0; i < ELEMS; ++i) {
+                int idx = tid + i * TC_THREADS;
+                int r = MODE == ST_K1 ? idx >> 5 : idx & (ROWS - 1);
+                int k = MODE == ST_K1 ? idx & 31 : idx / ROWS;
+                put<NSPLIT>(hi_tile, part_bytes, swz(r, k), v[i]);
+            }
+        } else if (MODE == ST_K4) {
+#pragma unroll
+            for (int i = 0; i < ELEMS / 4; ++i) {
+                int idx = tid + i * TC_THREADS;
+                uint32_t o = swz(idx >> 3, (idx & 7) * 4);   // one whole 16-byte chunk
+                float4 x = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                if (NSPLIT == 3) {
+                    float4 h;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    *(float4 *)(hi_tile + o) = h;
+                    *(float4 *)(hi_tile + part_bytes + o) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                } else {
+                    *(float4 *)(hi_tile + o) = x;
+                }
+            }
+        } else if (MODE == ST_K2) {
+#pragma unroll
+            for (int i = 0; i < ELEMS / 2; ++i) {
+                int idx = tid + i * TC_THREADS;
+                uint32_t o = swz(idx >> 4, (idx & 15) * 2);  // half of a 16-byte chunk
+                float2 x = make_float2(v[2 * i], v[2 * i + 1]);
+                if (NSPLIT == 3) {
+                    float2 h;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    *(float2 *)(hi_tile + o) = h;
+                    *(float2 *)(hi_tile + part_bytes + o) = make_float2(x.x - h.x, x.y - h.y);
+                } else {
+                    *(float2 *)(hi_tile + o) = x;
+                }
+            }
+        } else {  // ST_MN4: four rows at one k
+#pragma unroll
+            for (int i = 0; i < ELEMS / 4; ++i) {
+                int idx = tid + i * TC_THREADS;
+                int r = (idx % (ROWS / 4)) * 4, k = idx / (ROWS / 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) put<NSPLIT>(hi_tile, part_bytes, swz(r + j, k), v[4 * i + j]);
+            }
+        }
+    }
+};
+
+template <int AMODE, int BMODE, int NSPLIT, int BN>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, long long sak,
                const float *__restrict__ B, long long sbn, long long sbk, float *__restrict__ C, int ldc,
@@ -110,7 +227,6 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     constexpr int B_TILE_BYTES = BN * BK * 4;
     constexpr int STAGE_BYTES = PARTS * (A_TILE_BYTES + B_TILE_BYTES);
     constexpr int STAGES = NSPLIT == 3 ? 2 : 4;                 // <= 96 KB per CTA: two CTAs share an SM
-    constexpr int B_ITERS = BN * BK / TC_THREADS;               // elements of B staged per thread and K-block
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar_empty[4], bar_done;
     __shared__ uint32_t tmem_base_s;
@@ -138,77 +254,37 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     const uint32_t tmem_d = tmem_base_s;
     constexpr uint32_t idesc = make_idesc(BM, BN);
 
-    // register staging of the next K-block: 16 elements of A and BN/8 of B per thread
-    float ra[16], rb[B_ITERS];
-    auto fetch = [&](int kb) {
-        const int k0 = kbeg + kb * BK;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            int r, k;
-            tile_coord<A_KC, BM>(i, tid, r, k);
-            int gm = m0 + r, gk = k0 + k;
-            ra[i] = (gm < M && gk < kend) ? __ldg(A + (long long)gm * sam + (long long)gk * sak) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < B_ITERS; ++i) {
-            int r, k;
-            tile_coord<B_KC, BN>(i, tid, r, k);
-            int gn = n0 + r, gk = k0 + k;
-            rb[i] = (gn < N && gk < kend) ? __ldg(B + (long long)gn * sbn + (long long)gk * sbk) : 0.f;
-        }
-    };
-    auto stash = [&](int s) {
-        uint8_t *a_hi = smem + s * STAGE_BYTES, *b_hi = a_hi + PARTS * A_TILE_BYTES;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            int r, k;
-            tile_coord<A_KC, BM>(i, tid, r, k);
-            uint32_t o = swz(r, k);
-            if (NSPLIT == 3) {
-                float hi = __uint_as_float(__float_as_uint(ra[i]) & 0xFFFFE000u);
-                *(float *)(a_hi + o) = hi;
-                *(float *)(a_hi + A_TILE_BYTES + o) = ra[i] - hi;
-            } else {
-                *(float *)(a_hi + o) = ra[i];
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < B_ITERS; ++i) {
-            int r, k;
-            tile_coord<B_KC, BN>(i, tid, r, k);
-            uint32_t o = swz(r, k);
-            if (NSPLIT == 3) {
-                float hi = __uint_as_float(__float_as_uint(rb[i]) & 0xFFFFE000u);
-                *(float *)(b_hi + o) = hi;
-                *(float *)(b_hi + B_TILE_BYTES + o) = rb[i] - hi;
-            } else {
-                *(float *)(b_hi + o) = rb[i];
-            }
-        }
-    };
-
-    if (nkb > 0) fetch(0);
-    for (int kb = 0; kb < nkb; ++kb) {
+    // register staging, software-pipelined TWO K-blocks ahead (two register sets): these GEMMs are short
+    // (K <= 512 per CTA), so the exposed global-load latency per K-block is what bounds them
+    Stager<AMODE, BM> sa0, sa1;
+    Stager<BMODE, BN> sb0, sb1;
+    auto step = [&](int kb, Stager<AMODE, BM> &sa, Stager<BMODE, BN> &sb) {
         const int s = kb % STAGES;
         if (kb >= STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((kb / STAGES) - 1) & 1));  // MMAs of kb - STAGES retired
-        stash(s);
-        if (kb + 1 < nkb) fetch(kb + 1);                 // in flight while this block's MMAs are issued
+        uint8_t *a_hi = smem + s * STAGE_BYTES, *b_hi = a_hi + PARTS * A_TILE_BYTES;
+        sa.template stash<NSPLIT>(a_hi, A_TILE_BYTES, tid);
+        sb.template stash<NSPLIT>(b_hi, B_TILE_BYTES, tid);
+        if (kb + 2 < nkb) {                                 // refill this register set: in flight for two blocks
+            const int k0 = kbeg + (kb + 2) * BK;
+            sa.fetch(A, sam, sak, m0, M, k0, kend, tid);
+            sb.fetch(B, sbn, sbk, n0, N, k0, kend, tid);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
         __syncthreads();
         if (warp == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + PARTS * A_TILE_BYTES;
+                const uint32_t a_s = smem_u32(a_hi), b_s = smem_u32(b_hi);
 #pragma unroll
                 for (int kk = 0; kk < BK / 8; ++kk) {       // UMMA_K = 8 tf32 = 32 bytes: advance the start address
                     const uint32_t off = kk * 32;
                     const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
                     if (NSPLIT == 3) {
-                        umma_tf32(tmem_d, make_desc(a_hi + A_TILE_BYTES + off), make_desc(b_hi + off), idesc, acc);
-                        umma_tf32(tmem_d, make_desc(a_hi + off), make_desc(b_hi + B_TILE_BYTES + off), idesc, 1u);
-                        umma_tf32(tmem_d, make_desc(a_hi + off), make_desc(b_hi + off), idesc, 1u);
+                        umma_tf32(tmem_d, make_desc(a_s + A_TILE_BYTES + off), make_desc(b_s + off), idesc, acc);
+                        umma_tf32(tmem_d, make_desc(a_s + off), make_desc(b_s + B_TILE_BYTES + off), idesc, 1u);
+                        umma_tf32(tmem_d, make_desc(a_s + off), make_desc(b_s + off), idesc, 1u);
                     } else {
-                        umma_tf32(tmem_d, make_desc(a_hi + off), make_desc(b_hi + off), idesc, acc);
+                        umma_tf32(tmem_d, make_desc(a_s + off), make_desc(b_s + off), idesc, acc);
                     }
                 }
                 umma_commit(&bar_empty[s]);                 // frees the stage when these MMAs have read it
@@ -216,6 +292,18 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
             }
             __syncwarp();
         }
+    };
+    if (nkb > 0) {
+        sa0.fetch(A, sam, sak, m0, M, kbeg, kend, tid);
+        sb0.fetch(B, sbn, sbk, n0, N, kbeg, kend, tid);
+    }
+    if (nkb > 1) {
+        sa1.fetch(A, sam, sak, m0, M, kbeg + BK, kend, tid);
+        sb1.fetch(B, sbn, sbk, n0, N, kbeg + BK, kend, tid);
+    }
+    for (int kb = 0; kb < nkb; kb += 2) {
+        step(kb, sa0, sb0);
+        if (kb + 1 < nkb) step(kb + 1, sa1, sb1);
     }
 
     // ---- epilogue: TMEM -> registers -> shared (row-major, padded) -> coalesced global rows.
@@ -267,7 +355,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
 }
 
-template <bool A_KC, bool B_KC, int NSPLIT, int BN>
+template <int AMODE, int BMODE, int NSPLIT, int BN>
 int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
            const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias, int relu,
            const float *mask, int ldm, int accumulate, int k_chunk)
@@ -278,7 +366,7 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
     constexpr int EPILOGUE = BM * (BN + 1) * 4;
     constexpr int SMEM = (OPERANDS > EPILOGUE ? OPERANDS : EPILOGUE) + 1024;
     static bool configured = false;
-    auto kern = tc_gemm_kernel<A_KC, B_KC, NSPLIT, BN>;
+    auto kern = tc_gemm_kernel<AMODE, BMODE, NSPLIT, BN>;
     if (!configured) {
         HRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
@@ -289,16 +377,18 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
     return 0;
 }
 
-template <bool A_KC, bool B_KC>
+template <int AMODE, int BMODE>
 int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
              long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
              int relu, const float *mask, int ldm, int accumulate, int k_chunk)
 {
 #define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk
-    if (bn == 64) return nsplit == 3 ? launch<A_KC, B_KC, 3, 64>(HRP_TC_ARGS) : launch<A_KC, B_KC, 1, 64>(HRP_TC_ARGS);
-    return nsplit == 3 ? launch<A_KC, B_KC, 3, 128>(HRP_TC_ARGS) : launch<A_KC, B_KC, 1, 128>(HRP_TC_ARGS);
+    if (bn == 64) return nsplit == 3 ? launch<AMODE, BMODE, 3, 64>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 64>(HRP_TC_ARGS);
+    return nsplit == 3 ? launch<AMODE, BMODE, 3, 128>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 128>(HRP_TC_ARGS);
 #undef HRP_TC_ARGS
 }
+
+inline bool aligned(const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; }
 
 }  // namespace
 
@@ -320,10 +410,20 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     const int bn = (N <= 64 || mt * ((N + 127) / 128) * splits < 120) ? 64 : 128;
     dim3 grid((N + bn - 1) / bn, mt, splits);
     const bool akc = sak == 1, bkc = sbk == 1;
+    // vectorised staging where strides and base addresses allow it
+    const bool a_k4 = akc && K % 4 == 0 && sam % 4 == 0 && aligned(A, 16);
+    const bool b_k2 = bkc && K % 2 == 0 && sbn % 2 == 0 && aligned(B, 8);
+    const bool a_mn4 = sam == 1 && M % 4 == 0 && sak % 4 == 0 && aligned(A, 16);
+    const bool b_mn4 = sbn == 1 && N % 4 == 0 && sbk % 4 == 0 && aligned(B, 16);
+#define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk)
     int rc;
-    if (akc && bkc) rc = dispatch<true, true>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
-    else if (akc) rc = dispatch<true, false>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
-    else if (bkc) rc = dispatch<false, true>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
-    else rc = dispatch<false, false>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    if (a_k4 && b_k2) rc = HRP_TC_GO(ST_K4, ST_K2);
+    else if (a_k4 && sbn == 1) rc = HRP_TC_GO(ST_K4, ST_MN1);
+    else if (a_mn4 && b_mn4) rc = HRP_TC_GO(ST_MN4, ST_MN4);
+    else if (akc && bkc) rc = HRP_TC_GO(ST_K1, ST_K1);
+    else if (akc) rc = HRP_TC_GO(ST_K1, ST_MN1);
+    else if (bkc) rc = HRP_TC_GO(ST_MN1, ST_K1);
+    else rc = HRP_TC_GO(ST_MN1, ST_MN1);
+#undef HRP_TC_GO
     return rc < 0 ? rc : splits;
 }

@@ -404,6 +404,8 @@ class PPOAgent:
         self._metrics = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._stats = torch.zeros(3 + 512, dtype=torch.float64, device=self.device)
         self.launches = 0  # hrp_* calls enqueued by this agent (each is >= 1 kernel of this library)
+        self.use_cuda_graphs = True
+        self._graph_state: Optional[Dict[str, Any]] = None
 
     # -- acting ----------------------------------------------------------------------------------
     def select_action(self, state, deterministic: bool = False):
@@ -439,6 +441,44 @@ class PPOAgent:
             float(self.max_grad_norm), opt.scratch.data_ptr(), s), "hrp_clip_adam_step")
         self.launches += 2
 
+    # -- the epochs x minibatches loop as CUDA graphs --------------------------------------------------
+    def _graphed_epochs(self, flat: Dict[str, torch.Tensor], perm_dev: torch.Tensor, n: int, bs: int) -> None:
+        """One CUDA graph per minibatch (the ~40 launches of loss/backward/clip/Adam), replayed for every epoch
+        and re-used by later updates of the same size.  The rollout is first copied into persistent buffers so
+        that the captured pointers stay valid.  The first epoch of a new configuration runs eagerly (it also
+        warms every kernel variant before anything is captured)."""
+        ac = self.actor_critic
+        key = (n, bs, ac._h.value, float(self.eps_clip), float(self.value_coef), float(self.entropy_coef),
+               float(self.max_grad_norm), self.optimizer.lr, self.optimizer.betas, self.optimizer.eps)
+        st = self._graph_state
+        if st is None or st["key"] != key:
+            d = self.device
+            st = {"key": key, "graphs": {}, "warm": False,
+                  "buf": {k: torch.empty_like(v) for k, v in flat.items()},
+                  "perm": torch.empty(n, dtype=torch.int64, device=d)}
+            self._graph_state = st
+        for k, v in flat.items():
+            st["buf"][k].copy_(v)
+        st["perm"].copy_(perm_dev)
+        starts = list(range(0, n, bs))
+        for epoch in range(self.epochs):
+            if not st["warm"]:
+                for start in starts:
+                    B = min(bs, n - start)
+                    self._minibatch_step(st["buf"], st["perm"][start:start + B], B, 1)
+                st["warm"] = True
+                continue
+            for i, start in enumerate(starts):
+                g = st["graphs"].get(i)
+                if g is None:
+                    B = min(bs, n - start)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._minibatch_step(st["buf"], st["perm"][start:start + B], B, 1)
+                    st["graphs"][i] = g
+                g.replay()
+                self.launches += 2
+
     # -- PPOAgent.update (agent.py:196-308) --------------------------------------------------------
     def update(self, last_value=0.0) -> Dict[str, float]:
         mem, ac = self.memory, self.actor_critic
@@ -466,10 +506,13 @@ class PPOAgent:
         bs = int(mem.batch_size)
         ac._ensure_workspace(min(bs, n))
         self._metrics.zero_()
-        for _ in range(self.epochs):
-            for start in range(0, n, bs):
-                B = min(bs, n - start)
-                self._minibatch_step(flat, perm_dev[start:start + B], B, world)
+        if self.use_cuda_graphs and world == 1:
+            self._graphed_epochs(flat, perm_dev, n, bs)
+        else:
+            for _ in range(self.epochs):
+                for start in range(0, n, bs):
+                    B = min(bs, n - start)
+                    self._minibatch_step(flat, perm_dev[start:start + B], B, world)
         # explained variance of the value predictions (agent.py:276-285)
         y_pred, y_true = r["value"].reshape(n), ret.view(n)
         if world > 1:
