@@ -58,6 +58,20 @@ __device__ __forceinline__ float wrap_to_pi(float x)
     if (x >= -kPi && x < kPi) return x;
     return x - 2.f * kPi * floorf((x + kPi) / (2.f * kPi));
 }
+// sin and cos of a heading: traffic headings are a few tenths of a radian, where the Taylor polynomials
+// (|error| < 3e-10 for |x| <= 0.5) are exact to fp32 rounding; anything larger takes the library path
+__device__ __forceinline__ void sincos_heading(float x, float *s, float *c)
+{
+    if (fabsf(x) <= 0.5f) {
+        float x2 = x * x;
+        float ps = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.f);
+        float pc = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.f);
+        *s = x * ps;
+        *c = pc;
+    } else {
+        sincosf(x, s, c);
+    }
+}
 __device__ __forceinline__ int slot_front(ull mask, int p)
 {
     ull m = mask & ~((2ull << p) - 1ull);
@@ -89,7 +103,7 @@ __device__ __forceinline__ float desired_gap(const WarpS &S, int e, int f)
 // COMFORT_ACC_MAX * (1 - (max(v,0)/|not_zero(v0)|)^delta); v0 already clipped to [0, 30]
 __device__ __forceinline__ float idm_free(float v, float v0, float delta)
 {
-    float r = fmaxf(v, 0.f) / fabsf(nzf(v0));
+    float r = __fdividef(fmaxf(v, 0.f), fabsf(nzf(v0)));  // <= 2 ulp; the result goes through exp2/log2 anyway
     float p = r > 0.f ? exp2f(delta * __log2f(r)) : 0.f;
     return 3.f * (1.f - p);
 }
@@ -97,7 +111,7 @@ __device__ __forceinline__ float idm_free(float v, float v0, float delta)
 __device__ __forceinline__ float idm_interaction(const WarpS &S, int e, int f)
 {
     float d = S.xr[f] - S.xr[e];
-    float g = desired_gap(S, e, f) / nzf(d);
+    float g = __fdividef(desired_gap(S, e, f), nzf(d));
     return 3.f * g * g;
 }
 
@@ -270,7 +284,7 @@ __device__ void load_env(const EnvDev &P, WarpS &S, Veh (&u)[2], int e, int lane
             uint32_t f = P.flags[base + k];
             w.lane = f & 0xff; w.tlane = (f >> 8) & 0xff;
             w.crashed = (f >> 16) & 1; w.has_impact = (f >> 17) & 1;
-            sincosf(w.h, &w.sh, &w.ch);
+            sincos_heading(w.h, &w.sh, &w.ch);
             w.acc = 0.f; w.tb = 0.f;
             publish(S, w, k, xref);
         }
@@ -676,7 +690,7 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
         w.h += w.v * sb / 2.5f * dt;
         w.v += w.acc * dt;
         w.lane = closest_lane(w.y, P.lanes);
-        sincosf(w.h, &w.sh, &w.ch);
+        sincos_heading(w.h, &w.sh, &w.ch);
         S.x[k] = w.x; S.xr[k] = (float)(w.x - xref);
         S.y[k] = w.y; S.v[k] = w.v; S.ch[k] = w.ch; S.sh[k] = w.sh;
         S.lane[k] = (unsigned char)w.lane;

@@ -100,6 +100,26 @@ struct Stager {
     static constexpr int ELEMS = ROWS * BK / TC_THREADS;   // fp32 values per thread and K-block
     float v[ELEMS];
 
+    // scalar element of thread-slot idx.  K-contiguous: a warp covers one 128-byte row (coalesced, and the 32
+    // words of a swizzled row hit 32 banks).  MN-contiguous: a warp covers 8 rows x 4 k -- four fully used
+    // 32-byte sectors in global memory, and (chunk ^ row%8, k%4) is a bijection onto the 32 banks.
+    static __device__ __forceinline__ void coord1(int idx, int &r, int &k)
+    {
+        if (MODE == ST_K1) { r = idx >> 5; k = idx & 31; }
+        else {
+            int lane = idx & 31, unit = idx >> 5;
+            r = (unit % (ROWS / 8)) * 8 + (lane >> 2);
+            k = (unit / (ROWS / 8)) * 4 + (lane & 3);
+        }
+    }
+    // 4-row vector of thread-slot idx (ST_MN4): lane <-> k, so that each of the four scalar shared-memory
+    // stores of a warp goes to 32 different banks (k/4 ^ const covers the 8 chunks, k%4 the words)
+    static __device__ __forceinline__ void coord_mn4(int idx, int &r, int &k)
+    {
+        k = idx & 31;
+        r = (idx >> 5) * 4;
+    }
+
     // P(row, k) = P[row * srow + k * sk]; rows >= nrows and k >= kend read as zero
     __device__ __forceinline__ void fetch(const float *__restrict__ P, long long srow, long long sk, int row0,
                                           int nrows, int k0, int kend, int tid)
@@ -107,9 +127,8 @@ struct Stager {
         if (MODE == ST_K1 || MODE == ST_MN1) {
 #pragma unroll
             for (int i = 0; i < ELEMS; ++i) {
-                int idx = tid + i * TC_THREADS;
-                int r = MODE == ST_K1 ? idx >> 5 : idx & (ROWS - 1);
-                int k = MODE == ST_K1 ? idx & 31 : idx / ROWS;
+                int r, k;
+                coord1(tid + i * TC_THREADS, r, k);
                 int gr = row0 + r, gk = k0 + k;
                 v[i] = (gr < nrows && gk < kend) ? __ldg(P + (long long)gr * srow + (long long)gk * sk) : 0.f;
             }
@@ -136,8 +155,8 @@ struct Stager {
         } else {  // ST_MN4
 #pragma unroll
             for (int i = 0; i < ELEMS / 4; ++i) {
-                int idx = tid + i * TC_THREADS;
-                int r = (idx % (ROWS / 4)) * 4, k = idx / (ROWS / 4);
+                int r, k;
+                coord_mn4(tid + i * TC_THREADS, r, k);
                 int gr = row0 + r, gk = k0 + k;
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (gr < nrows && gk < kend) t = __ldg(reinterpret_cast<const float4 *>(P + (long long)gk * sk + gr));
@@ -165,9 +184,8 @@ struct Stager {
         if (MODE == ST_K1 || MODE == ST_MN1) {
 #pragma unroll
             for (int i = 0; i < ELEMS; ++i) {
-                int idx = tid + i * TC_THREADS;
-                int r = MODE == ST_K1 ? idx >> 5 : idx & (ROWS - 1);
-                int k = MODE == ST_K1 ? idx & 31 : idx / ROWS;
+                int r, k;
+                coord1(tid + i * TC_THREADS, r, k);
                 put<NSPLIT>(hi_tile, part_bytes, swz(r, k), v[i]);
             }
         } else if (MODE == ST_K4) {
@@ -207,8 +225,8 @@ struct Stager {
         } else {  // ST_MN4: four rows at one k
 #pragma unroll
             for (int i = 0; i < ELEMS / 4; ++i) {
-                int idx = tid + i * TC_THREADS;
-                int r = (idx % (ROWS / 4)) * 4, k = idx / (ROWS / 4);
+                int r, k;
+                coord_mn4(tid + i * TC_THREADS, r, k);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) put<NSPLIT>(hi_tile, part_bytes, swz(r + j, k), v[4 * i + j]);
             }
@@ -337,17 +355,24 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     }
     __syncthreads();
     float *Cz = C + (size_t)blockIdx.z * M * ldc;
-    for (int idx = tid; idx < BM * BN; idx += TC_THREADS) {
-        const int r = idx / BN, c = idx - r * BN;
-        const int gm = m0 + r, gn = n0 + c;
-        if (gm >= M || gn >= N) continue;
-        const size_t o = (size_t)gm * ldc + gn;
-        float x = stage_c[r * LDS + c];
-        if (accumulate) x += Cz[o];
-        if (bias) x += bias[gn];
-        if (relu) x = fmaxf(x, 0.f);
-        if (mask) x = mask[(size_t)gm * ldm + gn] > 0.f ? x : 0.f;
-        Cz[o] = x;
+    {
+        // thread t always writes column t % BN: its bias is loaded once; rows advance by TC_THREADS / BN
+        constexpr int RSTEP = TC_THREADS / BN;
+        const int c = tid % BN, gn = n0 + c;
+        const float bv = (bias && gn < N) ? bias[gn] : 0.f;
+        if (gn < N) {
+#pragma unroll 4
+            for (int r = tid / BN; r < BM; r += RSTEP) {
+                const int gm = m0 + r;
+                if (gm >= M) break;
+                const size_t o = (size_t)gm * ldc + gn;
+                float x = stage_c[r * LDS + c] + bv;
+                if (accumulate) x += Cz[o];
+                if (relu) x = fmaxf(x, 0.f);
+                if (mask) x = mask[(size_t)gm * ldm + gn] > 0.f ? x : 0.f;
+                Cz[o] = x;
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
