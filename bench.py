@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 METRIC = "policy env-steps/s (4096 envs/GPU)"
 UNIT = "env-steps/s"
 OVERRIDE = {"observation": {"order": "shuffled"}}
-KERNELS_PER_ACT = 6   # 4 x sgemm (trunk 2, actor 1, critic 1) + heads + act
+KERNELS_PER_ACT = 5   # 4 x tcgen05 GEMM (trunk 2, actor 1, critic 1) + heads_act (dot products, Philox sampling, log-prob)
 KERNELS_PER_ENV_STEP = 1
 
 

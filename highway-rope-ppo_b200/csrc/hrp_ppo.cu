@@ -252,28 +252,63 @@ heads_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const f
     }
 }
 
-// ActorCritic.get_action (agent.py:56-74) after the forward pass
-__global__ void act_kernel(const float *__restrict__ mean, const float *__restrict__ log_std,
-                           const float *__restrict__ noise, long long B, int A, float *__restrict__ action,
-                           float *__restrict__ pre_tanh, float *__restrict__ log_prob)
+// heads + ActorCritic.get_action (agent.py:56-74) in one pass for the rollout: one warp per row computes
+// mean[A] and value from the two hidden activations, lane 0 then samples z = mean + std * n with
+// n ~ N(0,1) from Philox4x32-10(counter = (row, draw), key = seed) through Box-Muller (or takes n from
+// noise[], or n = 0 when deterministic), and writes tanh(z), z, log-prob and value.
+__global__ void __launch_bounds__(256)
+heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const float *__restrict__ wa2,
+                 const float *__restrict__ ba2, const float *__restrict__ wc2, const float *__restrict__ bc2,
+                 const float *__restrict__ log_std, const float *__restrict__ noise, int mode /*0 det, 1 noise[], 2 philox*/,
+                 unsigned long long seed, unsigned long long draw, long long B, int H, int A,
+                 float *__restrict__ action, float *__restrict__ pre_tanh, float *__restrict__ log_prob,
+                 float *__restrict__ value)
 {
-    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long b = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
     if (b >= B) return;
+    const float *ra = a1 + (size_t)b * H, *rc = c1 + (size_t)b * H;
+    float out[5];
+    for (int a = 0; a <= A; ++a) {
+        const float *w = a < A ? wa2 + (size_t)a * H : wc2;
+        const float *x = a < A ? ra : rc;
+        float s = 0.f;
+        for (int k = lane; k < H; k += 32) s = fmaf(x[k], w[k], s);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(HRP_FULL, s, d);
+        out[a] = s + (a < A ? ba2[a] : bc2[0]);
+    }
+    if (lane != 0) return;
+    float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mode == 2) {
+        uint32_t r[4];
+        hrp_philox((uint32_t)b, (uint32_t)((unsigned long long)b >> 32), (uint32_t)draw, (uint32_t)(draw >> 32),
+                   (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5A5A5A5Au, r);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float u1 = ((float)(r[2 * q] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            float u2 = ((float)(r[2 * q + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            float rad = sqrtf(-2.f * logf(u1)), sn, cs;
+            sincospif(2.f * u2, &sn, &cs);
+            nrm[2 * q] = rad * cs;
+            nrm[2 * q + 1] = rad * sn;
+        }
+    } else if (mode == 1) {
+        for (int a = 0; a < A; ++a) nrm[a] = noise[b * A + a];
+    }
     float lp = 0.f;
     for (int a = 0; a < A; ++a) {
-        float mu = mean[b * A + a];
-        float ls = log_std[a];
-        float sd = expf(ls);
-        float z = noise ? mu + sd * noise[b * A + a] : mu;
+        float mu = out[a], ls = log_std[a], sd = expf(ls);
+        float z = mode ? mu + sd * nrm[a] : mu;
         float t = tanhf(z);
         pre_tanh[b * A + a] = z;
         action[b * A + a] = t;
-        // Normal.log_prob(z) - log1p(-tanh(z)^2 + 1e-6)
         float d = z - mu;
         lp += -(d * d) / (2.f * sd * sd) - ls - 0.91893853320467274f;
         lp -= log1pf(-(t * t) + 1e-6f);
     }
-    if (log_prob) log_prob[b] = noise ? lp : 0.f;
+    if (log_prob) log_prob[b] = mode ? lp : 0.f;
+    value[b] = out[A];
 }
 
 // PPO loss for one minibatch (agent.py:223-245) and its gradient w.r.t. mean, value, log_std.
@@ -569,8 +604,22 @@ static int forward_impl(hrp_ppo *h, const float *params, const float *x, long lo
     if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s) < 0) return -2;
     if (gemm(false, true, Bi, H, H, h->h2, H, params + L.wa1, H, h->a1, H, params + L.ba1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
     if (gemm(false, true, Bi, H, H, h->h2, H, params + L.wc1, H, h->c1, H, params + L.bc1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+    if (!mean) return 0;  // trunk + hidden head layers only (the caller fuses the heads)
     heads_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(h->a1, h->c1, params + L.wa2, params + L.ba2, params + L.wc2,
                                                         params + L.bc2, B, H, A, mean, value);
+    HRP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int act_impl(hrp_ppo *h, const float *params, const float *states, const float *noise, int mode,
+                    unsigned long long seed, unsigned long long draw, long long batch, float *action, float *pre_tanh,
+                    float *log_prob, float *value, cudaStream_t s)
+{
+    const Layout &L = h->L;
+    if (int rc = forward_impl(h, params, states, batch, nullptr, nullptr, s)) return rc;
+    heads_act_kernel<<<(unsigned)((batch + 7) / 8), 256, 0, s>>>(
+        h->a1, h->c1, params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2, params + L.log_std, noise, mode,
+        seed, draw, batch, L.H, L.A, action, pre_tanh, log_prob, value);
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -655,12 +704,17 @@ int hrp_ppo_act(hrp_ppo *h, const float *params, const float *states, const floa
 {
     if (!h || !params || !states || !action || !pre_tanh || !value) { hrp_set_error("hrp_ppo_act: null argument"); return -1; }
     if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
-    cudaStream_t s = (cudaStream_t)stream;
-    if (int rc = forward_impl(h, params, states, batch, h->mean, value, s)) return rc;
-    act_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(h->mean, params + h->L.log_std, noise, batch, h->L.A,
-                                                              action, pre_tanh, log_prob);
-    HRP_CUDA_OK(cudaGetLastError());
-    return 0;
+    return act_impl(h, params, states, noise, noise ? 1 : 0, 0ull, 0ull, batch, action, pre_tanh, log_prob, value,
+                    (cudaStream_t)stream);
+}
+
+int hrp_ppo_act_sample(hrp_ppo *h, const float *params, const float *states, uint64_t seed, uint64_t draw, int64_t batch,
+                       float *action, float *pre_tanh, float *log_prob, float *value, void *stream)
+{
+    if (!h || !params || !states || !action || !pre_tanh || !value) { hrp_set_error("hrp_ppo_act_sample: null argument"); return -1; }
+    if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
+    return act_impl(h, params, states, nullptr, 2, seed, draw, batch, action, pre_tanh, log_prob, value,
+                    (cudaStream_t)stream);
 }
 
 int hrp_gae(const float *reward, const float *value, const uint8_t *done, const float *last_value, int64_t T,

@@ -92,6 +92,8 @@ class ActorCritic:
         self._h = C.c_void_p()
         self.max_batch = 0
         self._ensure_workspace(max_batch)
+        self._noise_seed = int(torch.randint(0, 2**62, (1,)).item())
+        self._draw = 0
 
     def _ensure_workspace(self, batch: int) -> None:
         if batch <= self.max_batch:
@@ -190,7 +192,14 @@ class ActorCritic:
                    "log_prob": torch.empty(B, dtype=torch.float32, device=self.device),
                    "value": torch.empty(B, dtype=torch.float32, device=self.device)}
         if not deterministic and noise is None:
-            noise = torch.randn((B, A), dtype=torch.float32, device=self.device)
+            # standard normals drawn in the kernel (Philox keyed by a seed taken from torch's generator at
+            # construction, so set_random_seeds() still fixes the rollout; one draw counter per call)
+            self._draw += 1
+            _lib.check(self._lib.hrp_ppo_act_sample(self._h, self.flat.data_ptr(), states.data_ptr(), self._noise_seed,
+                                                    self._draw, B, out["action"].data_ptr(),
+                                                    out["pre_tanh"].data_ptr(), out["log_prob"].data_ptr(),
+                                                    out["value"].data_ptr(), self._stream()), "hrp_ppo_act_sample")
+            return out
         _lib.check(self._lib.hrp_ppo_act(self._h, self.flat.data_ptr(), states.data_ptr(),
                                          None if deterministic else noise.data_ptr(), B,
                                          out["action"].data_ptr(), out["pre_tanh"].data_ptr(),

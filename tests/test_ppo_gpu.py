@@ -226,3 +226,28 @@ def test_select_action_protocol():
     mean, std, value = a.actor_critic.forward(s)
     assert mean.shape == (2,) and std.shape == (2,) and value.shape == (1,)
     assert np.allclose(pre, mean.cpu().numpy(), atol=1e-6)
+
+
+def test_in_kernel_sampling_is_standard_normal_and_self_consistent():
+    """hrp_ppo_act_sample: z = mean + std * n with n from Philox + Box-Muller; the log-prob it returns is the
+    one evaluate() assigns to the same pre-tanh action (what PPO's ratio at epoch 0 relies on)."""
+    torch.manual_seed(3)
+    a = _agent(60, 2, 64, 8192)
+    x = torch.randn(8192, 60, device="cuda:0") * 0.3
+    out1 = {k: v.clone() for k, v in a.act(x).items()}
+    out2 = a.act(x)
+    mean, std, value = a.actor_critic.forward(x)
+    n1 = ((out1["pre_tanh"] - mean) / std).flatten()
+    n2 = ((out2["pre_tanh"] - mean) / std).flatten()
+    assert abs(float(n1.mean())) < 0.03 and abs(float(n1.std()) - 1) < 0.03
+    assert abs(float((n1 ** 3).mean())) < 0.1 and abs(float((n1 ** 4).mean()) - 3) < 0.25
+    assert abs(float((n1 * n2).mean())) < 0.03                       # successive draws are independent
+    assert abs(float((n1[0::2] * n1[1::2]).mean())) < 0.03           # so are the two action components
+    logp, v, _ = a.actor_critic.evaluate(x, None, out1["pre_tanh"])
+    np.testing.assert_allclose(out1["log_prob"].cpu().numpy(), logp.cpu().numpy(), atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(out1["value"].cpu().numpy(), value[:, 0].cpu().numpy(), atol=1e-6)
+    np.testing.assert_allclose(out1["action"].cpu().numpy(), np.tanh(out1["pre_tanh"].cpu().numpy()), atol=1e-6)
+    # same seed, same draw counter -> same sample
+    torch.manual_seed(3)
+    b = _agent(60, 2, 64, 8192)
+    assert torch.equal(b.act(x)["pre_tanh"], out1["pre_tanh"])
