@@ -115,6 +115,16 @@ __device__ __forceinline__ float idm_interaction(const WarpS &S, int e, int f)
     return 3.f * g * g;
 }
 
+// the same for the calling lane's own vehicle, whose state is in registers
+__device__ __forceinline__ float idm_interaction_own(const WarpS &S, float xr, float ve, float che, float she, int f)
+{
+    float dvx = ve * che - S.v[f] * S.ch[f];
+    float dvy = ve * she - S.v[f] * S.sh[f];
+    float gap = 10.f + ve * 1.5f + ve * (dvx * che + dvy * she) * kInvTwoSqrtAB;
+    float g = __fdividef(gap, nzf(S.xr[f] - xr));
+    return 3.f * g * g;
+}
+
 // IDMVehicle.mobil for vehicle i and the candidate on `side` (0: lane-1, 1: lane+1).
 // Returns candidate lane + 1, or 0.  The free-road term of self_pred_a - self_a cancels.
 __device__ int mobil_item(const WarpS &S, const EnvDev &P, int i, int side)
@@ -287,6 +297,9 @@ __device__ void load_env(const EnvDev &P, WarpS &S, Veh (&u)[2], int e, int lane
             sincos_heading(w.h, &w.sh, &w.ch);
             w.acc = 0.f; w.tb = 0.f;
             publish(S, w, k, xref);
+        } else {
+            u[q] = Veh{};  // empty slot: the frame code runs on it with selects, its results are never stored
+            u[q].ch = 1.f;
         }
     }
     __syncwarp();
@@ -633,68 +646,70 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
         __syncwarp();
     }
 
-    // ---- controls: steering_control + IDM acceleration (or the ego's own action)
+    // ---- controls: steering_control + IDM acceleration (or the ego's own action).  Straight-line code with
+    // selects: every lane runs the same instructions whether its slot holds a vehicle, a crashed one or none.
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        int k = lane + 32 * q;
+        const int k = lane + 32 * q;
         Veh &w = u[q];
-        if (k >= V || w.crashed) continue;
-        bool controlled = k > 0 || ego_ctrl;
-        if (!controlled) continue;  // ContinuousAction ego keeps its action dict
+        const bool valid = k < V;
+        const bool act = valid && !w.crashed && (k > 0 || ego_ctrl);  // ContinuousAction ego keeps its action dict
         // ControlledVehicle.steering_control(target_lane) -> tan(beta) without leaving the tangent
-        float lat = w.y - kLaneW * w.tlane;
-        float lsc = -(1.f / 0.6f) * lat;
-        float rv = 1.f / nzf(w.v);
+        const float lat = w.y - kLaneW * w.tlane;
+        const float lsc = -(1.f / 0.6f) * lat;
+        const float rv = 1.f / nzf(w.v);
         // clip(asin(clip(c, -1, 1)), -pi/4, pi/4) == asin(clip(c, -sin(pi/4), sin(pi/4))): asin is monotone
-        float hc = asinf(clipf(lsc * rv, -0.70710678118654752f, 0.70710678118654752f));
-        float href = clipf(hc, -kPi / 4.f, kPi / 4.f);
-        float hrc = 5.f * wrap_to_pi(href - w.h);
-        float ss = clipf(2.5f * rv * hrc, -1.f, 1.f);  // sin(slip)
-        float tslip = ss * rsqrtf(fmaxf(1.f - ss * ss, 0.f));  // tan(slip); +-inf at |ss| == 1
-        w.tb = clipf(tslip, -kTanBetaMax, kTanBetaMax);  // tan(beta) = clip(2 tan slip, +-tan(pi/3)) / 2
-        if (k > 0) {
-            int p = S.rank[k];
-            float a0 = idm_free(w.v, clipf(w.ts, 0.f, 30.f), w.delta);
-            int sf = slot_front(S.band[w.lane], p);
-            float acc = a0 - (sf >= 0 ? idm_interaction(S, k, S.order[sf]) : 0.f);
-            if (w.lane != w.tlane) {
-                int st = slot_front(S.band[w.tlane], p);
-                float acc_t = a0 - (st >= 0 ? idm_interaction(S, k, S.order[st]) : 0.f);
-                acc = fminf(acc, acc_t);
-            }
-            w.acc = clipf(acc, -6.f, 6.f);
-        } else {
-            w.acc = (1.f / 0.6f) * (w.ts - w.v);  // MDPVehicle: speed_control
-        }
+        const float hc = asinf(clipf(lsc * rv, -0.70710678118654752f, 0.70710678118654752f));
+        const float href = clipf(hc, -kPi / 4.f, kPi / 4.f);
+        const float hrc = 5.f * wrap_to_pi(href - w.h);
+        const float ss = clipf(2.5f * rv * hrc, -1.f, 1.f);  // sin(slip)
+        const float tslip = ss * rsqrtf(fmaxf(1.f - ss * ss, 0.f));  // tan(slip); +-inf at |ss| == 1
+        const float tb_new = clipf(tslip, -kTanBetaMax, kTanBetaMax);  // tan(beta) = clip(2 tan slip, +-tan(pi/3)) / 2
+        // IDMVehicle.acceleration against the front vehicle of the own lane and of the target lane
+        const int p = valid ? (int)S.rank[k] : 0;
+        const float a0 = idm_free(w.v, clipf(w.ts, 0.f, 30.f), w.delta);
+        const float xr_own = (float)(w.x - xref);
+        const int sf = slot_front(S.band[w.lane], p), st = slot_front(S.band[w.tlane], p);
+        const float i1 = idm_interaction_own(S, xr_own, w.v, w.ch, w.sh, S.order[max(sf, 0)]);
+        const float i2 = idm_interaction_own(S, xr_own, w.v, w.ch, w.sh, S.order[max(st, 0)]);
+        float acc = a0 - (sf >= 0 ? i1 : 0.f);
+        const float acc_t = a0 - (st >= 0 ? i2 : 0.f);
+        acc = w.lane != w.tlane ? fminf(acc, acc_t) : acc;
+        const float acc_idm = clipf(acc, -6.f, 6.f);
+        const float acc_mdp = (1.f / 0.6f) * (w.ts - w.v);  // MDPVehicle: speed_control
+        w.tb = act ? tb_new : w.tb;
+        w.acc = act ? (k > 0 ? acc_idm : acc_mdp) : w.acc;
     }
     __syncwarp();  // every read of the frame-start state is done
 
     // ---- Vehicle.step(dt): clip_actions, kinematic bicycle, pending impact, lane re-assignment
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        int k = lane + 32 * q;
+        const int k = lane + 32 * q;
         Veh &w = u[q];
-        if (k >= V) continue;
-        if (k > 0) w.timer += P.dt64;
-        if (w.crashed) { w.tb = 0.f; w.acc = -1.0f * w.v; }
-        if (w.v > 40.f) w.acc = fminf(w.acc, 40.f - w.v);
-        else if (w.v < -40.f) w.acc = fmaxf(w.acc, -40.f - w.v);
-        float cb = rsqrtf(1.f + w.tb * w.tb), sb = w.tb * cb;
-        float c = w.ch * cb - w.sh * sb, s = w.sh * cb + w.ch * sb;
+        w.timer += k > 0 ? P.dt64 : 0.0;
+        w.tb = w.crashed ? 0.f : w.tb;
+        w.acc = w.crashed ? -1.0f * w.v : w.acc;
+        w.acc = w.v > 40.f ? fminf(w.acc, 40.f - w.v) : (w.v < -40.f ? fmaxf(w.acc, -40.f - w.v) : w.acc);
+        const float cb = rsqrtf(1.f + w.tb * w.tb), sb = w.tb * cb;
+        const float c = w.ch * cb - w.sh * sb, s = w.sh * cb + w.ch * sb;
         w.x += (double)(w.v * c * dt);
         w.y += w.v * s * dt;
-        if (w.has_impact) {
-            w.x += (double)w.impx; w.y += w.impy;
-            w.crashed = true; w.has_impact = false; w.impx = w.impy = 0.f;
-        }
+        w.x += w.has_impact ? (double)w.impx : 0.0;   // pending impact of the previous frame's collision
+        w.y += w.has_impact ? w.impy : 0.f;
+        w.crashed = w.crashed || w.has_impact;
+        w.has_impact = false;
+        w.impx = w.impy = 0.f;
         w.h += w.v * sb / 2.5f * dt;
         w.v += w.acc * dt;
         w.lane = closest_lane(w.y, P.lanes);
         sincos_heading(w.h, &w.sh, &w.ch);
-        S.x[k] = w.x; S.xr[k] = (float)(w.x - xref);
-        S.y[k] = w.y; S.v[k] = w.v; S.ch[k] = w.ch; S.sh[k] = w.sh;
-        S.lane[k] = (unsigned char)w.lane;
-        S.tl_old[k] = S.tl_new[k] = (unsigned char)w.tlane;
+        if (k < V) {
+            S.x[k] = w.x; S.xr[k] = (float)(w.x - xref);
+            S.y[k] = w.y; S.v[k] = w.v; S.ch[k] = w.ch; S.sh[k] = w.sh;
+            S.lane[k] = (unsigned char)w.lane;
+            S.tl_old[k] = S.tl_new[k] = (unsigned char)w.tlane;
+        }
     }
     __syncwarp();
     rank_repair(S, V, lane);
