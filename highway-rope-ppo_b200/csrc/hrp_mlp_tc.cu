@@ -27,7 +27,8 @@
 namespace {
 
 constexpr int BM = 128, BK = 32;                  // BK * 4 B = 128 B = one swizzle row; BN is 64 or 128
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 256;                    // loader / epilogue threads (8 warps)
+constexpr int TC_LAUNCH_THREADS = TC_THREADS + 32;  // + one warp that only issues tcgen05.mma
 constexpr int A_TILE_BYTES = BM * BK * 4;         // 16 KB per part of the A tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -235,7 +236,7 @@ struct Stager {
 };
 
 template <int AMODE, int BMODE, int NSPLIT, int BN>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS)
 tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, long long sak,
                const float *__restrict__ B, long long sbn, long long sbk, float *__restrict__ C, int ldc,
                const float *__restrict__ bias, int relu, const float *__restrict__ mask, int ldm, int accumulate,
@@ -246,7 +247,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     constexpr int STAGE_BYTES = PARTS * (A_TILE_BYTES + B_TILE_BYTES);
     constexpr int STAGES = NSPLIT == 3 ? 2 : 4;                 // <= 96 KB per CTA: two CTAs share an SM
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bar_empty[4], bar_done;
+    __shared__ uint64_t bar_full[4], bar_empty[4], bar_done;
     __shared__ uint32_t tmem_base_s;
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
@@ -256,7 +257,10 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     const int nkb = (kend - kbeg + BK - 1) / BK;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bar_empty[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], TC_THREADS);   // every loader thread arrives once its part of the stage is written
+            mbar_init(&bar_empty[s], 1);           // tcgen05.commit arrives when the MMAs have read the stage
+        }
         mbar_init(&bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -272,56 +276,64 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     const uint32_t tmem_d = tmem_base_s;
     constexpr uint32_t idesc = make_idesc(BM, BN);
 
-    // register staging, software-pipelined TWO K-blocks ahead (two register sets): these GEMMs are short
-    // (K <= 512 per CTA), so the exposed global-load latency per K-block is what bounds them
-    Stager<AMODE, BM> sa0, sa1;
-    Stager<BMODE, BN> sb0, sb1;
-    auto step = [&](int kb, Stager<AMODE, BM> &sa, Stager<BMODE, BN> &sb) {
-        const int s = kb % STAGES;
-        if (kb >= STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((kb / STAGES) - 1) & 1));  // MMAs of kb - STAGES retired
-        uint8_t *a_hi = smem + s * STAGE_BYTES, *b_hi = a_hi + PARTS * A_TILE_BYTES;
-        sa.template stash<NSPLIT>(a_hi, A_TILE_BYTES, tid);
-        sb.template stash<NSPLIT>(b_hi, B_TILE_BYTES, tid);
-        if (kb + 2 < nkb) {                                 // refill this register set: in flight for two blocks
-            const int k0 = kbeg + (kb + 2) * BK;
-            sa.fetch(A, sam, sak, m0, M, k0, kend, tid);
-            sb.fetch(B, sbn, sbk, n0, N, k0, kend, tid);
+    if (warp < TC_THREADS / 32) {
+        // ===== loader warps: global -> registers (two K-blocks ahead) -> swizzled shared stage -> bar_full
+        Stager<AMODE, BM> sa0, sa1;
+        Stager<BMODE, BN> sb0, sb1;
+        auto step = [&](int kb, Stager<AMODE, BM> &sa, Stager<BMODE, BN> &sb) {
+            const int s = kb % STAGES;
+            if (kb >= STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((kb / STAGES) - 1) & 1));  // MMAs of kb - STAGES retired
+            uint8_t *a_hi = smem + s * STAGE_BYTES, *b_hi = a_hi + PARTS * A_TILE_BYTES;
+            sa.template stash<NSPLIT>(a_hi, A_TILE_BYTES, tid);
+            sb.template stash<NSPLIT>(b_hi, B_TILE_BYTES, tid);
+            if (kb + 2 < nkb) {                             // refill this register set: in flight for two blocks
+                const int k0 = kbeg + (kb + 2) * BK;
+                sa.fetch(A, sam, sak, m0, M, k0, kend, tid);
+                sb.fetch(B, sbn, sbk, n0, N, k0, kend, tid);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
+        };
+        if (nkb > 0) {
+            sa0.fetch(A, sam, sak, m0, M, kbeg, kend, tid);
+            sb0.fetch(B, sbn, sbk, n0, N, kbeg, kend, tid);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
-        __syncthreads();
-        if (warp == 0) {
+        if (nkb > 1) {
+            sa1.fetch(A, sam, sak, m0, M, kbeg + BK, kend, tid);
+            sb1.fetch(B, sbn, sbk, n0, N, kbeg + BK, kend, tid);
+        }
+        for (int kb = 0; kb < nkb; kb += 2) {
+            step(kb, sa0, sb0);
+            if (kb + 1 < nkb) step(kb + 1, sa1, sb1);
+        }
+    } else {
+        // ===== MMA warp: waits for a full stage, one elected lane issues the UMMAs, tcgen05.commit frees the stage
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&bar_full[s], (uint32_t)((kb / STAGES) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t a_s = smem_u32(a_hi), b_s = smem_u32(b_hi);
+                const uint32_t a_s = smem_u32(smem + s * STAGE_BYTES), b_s = a_s + PARTS * A_TILE_BYTES;
+                // descriptors differ only in the start-address field (bits 0-13, units of 16 bytes)
+                const uint64_t da_hi = make_desc(a_s), db_hi = make_desc(b_s);
+                const uint64_t da_lo = da_hi + (A_TILE_BYTES >> 4), db_lo = db_hi + (B_TILE_BYTES >> 4);
 #pragma unroll
-                for (int kk = 0; kk < BK / 8; ++kk) {       // UMMA_K = 8 tf32 = 32 bytes: advance the start address
-                    const uint32_t off = kk * 32;
+                for (int kk = 0; kk < BK / 8; ++kk) {       // UMMA_K = 8 tf32 = 32 bytes = 2 address units
+                    const uint64_t o = (uint64_t)(kk * 2);
                     const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
                     if (NSPLIT == 3) {
-                        umma_tf32(tmem_d, make_desc(a_s + A_TILE_BYTES + off), make_desc(b_s + off), idesc, acc);
-                        umma_tf32(tmem_d, make_desc(a_s + off), make_desc(b_s + B_TILE_BYTES + off), idesc, 1u);
-                        umma_tf32(tmem_d, make_desc(a_s + off), make_desc(b_s + off), idesc, 1u);
+                        umma_tf32(tmem_d, da_lo + o, db_hi + o, idesc, acc);
+                        umma_tf32(tmem_d, da_hi + o, db_lo + o, idesc, 1u);
+                        umma_tf32(tmem_d, da_hi + o, db_hi + o, idesc, 1u);
                     } else {
-                        umma_tf32(tmem_d, make_desc(a_s + off), make_desc(b_s + off), idesc, acc);
+                        umma_tf32(tmem_d, da_hi + o, db_hi + o, idesc, acc);
                     }
                 }
-                umma_commit(&bar_empty[s]);                 // frees the stage when these MMAs have read it
+                umma_commit(&bar_empty[s]);
                 if (kb + 1 == nkb) umma_commit(&bar_done);  // accumulator complete
             }
             __syncwarp();
         }
-    };
-    if (nkb > 0) {
-        sa0.fetch(A, sam, sak, m0, M, kbeg, kend, tid);
-        sb0.fetch(B, sbn, sbk, n0, N, kbeg, kend, tid);
-    }
-    if (nkb > 1) {
-        sa1.fetch(A, sam, sak, m0, M, kbeg + BK, kend, tid);
-        sb1.fetch(B, sbn, sbk, n0, N, kbeg + BK, kend, tid);
-    }
-    for (int kb = 0; kb < nkb; kb += 2) {
-        step(kb, sa0, sb0);
-        if (kb + 1 < nkb) step(kb + 1, sa1, sb1);
     }
 
     // ---- epilogue: TMEM -> registers -> shared (row-major, padded) -> coalesced global rows.
@@ -330,7 +342,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     constexpr int LDS = BN + 1;                       // odd row pitch: conflict-free column writes
     float *stage_c = (float *)smem;
-    {
+    if (warp < TC_THREADS / 32) {
         const int trow = 32 * (warp & 3) + lane;
 #pragma unroll 1
         for (int c0 = (BN / 2) * (warp >> 2); c0 < (BN / 2) * (warp >> 2) + BN / 2; c0 += 16) {
@@ -360,7 +372,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
         constexpr int RSTEP = TC_THREADS / BN;
         const int c = tid % BN, gn = n0 + c;
         const float bv = (bias && gn < N) ? bias[gn] : 0.f;
-        if (gn < N) {
+        if (gn < N && tid < TC_THREADS) {
 #pragma unroll 4
             for (int r = tid / BN; r < BM; r += RSTEP) {
                 const int gm = m0 + r;
@@ -396,7 +408,7 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
         HRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
     }
-    kern<<<grid, TC_THREADS, SMEM, s>>>(M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate,
+    kern<<<grid, TC_LAUNCH_THREADS, SMEM, s>>>(M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate,
                                        k_chunk);
     HRP_CUDA_OK(cudaGetLastError());
     return 0;

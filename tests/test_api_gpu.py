@@ -122,3 +122,43 @@ def test_vectorized_training_improves_reward(highway_config):
     print("mean step reward first/last", first, last)
     assert last > first
     env.close()
+
+
+def test_experiment_runner_result_schema(highway_config, tmp_path):
+    """experiments/runner.py:46-155 re-host: COMPLETED result with the reference's keys; failures are reported."""
+    from highway_rope_ppo_b200.experiments.config import Condition, ConditionHP, Experiment
+    from highway_rope_ppo_b200.experiments.runner import ExperimentRunner, experiment_name
+
+    hp = ConditionHP(lr=3e-4, hidden_dim=64, batch_size=32, epochs=2, d_embed=4, steps_per_update=48)
+    name = experiment_name("SORTED", hp, 42)
+    assert name == "sorted_lr0.0003_hidden_dim64_clip_eps0.2_entropy_coef0.005_epochs2_batch_size32_d_embed4_seed42"
+    runner = ExperimentRunner(highway_config, artifacts_dir=str(tmp_path))
+    res = runner.launch(Experiment(name, Condition.SORTED, hp, seed=42, max_episodes=3,
+                                   extra={"eval_interval": 3, "log_interval": 1}))
+    assert res["status"] == "COMPLETED", res.get("error_traceback")
+    assert set(res) >= {"experiment_name", "status", "rewards", "avg_rewards", "metrics_history", "duration_seconds"}
+    assert len(res["rewards"]) == 2 and res["metrics_history"]["experiment_name"] == name
+    bad = runner.launch(Experiment("bad", Condition.SHUFFLED_ROPE, ConditionHP(d_embed=16), seed=1, max_episodes=1))
+    assert bad["status"] == "FAILED" and "rotate_dim" in bad["error_message"] and "error_traceback" in bad
+
+
+def test_meta_action_env_through_make_env(highway_config):
+    """DiscreteMetaAction ego (north_star's MDPVehicle controller) through the gymnasium-protocol env."""
+    import copy
+
+    from highway_rope_ppo_b200.experiments.config import Condition
+    from highway_rope_ppo_b200.experiments.wrappers import make_env
+
+    cfg = copy.deepcopy(highway_config)
+    cfg["action"] = {"type": "DiscreteMetaAction"}
+    env = make_env(Condition.SORTED, cfg)
+    assert env.action_space.n == 5
+    obs, _ = env.reset(seed=3)
+    total = 0.0
+    for t in range(40):
+        obs, r, te, tr, _ = env.step(1 if t % 7 else 3)  # IDLE, occasionally FASTER
+        total += r
+        if te or tr:
+            break
+    assert obs.shape == (15, 4) and total > 0
+    env.close()
