@@ -309,7 +309,13 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_us": env_kernel_s * 1e6,
                 "share_of_step": env_ms / total_ms,
-                "note": "compute/latency-bound kernel (15 fused substeps per launch); see DESIGN.md"}
+                # the binding resource: warp-instruction issue slots.  1.10e8 warp instructions per 4096-env launch
+                # (ncu smsp__inst_executed.sum, profiles/r01_step_kernel_*), 4 schedulers x 148 SMs x sm clock
+                "issue": {"warp_instructions_per_launch": 1.10e8 * E / 4096,
+                          "achieved_ginst_s": 1.10e8 * E / 4096 / env_kernel_s / 1e9,
+                          "peak_ginst_s": 4 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6 / 1e9,
+                          "frac": 1.10e8 * E / 4096 / env_kernel_s / (4 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6)},
+                "note": "instruction-issue-bound kernel (15 fused substeps per launch), not HBM-bound; see DESIGN.md 3.1"}
 
     # e2e: the same step through the host-buffer API (pinned host obs -> policy -> host actions -> env -> host obs)
     e2e = None

@@ -235,7 +235,15 @@ struct Stager {
     }
 };
 
-template <int AMODE, int BMODE, int NSPLIT, int BN>
+template <int NSPLIT, int BN, bool ASYNC>
+__host__ __device__ constexpr int tc_stages()
+{
+    constexpr int stage = (NSPLIT == 3 ? 2 : 1) * (A_TILE_BYTES + BN * BK * 4);
+    // register-staged path: <= 96 KB per CTA so that two CTAs share an SM; cp.async path: as deep as 200 KB allow
+    return ASYNC ? (4 * stage <= 200 * 1024 ? 4 : 3) : (NSPLIT == 3 ? 2 : 4);
+}
+
+template <int AMODE, int BMODE, int NSPLIT, int BN, bool ASYNC>
 __global__ void __launch_bounds__(TC_LAUNCH_THREADS)
 tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, long long sak,
                const float *__restrict__ B, long long sbn, long long sbk, float *__restrict__ C, int ldc,
@@ -245,7 +253,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;                  // hi (+ lo) copy of every operand tile
     constexpr int B_TILE_BYTES = BN * BK * 4;
     constexpr int STAGE_BYTES = PARTS * (A_TILE_BYTES + B_TILE_BYTES);
-    constexpr int STAGES = NSPLIT == 3 ? 2 : 4;                 // <= 96 KB per CTA: two CTAs share an SM
+    constexpr int STAGES = tc_stages<NSPLIT, BN, ASYNC>();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar_full[4], bar_empty[4], bar_done;
     __shared__ uint32_t tmem_base_s;
@@ -276,7 +284,79 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     const uint32_t tmem_d = tmem_base_s;
     constexpr uint32_t idesc = make_idesc(BM, BN);
 
-    if (warp < TC_THREADS / 32) {
+    if (ASYNC && warp < TC_THREADS / 32) {
+        // ===== loader warps, cp.async path (A: 16-byte, B: 8-byte aligned K-contiguous operands).
+        // The tensor core TRUNCATES fp32 operands to TF32 (tools/tf32_probe.py), so the raw fp32 tile is the
+        // "hi" operand as it is: raw tiles go global -> shared with cp.async, STAGES - 1 K-blocks in flight, no
+        // registers involved; each thread then derives the "lo" tile (x - trunc(x)) from the chunks it copied.
+        constexpr int P = STAGES - 1;
+        constexpr int B_CHUNKS = BN * BK / 2 / TC_THREADS;     // 8-byte chunks of B per thread
+        auto issue = [&](int kb) {
+            const int s = kb % STAGES, k0 = kbeg + kb * BK;
+            const uint32_t a_raw = smem_u32(smem + s * STAGE_BYTES), b_raw = a_raw + PARTS * A_TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < BM * BK / 4 / TC_THREADS; ++i) {
+                const int idx = tid + i * TC_THREADS, r = idx >> 3, k = (idx & 7) * 4;
+                const int gr = m0 + r, gk = k0 + k;
+                const bool ok = gr < M && gk < kend;
+                const float *src = ok ? A + (long long)gr * sam + gk : A;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_raw + swz(r, k)), "l"(src),
+                             "r"(ok ? 16 : 0)
+                             : "memory");
+            }
+#pragma unroll
+            for (int i = 0; i < B_CHUNKS; ++i) {
+                const int idx = tid + i * TC_THREADS, r = idx >> 4, k = (idx & 15) * 2;
+                const int gr = n0 + r, gk = k0 + k;
+                const bool ok = gr < N && gk < kend;
+                const float *src = ok ? B + (long long)gr * sbn + gk : B;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(b_raw + swz(r, k)), "l"(src),
+                             "r"(ok ? 8 : 0)
+                             : "memory");
+            }
+        };
+        for (int kb = 0; kb < P; ++kb) {
+            if (kb < nkb) issue(kb);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            asm volatile("cp.async.wait_group %0;" ::"n"(P - 1) : "memory");   // this thread's chunks of block kb landed
+            if (NSPLIT == 3) {
+                uint8_t *a_raw = smem + s * STAGE_BYTES, *b_raw = a_raw + PARTS * A_TILE_BYTES;
+#pragma unroll
+                for (int i = 0; i < BM * BK / 4 / TC_THREADS; ++i) {
+                    const int idx = tid + i * TC_THREADS;
+                    const uint32_t o = swz(idx >> 3, (idx & 7) * 4);
+                    const float4 x = *(const float4 *)(a_raw + o);
+                    float4 l;
+                    l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    *(float4 *)(a_raw + A_TILE_BYTES + o) = l;
+                }
+#pragma unroll
+                for (int i = 0; i < B_CHUNKS; ++i) {
+                    const int idx = tid + i * TC_THREADS;
+                    const uint32_t o = swz(idx >> 4, (idx & 15) * 2);
+                    const float2 x = *(const float2 *)(b_raw + o);
+                    float2 l;
+                    l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    *(float2 *)(b_raw + B_TILE_BYTES + o) = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
+            const int nx = kb + P;                           // refill the stage that block kb - 1 used
+            if (nx < nkb) {
+                if (nx >= STAGES) mbar_wait(&bar_empty[nx % STAGES], (uint32_t)(((nx / STAGES) - 1) & 1));
+                issue(nx);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    } else if (warp < TC_THREADS / 32) {
         // ===== loader warps: global -> registers (two K-blocks ahead) -> swizzled shared stage -> bar_full
         Stager<AMODE, BM> sa0, sa1;
         Stager<BMODE, BN> sb0, sb1;
@@ -392,18 +472,18 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
 }
 
-template <int AMODE, int BMODE, int NSPLIT, int BN>
+template <int AMODE, int BMODE, int NSPLIT, int BN, bool ASYNC = false>
 int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
            const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias, int relu,
            const float *mask, int ldm, int accumulate, int k_chunk)
 {
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;
-    constexpr int STAGES = NSPLIT == 3 ? 2 : 4;
+    constexpr int STAGES = tc_stages<NSPLIT, BN, ASYNC>();
     constexpr int OPERANDS = STAGES * PARTS * (A_TILE_BYTES + BN * BK * 4);
     constexpr int EPILOGUE = BM * (BN + 1) * 4;
     constexpr int SMEM = (OPERANDS > EPILOGUE ? OPERANDS : EPILOGUE) + 1024;
     static bool configured = false;
-    auto kern = tc_gemm_kernel<AMODE, BMODE, NSPLIT, BN>;
+    auto kern = tc_gemm_kernel<AMODE, BMODE, NSPLIT, BN, ASYNC>;
     if (!configured) {
         HRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
@@ -422,6 +502,18 @@ int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K,
 #define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk
     if (bn == 64) return nsplit == 3 ? launch<AMODE, BMODE, 3, 64>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 64>(HRP_TC_ARGS);
     return nsplit == 3 ? launch<AMODE, BMODE, 3, 128>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 128>(HRP_TC_ARGS);
+#undef HRP_TC_ARGS
+}
+
+// forward-pass operands (activations x weights, both K-contiguous and aligned): cp.async staging
+int dispatch_async(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
+                   long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
+                   int relu, const float *mask, int ldm, int accumulate, int k_chunk)
+{
+#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk
+    if (bn == 64)
+        return nsplit == 3 ? launch<ST_K4, ST_K2, 3, 64, true>(HRP_TC_ARGS) : launch<ST_K4, ST_K2, 1, 64, true>(HRP_TC_ARGS);
+    return nsplit == 3 ? launch<ST_K4, ST_K2, 3, 128, true>(HRP_TC_ARGS) : launch<ST_K4, ST_K2, 1, 128, true>(HRP_TC_ARGS);
 #undef HRP_TC_ARGS
 }
 
@@ -454,7 +546,10 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     const bool b_mn4 = sbn == 1 && N % 4 == 0 && sbk % 4 == 0 && aligned(B, 16);
 #define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk)
     int rc;
-    if (a_k4 && b_k2) rc = HRP_TC_GO(ST_K4, ST_K2);
+    // cp.async staging pays off for the single-pass mode only (measured: 3xTF32 hidden forward 12.6 us register-staged
+    // vs 14.5 us cp.async -- the lo tiles need a second pass through shared memory; TF32 H=512 19.6 -> 16.6 us)
+    if (a_k4 && b_k2 && nsplit == 1) rc = dispatch_async(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    else if (a_k4 && b_k2) rc = HRP_TC_GO(ST_K4, ST_K2);
     else if (a_k4 && sbn == 1) rc = HRP_TC_GO(ST_K4, ST_MN1);
     else if (a_mn4 && b_mn4) rc = HRP_TC_GO(ST_MN4, ST_MN4);
     else if (akc && bkc) rc = HRP_TC_GO(ST_K1, ST_K1);
