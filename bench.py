@@ -323,8 +323,9 @@ def run_ours(args):
         Ke = min(K, 200)
         obs_h = torch.zeros((E, 15, 4), dtype=torch.float32).pin_memory()
         act_h = torch.zeros((E, 2), dtype=torch.float32).pin_memory()
-        rew_h = np.zeros(E, dtype=np.float32)
-        te_h, tr_h = np.zeros(E, dtype=np.uint8), np.zeros(E, dtype=np.uint8)
+        rew_h = torch.zeros(E, dtype=torch.float32).pin_memory().numpy()
+        te_h = torch.zeros(E, dtype=torch.uint8).pin_memory().numpy()
+        tr_h = torch.zeros(E, dtype=torch.uint8).pin_memory().numpy()
         obs_np, act_np = obs_h.numpy(), act_h.numpy()
         env.reset_host(42, obs_np)
         obs_d = torch.empty((E, S), device=dev)

@@ -270,6 +270,15 @@ static int ensure_host_path(hrp_env *h)
     return 0;
 }
 
+// page-locked caller memory (cudaMallocHost / cudaHostRegister / torch pin_memory) is copied to and from directly;
+// pageable memory goes through the handle's own pinned staging buffers
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int hrp_env_step_host(hrp_env *h, const float *actions_host, float *obs_host, float *reward_host,
                       uint8_t *terminated_host, uint8_t *truncated_host)
 {
@@ -280,20 +289,25 @@ int hrp_env_step_host(hrp_env *h, const float *actions_host, float *obs_host, fl
     if (int rc = ensure_host_path(h)) return rc;
     size_t E = h->P.E, no = E * h->P.N * h->P.Fout;
     cudaStream_t s = h->host_stream;
-    memcpy(h->h_actions, actions_host, E * 2 * sizeof(float));
-    HRP_CUDA_OK(cudaMemcpyAsync(h->d_actions, h->h_actions, E * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    const bool pin_a = is_pinned(actions_host), pin_o = is_pinned(obs_host);
+    const bool pin_r = is_pinned(reward_host) && is_pinned(terminated_host) && is_pinned(truncated_host);
+    if (!pin_a) memcpy(h->h_actions, actions_host, E * 2 * sizeof(float));
+    HRP_CUDA_OK(cudaMemcpyAsync(h->d_actions, pin_a ? actions_host : h->h_actions, E * 2 * sizeof(float),
+                                cudaMemcpyHostToDevice, s));
     if (int rc = hrp_launch_step(h->P, h->d_actions, h->d_obs, h->d_reward, h->d_term, h->d_trunc, nullptr,
                                  nullptr, s))
         return rc;
-    HRP_CUDA_OK(cudaMemcpyAsync(h->h_obs, h->d_obs, no * sizeof(float), cudaMemcpyDeviceToHost, s));
-    HRP_CUDA_OK(cudaMemcpyAsync(h->h_reward, h->d_reward, E * sizeof(float), cudaMemcpyDeviceToHost, s));
-    HRP_CUDA_OK(cudaMemcpyAsync(h->h_term, h->d_term, E, cudaMemcpyDeviceToHost, s));
-    HRP_CUDA_OK(cudaMemcpyAsync(h->h_trunc, h->d_trunc, E, cudaMemcpyDeviceToHost, s));
+    HRP_CUDA_OK(cudaMemcpyAsync(pin_o ? obs_host : h->h_obs, h->d_obs, no * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HRP_CUDA_OK(cudaMemcpyAsync(pin_r ? reward_host : h->h_reward, h->d_reward, E * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HRP_CUDA_OK(cudaMemcpyAsync(pin_r ? terminated_host : h->h_term, h->d_term, E, cudaMemcpyDeviceToHost, s));
+    HRP_CUDA_OK(cudaMemcpyAsync(pin_r ? truncated_host : h->h_trunc, h->d_trunc, E, cudaMemcpyDeviceToHost, s));
     HRP_CUDA_OK(cudaStreamSynchronize(s));
-    memcpy(obs_host, h->h_obs, no * sizeof(float));
-    memcpy(reward_host, h->h_reward, E * sizeof(float));
-    memcpy(terminated_host, h->h_term, E);
-    memcpy(truncated_host, h->h_trunc, E);
+    if (!pin_o) memcpy(obs_host, h->h_obs, no * sizeof(float));
+    if (!pin_r) {
+        memcpy(reward_host, h->h_reward, E * sizeof(float));
+        memcpy(terminated_host, h->h_term, E);
+        memcpy(truncated_host, h->h_trunc, E);
+    }
     return 0;
 }
 
@@ -303,10 +317,12 @@ int hrp_env_reset_host(hrp_env *h, uint64_t seed, float *obs_host)
     if (int rc = ensure_host_path(h)) return rc;
     size_t no = (size_t)h->P.E * h->P.N * h->P.Fout;
     h->P.seed = seed;
+    const bool pin_o = is_pinned(obs_host);
     if (int rc = hrp_launch_reset(h->P, nullptr, h->d_obs, h->host_stream)) return rc;
-    HRP_CUDA_OK(cudaMemcpyAsync(h->h_obs, h->d_obs, no * sizeof(float), cudaMemcpyDeviceToHost, h->host_stream));
+    HRP_CUDA_OK(cudaMemcpyAsync(pin_o ? obs_host : h->h_obs, h->d_obs, no * sizeof(float), cudaMemcpyDeviceToHost,
+                                h->host_stream));
     HRP_CUDA_OK(cudaStreamSynchronize(h->host_stream));
-    memcpy(obs_host, h->h_obs, no * sizeof(float));
+    if (!pin_o) memcpy(obs_host, h->h_obs, no * sizeof(float));
     return 0;
 }
 
