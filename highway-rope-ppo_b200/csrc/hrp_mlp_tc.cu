@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS)
 tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, long long sak,
                const float *__restrict__ B, long long sbn, long long sbk, float *__restrict__ C, int ldc,
                const float *__restrict__ bias, int relu, const float *__restrict__ mask, int ldm, int accumulate,
-               int k_chunk)
+               int k_chunk, int nseg, const float *__restrict__ B2, const float *__restrict__ bias2)
 {
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;                  // hi (+ lo) copy of every operand tile
     constexpr int B_TILE_BYTES = BN * BK * 4;
@@ -261,6 +261,13 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // N-segmented B operand: output columns >= nseg multiply the rows of a second matrix (two weight matrices that
+    // are not adjacent in memory act as one [N, K] operand; tiles never straddle the boundary, see hrp_tc_gemm)
+    const bool seg2 = nseg > 0 && n0 >= nseg;
+    const float *__restrict__ Bp = seg2 ? B2 : B;
+    const float *__restrict__ biasp = seg2 ? bias2 : bias;
+    const int bn0 = seg2 ? n0 - nseg : n0;                       // first row of this tile inside Bp
+    const int bN = nseg > 0 ? (seg2 ? N - nseg : nseg) : N;      // rows of Bp
     const int kbeg = blockIdx.z * k_chunk, kend = min(K, kbeg + k_chunk);
     const int nkb = (kend - kbeg + BK - 1) / BK;
 
@@ -307,9 +314,9 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
 #pragma unroll
             for (int i = 0; i < B_CHUNKS; ++i) {
                 const int idx = tid + i * TC_THREADS, r = idx >> 4, k = (idx & 15) * 2;
-                const int gr = n0 + r, gk = k0 + k;
-                const bool ok = gr < N && gk < kend;
-                const float *src = ok ? B + (long long)gr * sbn + gk : B;
+                const int gr = bn0 + r, gk = k0 + k;
+                const bool ok = gr < bN && gk < kend;
+                const float *src = ok ? Bp + (long long)gr * sbn + gk : Bp;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(b_raw + swz(r, k)), "l"(src),
                              "r"(ok ? 8 : 0)
                              : "memory");
@@ -369,18 +376,18 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
             if (kb + 2 < nkb) {                             // refill this register set: in flight for two blocks
                 const int k0 = kbeg + (kb + 2) * BK;
                 sa.fetch(A, sam, sak, m0, M, k0, kend, tid);
-                sb.fetch(B, sbn, sbk, n0, N, k0, kend, tid);
+                sb.fetch(Bp, sbn, sbk, bn0, bN, k0, kend, tid);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
         };
         if (nkb > 0) {
             sa0.fetch(A, sam, sak, m0, M, kbeg, kend, tid);
-            sb0.fetch(B, sbn, sbk, n0, N, kbeg, kend, tid);
+            sb0.fetch(Bp, sbn, sbk, bn0, bN, kbeg, kend, tid);
         }
         if (nkb > 1) {
             sa1.fetch(A, sam, sak, m0, M, kbeg + BK, kend, tid);
-            sb1.fetch(B, sbn, sbk, n0, N, kbeg + BK, kend, tid);
+            sb1.fetch(Bp, sbn, sbk, bn0, bN, kbeg + BK, kend, tid);
         }
         for (int kb = 0; kb < nkb; kb += 2) {
             step(kb, sa0, sb0);
@@ -451,7 +458,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
         // thread t always writes column t % BN: its bias is loaded once; rows advance by TC_THREADS / BN
         constexpr int RSTEP = TC_THREADS / BN;
         const int c = tid % BN, gn = n0 + c;
-        const float bv = (bias && gn < N) ? bias[gn] : 0.f;
+        const float bv = (biasp && gn < N) ? biasp[bn0 + c] : 0.f;
         if (gn < N && tid < TC_THREADS) {
 #pragma unroll 4
             for (int r = tid / BN; r < BM; r += RSTEP) {
@@ -475,7 +482,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
 template <int AMODE, int BMODE, int NSPLIT, int BN, bool ASYNC = false>
 int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
            const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias, int relu,
-           const float *mask, int ldm, int accumulate, int k_chunk)
+           const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2, const float *bias2)
 {
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;
     constexpr int STAGES = tc_stages<NSPLIT, BN, ASYNC>();
@@ -489,7 +496,7 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
         configured = true;
     }
     kern<<<grid, TC_LAUNCH_THREADS, SMEM, s>>>(M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate,
-                                       k_chunk);
+                                       k_chunk, nseg, B2, bias2);
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -497,9 +504,10 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
 template <int AMODE, int BMODE>
 int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
              long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
-             int relu, const float *mask, int ldm, int accumulate, int k_chunk)
+             int relu, const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2,
+             const float *bias2)
 {
-#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk
+#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2
     if (bn == 64) return nsplit == 3 ? launch<AMODE, BMODE, 3, 64>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 64>(HRP_TC_ARGS);
     return nsplit == 3 ? launch<AMODE, BMODE, 3, 128>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 128>(HRP_TC_ARGS);
 #undef HRP_TC_ARGS
@@ -508,9 +516,10 @@ int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K,
 // forward-pass operands (activations x weights, both K-contiguous and aligned): cp.async staging
 int dispatch_async(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
                    long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
-                   int relu, const float *mask, int ldm, int accumulate, int k_chunk)
+                   int relu, const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2,
+                   const float *bias2)
 {
-#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk
+#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2
     if (bn == 64)
         return nsplit == 3 ? launch<ST_K4, ST_K2, 3, 64, true>(HRP_TC_ARGS) : launch<ST_K4, ST_K2, 1, 64, true>(HRP_TC_ARGS);
     return nsplit == 3 ? launch<ST_K4, ST_K2, 3, 128, true>(HRP_TC_ARGS) : launch<ST_K4, ST_K2, 1, 128, true>(HRP_TC_ARGS);
@@ -525,7 +534,7 @@ inline bool aligned(const void *p, int bytes) { return ((uintptr_t)p % bytes) ==
 // nsplit: 3 = 3xTF32 (fp32-grade accuracy), 1 = single TF32 pass.
 int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
-                int accumulate, int splits, int nsplit, cudaStream_t s)
+                int accumulate, int splits, int nsplit, cudaStream_t s, int nseg, const float *B2, const float *bias2)
 {
     int k_chunk = K;
     if (splits > 1) {
@@ -536,19 +545,25 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     }
     // 64-wide N tiles when 128-wide ones would leave most of the 148 SMs idle
     const int mt = (M + BM - 1) / BM;
-    const int bn = (N <= 64 || mt * ((N + 127) / 128) * splits < 120) ? 64 : 128;
+    int bn = (N <= 64 || mt * ((N + 127) / 128) * splits < 120) ? 64 : 128;
+    if (nseg > 0) {
+        if (nseg % 64 != 0 || nseg >= N || B2 == nullptr) { hrp_set_error("hrp_tc_gemm: bad N segmentation"); return -1; }
+        if (nseg % 128 != 0) bn = 64;   // a tile must not straddle the two B matrices
+    }
     dim3 grid((N + bn - 1) / bn, mt, splits);
     const bool akc = sak == 1, bkc = sbk == 1;
     // vectorised staging where strides and base addresses allow it
     const bool a_k4 = akc && K % 4 == 0 && sam % 4 == 0 && aligned(A, 16);
-    const bool b_k2 = bkc && K % 2 == 0 && sbn % 2 == 0 && aligned(B, 8);
+    const bool b_k2 = bkc && K % 2 == 0 && sbn % 2 == 0 && aligned(B, 8) && (nseg == 0 || aligned(B2, 8));
+    const bool b_k4 = bkc && K % 4 == 0 && sbn % 4 == 0 && aligned(B, 16) && (nseg == 0 || aligned(B2, 16));
     const bool a_mn4 = sam == 1 && M % 4 == 0 && sak % 4 == 0 && aligned(A, 16);
-    const bool b_mn4 = sbn == 1 && N % 4 == 0 && sbk % 4 == 0 && aligned(B, 16);
-#define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk)
+    const bool b_mn4 = sbn == 1 && N % 4 == 0 && sbk % 4 == 0 && aligned(B, 16) && nseg == 0;
+#define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2)
     int rc;
     // cp.async staging pays off for the single-pass mode only (measured: 3xTF32 hidden forward 12.6 us register-staged
     // vs 14.5 us cp.async -- the lo tiles need a second pass through shared memory; TF32 H=512 19.6 -> 16.6 us)
-    if (a_k4 && b_k2 && nsplit == 1) rc = dispatch_async(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk);
+    if (a_k4 && b_k2 && nsplit == 1) rc = dispatch_async(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2);
+    else if (a_k4 && b_k4) rc = HRP_TC_GO(ST_K4, ST_K4);
     else if (a_k4 && b_k2) rc = HRP_TC_GO(ST_K4, ST_K2);
     else if (a_k4 && sbn == 1) rc = HRP_TC_GO(ST_K4, ST_MN1);
     else if (a_mn4 && b_mn4) rc = HRP_TC_GO(ST_MN4, ST_MN4);

@@ -120,14 +120,43 @@ sgemm_kernel(int M, int N, int K, const float *__restrict__ A, int lda, const fl
     }
 }
 
+// sums the split partials in split order; elements >= n1 go to out2 (two gradient tensors that are not adjacent
+// in the flat buffer but were produced by one GEMM)
 __global__ void reduce_partials_kernel(const float *__restrict__ part, float *__restrict__ out, long long n,
-                                       int splits)
+                                       int splits, long long n1, float *__restrict__ out2)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[(size_t)z * n + i];
-    out[i] = s;
+    if (i < n1) out[i] = s;
+    else out2[i - n1] = s;
+}
+
+// transposed, 16-byte aligned copies of the hidden weight matrices for the input-gradient GEMMs (the flat
+// parameter buffer holds W[out, in]; dX = dY W wants W^T K-contiguous).  z = 0: actor_mean.0 -> wt_ac[:, 0:H],
+// z = 1: critic.0 -> wt_ac[:, H:2H] (row pitch 2H), z = 2: shared.2 -> wt_2 (row pitch H)
+__global__ void __launch_bounds__(256)
+transpose_weights_kernel(const float *__restrict__ wa1, const float *__restrict__ wc1, const float *__restrict__ w2,
+                         int H, float *__restrict__ wt_ac, float *__restrict__ wt_2)
+{
+    __shared__ float tile[32][33];
+    const float *src = blockIdx.z == 0 ? wa1 : (blockIdx.z == 1 ? wc1 : w2);
+    float *dst = blockIdx.z == 2 ? wt_2 : wt_ac + (blockIdx.z == 1 ? H : 0);
+    const int ldd = blockIdx.z == 2 ? H : 2 * H;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int r = r0 + ty + 8 * i, c = c0 + tx;
+        tile[ty + 8 * i][tx] = (r < H && c < H) ? src[(size_t)r * H + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int r = c0 + ty + 8 * i, c = r0 + tx;   // dst[r, c] = src[c, r]
+        if (r < H && c < H) dst[(size_t)r * ldd + c] = tile[tx][ty + 8 * i];
+    }
 }
 
 // column sums, stage 1: block (x, y) reduces rows [y*rows_per, ...) of 32 columns -> part[y][N]
@@ -156,7 +185,7 @@ colsum_partial_kernel(const float *__restrict__ G, int ldg, long long B, int N, 
 // part[y] holds [A*H | A | H | 1] floats.
 __global__ void __launch_bounds__(256)
 heads_wgrad_partial_kernel(const float *__restrict__ dmean, const float *__restrict__ dvalue,
-                           const float *__restrict__ a1, const float *__restrict__ c1, long long B, int H, int A,
+                           const float *__restrict__ a1, const float *__restrict__ c1, int ld, long long B, int H, int A,
                            int rows_per, float *__restrict__ part)
 {
     __shared__ float red[8][6][33];
@@ -167,9 +196,9 @@ heads_wgrad_partial_kernel(const float *__restrict__ dmean, const float *__restr
     for (long long b = r0 + w; b < r1; b += 8) {
         float dv = dvalue[b];
         if (h < H) {
-            float av = a1[(size_t)b * H + h];
+            float av = a1[(size_t)b * ld + h];
             for (int a = 0; a < A; ++a) acc[a] = fmaf(dmean[b * A + a], av, acc[a]);
-            accc = fmaf(dv, c1[(size_t)b * H + h], accc);
+            accc = fmaf(dv, c1[(size_t)b * ld + h], accc);
         }
         if (blockIdx.x == 0 && l <= A) accb += l < A ? dmean[b * A + l] : dv;
     }
@@ -232,12 +261,12 @@ __global__ void gather_batch_kernel(const float *__restrict__ states, const floa
 __global__ void __launch_bounds__(256)
 heads_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const float *__restrict__ wa2,
              const float *__restrict__ ba2, const float *__restrict__ wc2, const float *__restrict__ bc2,
-             long long B, int H, int A, float *__restrict__ mean, float *__restrict__ value)
+             int ld, long long B, int H, int A, float *__restrict__ mean, float *__restrict__ value)
 {
     long long b = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (b >= B) return;
-    const float *ra = a1 + (size_t)b * H, *rc = c1 + (size_t)b * H;
+    const float *ra = a1 + (size_t)b * ld, *rc = c1 + (size_t)b * ld;
     for (int a = 0; a <= A; ++a) {
         const float *w = a < A ? wa2 + (size_t)a * H : wc2;
         const float *x = a < A ? ra : rc;
@@ -260,14 +289,14 @@ __global__ void __launch_bounds__(256)
 heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const float *__restrict__ wa2,
                  const float *__restrict__ ba2, const float *__restrict__ wc2, const float *__restrict__ bc2,
                  const float *__restrict__ log_std, const float *__restrict__ noise, int mode /*0 det, 1 noise[], 2 philox*/,
-                 unsigned long long seed, unsigned long long draw, long long B, int H, int A,
+                 unsigned long long seed, unsigned long long draw, int ld, long long B, int H, int A,
                  float *__restrict__ action, float *__restrict__ pre_tanh, float *__restrict__ log_prob,
                  float *__restrict__ value)
 {
     long long b = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (b >= B) return;
-    const float *ra = a1 + (size_t)b * H, *rc = c1 + (size_t)b * H;
+    const float *ra = a1 + (size_t)b * ld, *rc = c1 + (size_t)b * ld;
     float out[5];
     for (int a = 0; a <= A; ++a) {
         const float *w = a < A ? wa2 + (size_t)a * H : wc2;
@@ -312,24 +341,28 @@ heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, con
 }
 
 // PPO loss for one minibatch (agent.py:223-245) and its gradient w.r.t. mean, value, log_std.
-// Single CTA: deterministic reductions.  metrics += (loss, policy, value, entropy, clipfrac, kl, 1, 0)
-__global__ void __launch_bounds__(1024)
+// Grid-stride over the rows; every CTA leaves its 8 partial sums in part[blockIdx.x][8] and the CTA that
+// finishes last adds them in block order (deterministic) and writes d(log_std) and the metrics:
+// metrics += (loss, policy, value, entropy, clipfrac, kl, 1, 0).  `counter` returns to zero.
+constexpr int LOSS_MAX_CTAS = 64;
+__global__ void __launch_bounds__(256)
 ppo_loss_kernel(const float *__restrict__ mean, const float *__restrict__ value,
                 const float *__restrict__ log_std, const float *__restrict__ pre_tanh,
                 const float *__restrict__ old_lp, const float *__restrict__ adv, const float *__restrict__ ret,
                 long long B, int A, float eps_clip, float value_coef, float entropy_coef, float scale,
                 float *__restrict__ dmean, float *__restrict__ dvalue, float *__restrict__ dlog_std,
-                float *__restrict__ metrics)
+                float *__restrict__ metrics, float *__restrict__ part, unsigned *__restrict__ counter)
 {
-    __shared__ float red[32][8];
+    __shared__ float red[8][8];
+    __shared__ bool last;
     float s_pol = 0.f, s_val = 0.f, s_clip = 0.f, s_kl = 0.f, s_dls[4] = {0.f, 0.f, 0.f, 0.f};
-    float ent = 0.f;
-    for (int a = 0; a < A; ++a) ent += 0.5f + 0.91893853320467274f + log_std[a];
-    for (long long b = threadIdx.x; b < B; b += blockDim.x) {
+    float ls_[4], sd_[4];
+    for (int a = 0; a < A; ++a) { ls_[a] = log_std[a]; sd_[a] = expf(ls_[a]); }
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
         float lp = 0.f;
         float dmu[4], dls[4];
         for (int a = 0; a < A; ++a) {
-            float mu = mean[b * A + a], ls = log_std[a], sd = expf(ls);
+            float mu = mean[b * A + a], ls = ls_[a], sd = sd_[a];
             float z = pre_tanh[b * A + a];
             float t = tanhf(z);
             float d = z - mu, var = sd * sd;
@@ -374,12 +407,28 @@ ppo_loss_kernel(const float *__restrict__ mean, const float *__restrict__ value,
     __syncthreads();
     if (threadIdx.x < 8) {
         float x = 0.f;
-        int nw = blockDim.x >> 5;
-        for (int i = 0; i < nw; ++i) x += red[i][threadIdx.x];
+        for (int i = 0; i < 8; ++i) x += red[i][threadIdx.x];
+        part[blockIdx.x * 8 + threadIdx.x] = x;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned prev = atomicAdd(counter, 1u);
+        last = prev == gridDim.x - 1;
+        if (last) *counter = 0u;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 8) {
+        float x = 0.f;
+        for (unsigned i = 0; i < gridDim.x; ++i) x += __ldcg(part + i * 8 + threadIdx.x);
         red[0][threadIdx.x] = x;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        float ent = 0.f;
+        for (int a = 0; a < A; ++a) ent += 0.5f + 0.91893853320467274f + ls_[a];
         float pol = red[0][0] * scale, val = red[0][1] * scale;
         float frac = (float)B * scale;  // share of the global minibatch held by this shard
         float loss = pol + value_coef * val - entropy_coef * ent * frac;
@@ -394,17 +443,18 @@ ppo_loss_kernel(const float *__restrict__ mean, const float *__restrict__ value,
 // d(a1) = dmean Wa2 (.) (a1>0) and d(c1) = dvalue Wc2 (.) (c1>0): rank-A / rank-1 outer products
 __global__ void heads_backward_kernel(const float *__restrict__ dmean, const float *__restrict__ dvalue,
                                       const float *__restrict__ wa2, const float *__restrict__ wc2,
-                                      const float *__restrict__ a1, const float *__restrict__ c1, long long B,
+                                      const float *__restrict__ a1, const float *__restrict__ c1, int ld, long long B,
                                       int H, int A, float *__restrict__ da1, float *__restrict__ dc1)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * H) return;
     long long b = i / H;
     int k = (int)(i - b * H);
+    size_t o = (size_t)b * ld + k;   // a1 | c1 and d(a1) | d(c1) share the [B, 2H] row pitch
     float s = 0.f;
     for (int a = 0; a < A; ++a) s = fmaf(dmean[b * A + a], wa2[(size_t)a * H + k], s);
-    da1[i] = a1[i] > 0.f ? s : 0.f;
-    dc1[i] = c1[i] > 0.f ? dvalue[b] * wc2[k] : 0.f;
+    da1[o] = a1[o] > 0.f ? s : 0.f;
+    dc1[o] = c1[o] > 0.f ? dvalue[b] * wc2[k] : 0.f;
 }
 
 // PPOMemory.compute_advantages (agent.py:126-138): fp64 arithmetic, float32 store of every A_t
@@ -527,18 +577,24 @@ struct hrp_ppo {
     int device;
     float *ws;  // one arena
     float *x, *z, *olp, *adv, *ret;          // gathered minibatch
-    float *h1, *h2, *a1, *c1;                // activations [B,H]
+    float *h1, *h2;                          // trunk activations [B,H]
+    float *ac;                               // actor | critic hidden activations, one [B, 2H] matrix
     float *mean, *value, *dmean, *dvalue;    // heads and their gradients
-    float *d1, *d2;                          // activation gradients [B,H]
+    float *d12;                              // d(actor hidden) | d(critic hidden), [B, 2H]
+    float *dh2, *dh1;                        // trunk activation gradients [B,H]
+    float *wt_ac, *wt_2;                     // transposed weights: [H, 2H] (actor_mean.0 | critic.0) and [H, H] (shared.2)
     float *part;                             // split-K partials
     float *part2;                            // column-sum / head-gradient partials (<= 64 chunks)
+    float *loss_part;                        // ppo_loss_kernel partial sums [LOSS_MAX_CTAS][8]
+    unsigned *loss_counter;
     int splits_cap;
 };
 
 // tensor-core path (hrp_mlp_tc.cu)
 int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
-                int accumulate, int splits, int nsplit, cudaStream_t s);
+                int accumulate, int splits, int nsplit, cudaStream_t s, int nseg = 0, const float *B2 = nullptr,
+                const float *bias2 = nullptr);
 
 // math mode of the hidden-layer GEMMs: 0 = fp32 SIMT, 1 = TF32 tcgen05, 3 = 3xTF32 tcgen05 (default)
 static int g_math_mode = 3;
@@ -564,25 +620,25 @@ static int gemm(bool AT, bool BT, int M, int N, int K, const float *A, int lda, 
     return splits;
 }
 
-// weight gradient dW[N,K] = dY[B,N]^T X[B,K], split over B, deterministic
-static int wgrad(hrp_ppo *h, int N, int K, long long B, const float *dY, const float *X, float *dW, cudaStream_t s)
+// weight gradient dW[N,K] = dY[B,N]^T X[B,K] (row pitches lddy, ldx), split over B, deterministic.  Rows >= n1 of
+// dW go to dW2 (two weight matrices fed by one [B, N] gradient matrix); n1 = N, dW2 = nullptr for a single one.
+static int wgrad(hrp_ppo *h, int N, int K, long long B, const float *dY, int lddy, const float *X, int ldx, float *dW,
+                 int n1, float *dW2, cudaStream_t s)
 {
     int splits = (int)((B + 255) / 256);
     if (splits > h->splits_cap) splits = h->splits_cap;
-    if (splits <= 1) {
-        int rc = gemm(true, false, N, K, (int)B, dY, N, X, K, dW, K, nullptr, 0, nullptr, 0, 0, 1, s);
-        return rc < 0 ? rc : 0;
-    }
-    int used = gemm(true, false, N, K, (int)B, dY, N, X, K, h->part, K, nullptr, 0, nullptr, 0, 0, splits, s);
+    if (splits < 1) splits = 1;
+    int used = gemm(true, false, N, K, (int)B, dY, lddy, X, ldx, h->part, K, nullptr, 0, nullptr, 0, 0, splits, s);
     if (used < 0) return used;
     long long n = (long long)N * K;
-    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->part, dW, n, used);
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->part, dW, n, used, (long long)n1 * K, dW2);
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// bias gradient db[N] = column sums of G[B, N], deterministic two-stage
-static int colsum(hrp_ppo *h, const float *G, int ldg, long long B, int N, float *out, cudaStream_t s)
+// bias gradient db[N] = column sums of G[B, N], deterministic two-stage; columns >= n1 go to out2
+static int colsum(hrp_ppo *h, const float *G, int ldg, long long B, int N, float *out, int n1, float *out2,
+                  cudaStream_t s)
 {
     int chunks = (int)((B + 63) / 64);
     if (chunks > 64) chunks = 64;
@@ -590,11 +646,13 @@ static int colsum(hrp_ppo *h, const float *G, int ldg, long long B, int N, float
     int rows_per = (int)((B + chunks - 1) / chunks);
     dim3 grid((N + 31) / 32, chunks);
     colsum_partial_kernel<<<grid, 256, 0, s>>>(G, ldg, B, N, rows_per, h->part2);
-    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, s>>>(h->part2, out, N, chunks);
+    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, s>>>(h->part2, out, N, chunks, n1, out2);
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
+// shared trunk and the two hidden head layers; the latter are one GEMM over the row-stacked weights
+// [actor_mean.0 ; critic.0] into h->ac = [a1 | c1]
 static int forward_impl(hrp_ppo *h, const float *params, const float *x, long long B, float *mean, float *value,
                         cudaStream_t s)
 {
@@ -602,11 +660,17 @@ static int forward_impl(hrp_ppo *h, const float *params, const float *x, long lo
     int H = L.H, S = L.S, A = L.A, Bi = (int)B;
     if (gemm(false, true, Bi, H, S, x, S, params + L.w1, S, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
     if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s) < 0) return -2;
-    if (gemm(false, true, Bi, H, H, h->h2, H, params + L.wa1, H, h->a1, H, params + L.ba1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
-    if (gemm(false, true, Bi, H, H, h->h2, H, params + L.wc1, H, h->c1, H, params + L.bc1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+    if (g_math_mode != 0 && H % 64 == 0 && Bi >= 32) {
+        if (hrp_tc_gemm(Bi, 2 * H, H, h->h2, H, 1, params + L.wa1, H, 1, h->ac, 2 * H, params + L.ba1, 1, nullptr, 0, 0, 1,
+                        g_math_mode == 1 ? 1 : 3, s, H, params + L.wc1, params + L.bc1) < 0)
+            return -2;
+    } else {
+        if (gemm(false, true, Bi, H, H, h->h2, H, params + L.wa1, H, h->ac, 2 * H, params + L.ba1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+        if (gemm(false, true, Bi, H, H, h->h2, H, params + L.wc1, H, h->ac + H, 2 * H, params + L.bc1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+    }
     if (!mean) return 0;  // trunk + hidden head layers only (the caller fuses the heads)
-    heads_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(h->a1, h->c1, params + L.wa2, params + L.ba2, params + L.wc2,
-                                                        params + L.bc2, B, H, A, mean, value);
+    heads_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(h->ac, h->ac + H, params + L.wa2, params + L.ba2, params + L.wc2,
+                                                        params + L.bc2, 2 * H, B, H, A, mean, value);
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -618,8 +682,8 @@ static int act_impl(hrp_ppo *h, const float *params, const float *states, const 
     const Layout &L = h->L;
     if (int rc = forward_impl(h, params, states, batch, nullptr, nullptr, s)) return rc;
     heads_act_kernel<<<(unsigned)((batch + 7) / 8), 256, 0, s>>>(
-        h->a1, h->c1, params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2, params + L.log_std, noise, mode,
-        seed, draw, batch, L.H, L.A, action, pre_tanh, log_prob, value);
+        h->ac, h->ac + L.H, params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2, params + L.log_std, noise, mode,
+        seed, draw, 2 * L.H, batch, L.H, L.A, action, pre_tanh, log_prob, value);
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -666,18 +730,28 @@ int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, in
     h->max_batch = max_batch; h->device = device;
     h->splits_cap = 32;
     size_t B = (size_t)max_batch, H = hidden_dim, S = state_dim, A = action_dim;
-    size_t big = H * (H > S ? H : S);
-    size_t part2 = 64 * ((A + 1) * H + A + 1 > H ? (A + 1) * H + A + 1 : H);
-    size_t n = B * S + B * A + 3 * B + 4 * B * H + 2 * B * A + 2 * B + 2 * B * H + (size_t)h->splits_cap * big + part2;
+    size_t big = 2 * H * (H > S ? H : S);   // largest weight-gradient GEMM output: [2H, H]
+    size_t part2 = 64 * ((A + 1) * H + A + 1 > 2 * H ? (A + 1) * H + A + 1 : 2 * H);
+    // every sub-buffer starts on a 128-byte boundary (float4 / cp.async operand staging)
+    auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
+    const size_t sizes[] = {B * S, B * A, B, B, B, B * H, B * H, 2 * B * H, B * A, B * A, B, B, 2 * B * H, B * H, B * H,
+                            2 * H * H, H * H, (size_t)h->splits_cap * big, part2, (size_t)LOSS_MAX_CTAS * 8, 32};
+    size_t n = 0;
+    for (size_t q : sizes) n += pad(q);
     cudaError_t ce = cudaMalloc(&h->ws, n * sizeof(float));
     if (ce != cudaSuccess) { hrp_set_error("cudaMalloc(%zu): %s", n * sizeof(float), cudaGetErrorString(ce)); delete h; return -2; }
     float *p = h->ws;
-    h->x = p; p += B * S; h->z = p; p += B * A; h->olp = p; p += B; h->adv = p; p += B; h->ret = p; p += B;
-    h->h1 = p; p += B * H; h->h2 = p; p += B * H; h->a1 = p; p += B * H; h->c1 = p; p += B * H;
-    h->mean = p; p += B * A; h->dmean = p; p += B * A; h->value = p; p += B; h->dvalue = p; p += B;
-    h->d1 = p; p += B * H; h->d2 = p; p += B * H;
-    h->part = p; p += (size_t)h->splits_cap * big;
-    h->part2 = p;
+    int qi = 0;
+    auto take = [&]() { float *r = p; p += pad(sizes[qi++]); return r; };
+    h->x = take(); h->z = take(); h->olp = take(); h->adv = take(); h->ret = take();
+    h->h1 = take(); h->h2 = take(); h->ac = take();
+    h->mean = take(); h->dmean = take(); h->value = take(); h->dvalue = take();
+    h->d12 = take(); h->dh2 = take(); h->dh1 = take();
+    h->wt_ac = take(); h->wt_2 = take();
+    h->part = take(); h->part2 = take(); h->loss_part = take();
+    h->loss_counter = (unsigned *)take();
+    ce = cudaMemset(h->loss_counter, 0, 32 * sizeof(float));
+    if (ce != cudaSuccess) { hrp_set_error("cudaMemset: %s", cudaGetErrorString(ce)); cudaFree(h->ws); delete h; return -2; }
     *out = h;
     return 0;
 }
@@ -772,39 +846,47 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         x = h->x; z = h->z; olp = h->olp; ad = h->adv; rt = h->ret;
     }
     if (int rc = forward_impl(h, params, x, B, h->mean, h->value, s)) return rc;
-    ppo_loss_kernel<<<1, 1024, 0, s>>>(h->mean, h->value, params + L.log_std, z, olp, ad, rt, B, A, eps_clip, value_coef,
-                                       entropy_coef, loss_scale, h->dmean, h->dvalue, grad + L.log_std, metrics);
-    HRP_CUDA_OK(cudaGetLastError());
+    {
+        int ctas = (int)((B + 255) / 256);
+        if (ctas > LOSS_MAX_CTAS) ctas = LOSS_MAX_CTAS;
+        ppo_loss_kernel<<<ctas, 256, 0, s>>>(h->mean, h->value, params + L.log_std, z, olp, ad, rt, B, A, eps_clip,
+                                             value_coef, entropy_coef, loss_scale, h->dmean, h->dvalue, grad + L.log_std,
+                                             metrics, h->loss_part, h->loss_counter);
+        HRP_CUDA_OK(cudaGetLastError());
+    }
+    const float *a1 = h->ac, *c1 = h->ac + H;
+    const int H2 = 2 * H;
     // heads: dWa2 = dmean^T a1, dba2 = colsum(dmean); dWc2 = dvalue^T c1, dbc2 = sum(dvalue)
     {
         int chunks = (int)((B + 63) / 64);
         if (chunks > 64) chunks = 64;
         int rows_per = (int)((B + chunks - 1) / chunks);
         dim3 grid((H + 31) / 32, chunks);
-        heads_wgrad_partial_kernel<<<grid, 256, 0, s>>>(h->dmean, h->dvalue, h->a1, h->c1, B, H, A, rows_per, h->part2);
+        heads_wgrad_partial_kernel<<<grid, 256, 0, s>>>(h->dmean, h->dvalue, a1, c1, H2, B, H, A, rows_per, h->part2);
         int n = A * H + A + H + 1;
         heads_wgrad_final_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->part2, chunks, H, A, grad + L.wa2, grad + L.wc2);
         HRP_CUDA_OK(cudaGetLastError());
     }
-    // d(a1), d(c1) into d1, d2 (ReLU masks applied)
+    // d(a1) | d(c1) into d12 (ReLU masks applied)
     heads_backward_kernel<<<(unsigned)((B * H + 255) / 256), 256, 0, s>>>(h->dmean, h->dvalue, params + L.wa2,
-                                                                        params + L.wc2, h->a1, h->c1, B, H, A, h->d1, h->d2);
+                                                                        params + L.wc2, a1, c1, H2, B, H, A, h->d12,
+                                                                        h->d12 + H);
+    {
+        dim3 grid((H + 31) / 32, (H + 31) / 32, 3);
+        transpose_weights_kernel<<<grid, 256, 0, s>>>(params + L.wa1, params + L.wc1, params + L.w2, H, h->wt_ac, h->wt_2);
+    }
     HRP_CUDA_OK(cudaGetLastError());
-    if (wgrad(h, H, H, B, h->d1, h->h2, grad + L.wa1, s)) return -2;
-    if (wgrad(h, H, H, B, h->d2, h->h2, grad + L.wc1, s)) return -2;
-    if (colsum(h, h->d1, H, B, H, grad + L.ba1, s)) return -2;
-    if (colsum(h, h->d2, H, B, H, grad + L.bc1, s)) return -2;
-    // d(h2) = (d(a1) Wa1 + d(c1) Wc1) (.) (h2>0) -> reuse a1 as the destination
-    float *dh2 = h->a1;
-    if (gemm(false, false, Bi, H, H, h->d1, H, params + L.wa1, H, dh2, H, nullptr, 0, nullptr, 0, 0, 1, s) < 0) return -2;
-    if (gemm(false, false, Bi, H, H, h->d2, H, params + L.wc1, H, dh2, H, nullptr, 0, h->h2, H, 1, 1, s) < 0) return -2;
-    if (wgrad(h, H, H, B, dh2, h->h1, grad + L.w2, s)) return -2;
-    if (colsum(h, dh2, H, B, H, grad + L.b2, s)) return -2;
-    // d(h1) = d(h2) W2 (.) (h1>0) -> c1
-    float *dh1 = h->c1;
-    if (gemm(false, false, Bi, H, H, dh2, H, params + L.w2, H, dh1, H, nullptr, 0, h->h1, H, 0, 1, s) < 0) return -2;
-    if (wgrad(h, H, S, B, dh1, x, grad + L.w1, s)) return -2;
-    if (colsum(h, dh1, H, B, H, grad + L.b1, s)) return -2;
+    // [dWa1 ; dWc1] = [d(a1) | d(c1)]^T h2 in one GEMM, [dba1 | dbc1] in one column sum
+    if (wgrad(h, H2, H, B, h->d12, H2, h->h2, H, grad + L.wa1, H, grad + L.wc1, s)) return -2;
+    if (colsum(h, h->d12, H2, B, H2, grad + L.ba1, H, grad + L.bc1, s)) return -2;
+    // d(h2) = [d(a1) | d(c1)] [Wa1 ; Wc1] (.) (h2>0): K = 2H against the transposed copies
+    if (gemm(false, true, Bi, H, H2, h->d12, H2, h->wt_ac, H2, h->dh2, H, nullptr, 0, h->h2, H, 0, 1, s) < 0) return -2;
+    if (wgrad(h, H, H, B, h->dh2, H, h->h1, H, grad + L.w2, H, nullptr, s)) return -2;
+    if (colsum(h, h->dh2, H, B, H, grad + L.b2, H, nullptr, s)) return -2;
+    // d(h1) = d(h2) W2 (.) (h1>0)
+    if (gemm(false, true, Bi, H, H, h->dh2, H, h->wt_2, H, h->dh1, H, nullptr, 0, h->h1, H, 0, 1, s) < 0) return -2;
+    if (wgrad(h, H, S, B, h->dh1, H, x, S, grad + L.w1, H, nullptr, s)) return -2;
+    if (colsum(h, h->dh1, H, B, H, grad + L.b1, H, nullptr, s)) return -2;
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }
