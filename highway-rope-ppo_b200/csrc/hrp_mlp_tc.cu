@@ -455,21 +455,31 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     __syncthreads();
     float *Cz = C + (size_t)blockIdx.z * M * ldc;
     {
-        // thread t always writes column t % BN: its bias is loaded once; rows advance by TC_THREADS / BN
-        constexpr int RSTEP = TC_THREADS / BN;
+        // thread t always writes column t % BN: its bias is loaded once; rows advance by TC_THREADS / BN.
+        // Rows are handled eight at a time with the global reads (accumulate, mask) of all eight issued before
+        // the first is used: one memory round trip per eight rows instead of one per row.
+        constexpr int RSTEP = TC_THREADS / BN, GROUP = 8;
         const int c = tid % BN, gn = n0 + c;
         const float bv = (biasp && gn < N) ? biasp[bn0 + c] : 0.f;
         if (gn < N && tid < TC_THREADS) {
-#pragma unroll 4
-            for (int r = tid / BN; r < BM; r += RSTEP) {
-                const int gm = m0 + r;
-                if (gm >= M) break;
-                const size_t o = (size_t)gm * ldc + gn;
-                float x = stage_c[r * LDS + c] + bv;
-                if (accumulate) x += Cz[o];
-                if (relu) x = fmaxf(x, 0.f);
-                if (mask) x = mask[(size_t)gm * ldm + gn] > 0.f ? x : 0.f;
-                Cz[o] = x;
+#pragma unroll 1
+            for (int rb = tid / BN; rb < BM; rb += RSTEP * GROUP) {
+                float prev[GROUP], mk[GROUP];
+#pragma unroll
+                for (int j = 0; j < GROUP; ++j) {
+                    const int gm = m0 + rb + j * RSTEP;
+                    const bool ok = gm < M;
+                    prev[j] = (accumulate && ok) ? Cz[(size_t)gm * ldc + gn] : 0.f;
+                    mk[j] = (mask && ok) ? __ldg(mask + (size_t)gm * ldm + gn) : 1.f;
+                }
+#pragma unroll
+                for (int j = 0; j < GROUP; ++j) {
+                    const int r = rb + j * RSTEP, gm = m0 + r;
+                    float x = stage_c[r * LDS + c] + bv + prev[j];
+                    if (relu) x = fmaxf(x, 0.f);
+                    x = mk[j] > 0.f ? x : 0.f;
+                    if (gm < M) Cz[(size_t)gm * ldc + gn] = x;
+                }
             }
         }
     }

@@ -43,7 +43,7 @@ __host__ __device__ inline Layout make_layout(int S, int A, int H)
 //   AT == false: A stored [M,K] (K contiguous);  AT == true: A stored [K,M].
 //   BT == false: B stored [K,N] (N contiguous);  BT == true: B stored [N,K].
 // Epilogue, in this order: + C (accumulate), + bias[n], ReLU, * (mask[m,n] > 0).  gridDim.z > 1 splits K and
-// writes partial tiles to C + z*M*N (reduced by reduce_partials_kernel, deterministic).
+// writes partial tiles to C + z*M*N (summed in split order by final_reduce_kernel, deterministic).
 constexpr int GM = 64, GN = 64, GK = 16;
 
 template <bool AT, bool BT>
@@ -120,17 +120,38 @@ sgemm_kernel(int M, int N, int K, const float *__restrict__ A, int lda, const fl
     }
 }
 
-// sums the split partials in split order; elements >= n1 go to out2 (two gradient tensors that are not adjacent
-// in the flat buffer but were produced by one GEMM)
-__global__ void reduce_partials_kernel(const float *__restrict__ part, float *__restrict__ out, long long n,
-                                       int splits, long long n1, float *__restrict__ out2)
+// every deterministic second-stage reduction of one backward pass in ONE launch: segment q sums `splits` partial
+// arrays of n elements in split order; elements >= n1 go to dst2.
+struct ReduceSeg {
+    const float *part;
+    float *dst, *dst2;
+    long long n, n1;
+    int splits, block0;
+};
+struct ReducePlan {
+    ReduceSeg seg[8];
+    int nseg, blocks;
+};
+__global__ void __launch_bounds__(256) final_reduce_kernel(const ReducePlan P)
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    int q = 0;
+#pragma unroll
+    for (int t = 1; t < 8; ++t)
+        if (t < P.nseg && (int)blockIdx.x >= P.seg[t].block0) q = t;
+    const ReduceSeg &g = P.seg[q];
+    long long i = (long long)(blockIdx.x - g.block0) * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(size_t)z * n + i];
-    if (i < n1) out[i] = s;
-    else out2[i - n1] = s;
+    for (int z = 0; z < g.splits; ++z) s += g.part[(size_t)z * g.n + i];
+    if (i < g.n1) g.dst[i] = s;
+    else g.dst2[i - g.n1] = s;
+}
+static void plan_add(ReducePlan &P, const float *part, long long n, int splits, float *dst, long long n1, float *dst2)
+{
+    ReduceSeg &g = P.seg[P.nseg++];
+    g.part = part; g.n = n; g.splits = splits; g.dst = dst; g.n1 = n1; g.dst2 = dst2;
+    g.block0 = P.blocks;
+    P.blocks += (int)((n + 255) / 256);
 }
 
 // transposed, 16-byte aligned copies of the hidden weight matrices for the input-gradient GEMMs (the flat
@@ -223,19 +244,6 @@ heads_wgrad_partial_kernel(const float *__restrict__ dmean, const float *__restr
         }
     }
 }
-// stage 2: sum the chunks; [A*H + A] go to grad + wa2 (ba2 follows wa2), [H + 1] to grad + wc2 (bc2 follows wc2)
-__global__ void heads_wgrad_final_kernel(const float *__restrict__ part, int chunks, int H, int A,
-                                         float *__restrict__ g_wa2, float *__restrict__ g_wc2)
-{
-    int n = A * H + A + H + 1;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += part[(size_t)c * n + i];
-    if (i < A * H + A) g_wa2[i] = s;
-    else g_wc2[i - (A * H + A)] = s;
-}
-
 // gather the minibatch out of the rollout in one launch: states, pre_tanh, old log-prob, advantage, return
 __global__ void gather_batch_kernel(const float *__restrict__ states, const float *__restrict__ pre_tanh,
                                     const float *__restrict__ olp, const float *__restrict__ adv,
@@ -583,11 +591,16 @@ struct hrp_ppo {
     float *d12;                              // d(actor hidden) | d(critic hidden), [B, 2H]
     float *dh2, *dh1;                        // trunk activation gradients [B,H]
     float *wt_ac, *wt_2;                     // transposed weights: [H, 2H] (actor_mean.0 | critic.0) and [H, H] (shared.2)
-    float *part;                             // split-K partials
-    float *part2;                            // column-sum / head-gradient partials (<= 64 chunks)
+    float *part_w[3];                        // split-K partials of the three weight-gradient GEMMs
+    float *part_b[3];                        // column-sum partials of the three bias gradients (<= 64 chunks)
+    float *part_h;                           // head-gradient partials (<= 64 chunks)
     float *loss_part;                        // ppo_loss_kernel partial sums [LOSS_MAX_CTAS][8]
     unsigned *loss_counter;
     int splits_cap;
+    // fork / join inside one backward pass: the weight- and bias-gradient kernels of a layer do not depend on the
+    // input-gradient GEMM of the same layer, so they run on two side streams (captured as parallel graph branches)
+    cudaStream_t side[2];
+    cudaEvent_t ev[8];
 };
 
 // tensor-core path (hrp_mlp_tc.cu)
@@ -620,34 +633,33 @@ static int gemm(bool AT, bool BT, int M, int N, int K, const float *A, int lda, 
     return splits;
 }
 
-// weight gradient dW[N,K] = dY[B,N]^T X[B,K] (row pitches lddy, ldx), split over B, deterministic.  Rows >= n1 of
-// dW go to dW2 (two weight matrices fed by one [B, N] gradient matrix); n1 = N, dW2 = nullptr for a single one.
-static int wgrad(hrp_ppo *h, int N, int K, long long B, const float *dY, int lddy, const float *X, int ldx, float *dW,
-                 int n1, float *dW2, cudaStream_t s)
+// weight gradient dW[N,K] = dY[B,N]^T X[B,K] (row pitches lddy, ldx), split over B into `part`; the plan's final
+// reduction sums the splits in order (deterministic).  Rows >= n1 of dW go to dW2 (two weight matrices fed by
+// one [B, N] gradient matrix); n1 = N, dW2 = nullptr for a single one.
+static int wgrad(hrp_ppo *h, ReducePlan &plan, float *part, int N, int K, long long B, const float *dY, int lddy,
+                 const float *X, int ldx, float *dW, int n1, float *dW2, cudaStream_t s)
 {
     int splits = (int)((B + 255) / 256);
     if (splits > h->splits_cap) splits = h->splits_cap;
     if (splits < 1) splits = 1;
-    int used = gemm(true, false, N, K, (int)B, dY, lddy, X, ldx, h->part, K, nullptr, 0, nullptr, 0, 0, splits, s);
+    int used = gemm(true, false, N, K, (int)B, dY, lddy, X, ldx, part, K, nullptr, 0, nullptr, 0, 0, splits, s);
     if (used < 0) return used;
-    long long n = (long long)N * K;
-    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->part, dW, n, used, (long long)n1 * K, dW2);
-    HRP_CUDA_OK(cudaGetLastError());
+    plan_add(plan, part, (long long)N * K, used, dW, (long long)n1 * K, dW2);
     return 0;
 }
 
-// bias gradient db[N] = column sums of G[B, N], deterministic two-stage; columns >= n1 go to out2
-static int colsum(hrp_ppo *h, const float *G, int ldg, long long B, int N, float *out, int n1, float *out2,
-                  cudaStream_t s)
+// bias gradient db[N] = column sums of G[B, N], first stage (<= 64 row chunks); columns >= n1 go to out2
+static int colsum(ReducePlan &plan, float *part, const float *G, int ldg, long long B, int N, float *out, int n1,
+                  float *out2, cudaStream_t s)
 {
     int chunks = (int)((B + 63) / 64);
     if (chunks > 64) chunks = 64;
     if (chunks < 1) chunks = 1;
     int rows_per = (int)((B + chunks - 1) / chunks);
     dim3 grid((N + 31) / 32, chunks);
-    colsum_partial_kernel<<<grid, 256, 0, s>>>(G, ldg, B, N, rows_per, h->part2);
-    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, s>>>(h->part2, out, N, chunks, n1, out2);
+    colsum_partial_kernel<<<grid, 256, 0, s>>>(G, ldg, B, N, rows_per, part);
     HRP_CUDA_OK(cudaGetLastError());
+    plan_add(plan, part, N, chunks, out, n1, out2);
     return 0;
 }
 
@@ -730,12 +742,12 @@ int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, in
     h->max_batch = max_batch; h->device = device;
     h->splits_cap = 32;
     size_t B = (size_t)max_batch, H = hidden_dim, S = state_dim, A = action_dim;
-    size_t big = 2 * H * (H > S ? H : S);   // largest weight-gradient GEMM output: [2H, H]
-    size_t part2 = 64 * ((A + 1) * H + A + 1 > 2 * H ? (A + 1) * H + A + 1 : 2 * H);
+    const size_t cap = (size_t)h->splits_cap;
     // every sub-buffer starts on a 128-byte boundary (float4 / cp.async operand staging)
     auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
     const size_t sizes[] = {B * S, B * A, B, B, B, B * H, B * H, 2 * B * H, B * A, B * A, B, B, 2 * B * H, B * H, B * H,
-                            2 * H * H, H * H, (size_t)h->splits_cap * big, part2, (size_t)LOSS_MAX_CTAS * 8, 32};
+                            2 * H * H, H * H, cap * 2 * H * H, cap * H * H, cap * H * S, 64 * 2 * H, 64 * H, 64 * H,
+                            64 * ((A + 1) * H + A + 1), (size_t)LOSS_MAX_CTAS * 8, 32};
     size_t n = 0;
     for (size_t q : sizes) n += pad(q);
     cudaError_t ce = cudaMalloc(&h->ws, n * sizeof(float));
@@ -748,10 +760,14 @@ int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, in
     h->mean = take(); h->dmean = take(); h->value = take(); h->dvalue = take();
     h->d12 = take(); h->dh2 = take(); h->dh1 = take();
     h->wt_ac = take(); h->wt_2 = take();
-    h->part = take(); h->part2 = take(); h->loss_part = take();
+    for (int q = 0; q < 3; ++q) h->part_w[q] = take();
+    for (int q = 0; q < 3; ++q) h->part_b[q] = take();
+    h->part_h = take(); h->loss_part = take();
     h->loss_counter = (unsigned *)take();
     ce = cudaMemset(h->loss_counter, 0, 32 * sizeof(float));
-    if (ce != cudaSuccess) { hrp_set_error("cudaMemset: %s", cudaGetErrorString(ce)); cudaFree(h->ws); delete h; return -2; }
+    for (int q = 0; q < 2 && ce == cudaSuccess; ++q) ce = cudaStreamCreateWithFlags(&h->side[q], cudaStreamNonBlocking);
+    for (int q = 0; q < 8 && ce == cudaSuccess; ++q) ce = cudaEventCreateWithFlags(&h->ev[q], cudaEventDisableTiming);
+    if (ce != cudaSuccess) { hrp_set_error("hrp_ppo_create: %s", cudaGetErrorString(ce)); cudaFree(h->ws); delete h; return -2; }
     *out = h;
     return 0;
 }
@@ -761,6 +777,8 @@ int hrp_ppo_destroy(hrp_ppo *h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaFree(h->ws);
+    for (int q = 0; q < 2; ++q) if (h->side[q]) cudaStreamDestroy(h->side[q]);
+    for (int q = 0; q < 8; ++q) if (h->ev[q]) cudaEventDestroy(h->ev[q]);
     delete h;
     return 0;
 }
@@ -832,11 +850,24 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         return -1;
     }
     if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
-    cudaStream_t s = (cudaStream_t)stream;
+    cudaStream_t s = (cudaStream_t)stream, s0 = h->side[0], s1 = h->side[1];
     const Layout &L = h->L;
-    const int H = L.H, S = L.S, A = L.A, Bi = (int)batch;
+    const int H = L.H, S = L.S, A = L.A, Bi = (int)batch, H2 = 2 * H;
     const long long B = batch;
     const float *x = states, *z = pre_tanh, *olp = old_log_prob, *ad = adv, *rt = ret;
+    // `from` has produced something `to` consumes (also valid while the caller's stream is being captured: the side
+    // streams join the capture and are joined back before this function returns)
+    auto after = [&](int e, cudaStream_t from, cudaStream_t to) -> cudaError_t {
+        cudaError_t ce = cudaEventRecord(h->ev[e], from);
+        return ce != cudaSuccess ? ce : cudaStreamWaitEvent(to, h->ev[e], 0);
+    };
+    // side stream 1: transposed weight copies for the input-gradient GEMMs (needs the parameters only)
+    HRP_CUDA_OK(after(0, s, s1));
+    {
+        dim3 grid((H + 31) / 32, (H + 31) / 32, 3);
+        transpose_weights_kernel<<<grid, 256, 0, s1>>>(params + L.wa1, params + L.wc1, params + L.w2, H, h->wt_ac, h->wt_2);
+        HRP_CUDA_OK(cudaGetLastError());
+    }
     if (idx) {
         const long long *ix = (const long long *)idx;
         long long tot = B * (S + A + 3);
@@ -855,38 +886,46 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         HRP_CUDA_OK(cudaGetLastError());
     }
     const float *a1 = h->ac, *c1 = h->ac + H;
-    const int H2 = 2 * H;
-    // heads: dWa2 = dmean^T a1, dba2 = colsum(dmean); dWc2 = dvalue^T c1, dbc2 = sum(dvalue)
+    ReducePlan plan;
+    plan.nseg = 0; plan.blocks = 0;
+    // side stream 0 -- heads: dWa2 = dmean^T a1, dba2 = colsum(dmean); dWc2 = dvalue^T c1, dbc2 = sum(dvalue).  The
+    // chunk sums are laid out [A*H + A | H + 1]: the first part lands on grad + wa2 (ba2 follows wa2), the second on
+    // grad + wc2.
+    HRP_CUDA_OK(after(1, s, s0));
     {
         int chunks = (int)((B + 63) / 64);
         if (chunks > 64) chunks = 64;
         int rows_per = (int)((B + chunks - 1) / chunks);
         dim3 grid((H + 31) / 32, chunks);
-        heads_wgrad_partial_kernel<<<grid, 256, 0, s>>>(h->dmean, h->dvalue, a1, c1, H2, B, H, A, rows_per, h->part2);
-        int n = A * H + A + H + 1;
-        heads_wgrad_final_kernel<<<(n + 255) / 256, 256, 0, s>>>(h->part2, chunks, H, A, grad + L.wa2, grad + L.wc2);
+        heads_wgrad_partial_kernel<<<grid, 256, 0, s0>>>(h->dmean, h->dvalue, a1, c1, H2, B, H, A, rows_per, h->part_h);
         HRP_CUDA_OK(cudaGetLastError());
+        plan_add(plan, h->part_h, (long long)A * H + A + H + 1, chunks, grad + L.wa2, (long long)A * H + A, grad + L.wc2);
     }
-    // d(a1) | d(c1) into d12 (ReLU masks applied)
+    // main: d(a1) | d(c1) into d12 (ReLU masks applied)
     heads_backward_kernel<<<(unsigned)((B * H + 255) / 256), 256, 0, s>>>(h->dmean, h->dvalue, params + L.wa2,
                                                                         params + L.wc2, a1, c1, H2, B, H, A, h->d12,
                                                                         h->d12 + H);
-    {
-        dim3 grid((H + 31) / 32, (H + 31) / 32, 3);
-        transpose_weights_kernel<<<grid, 256, 0, s>>>(params + L.wa1, params + L.wc1, params + L.w2, H, h->wt_ac, h->wt_2);
-    }
     HRP_CUDA_OK(cudaGetLastError());
-    // [dWa1 ; dWc1] = [d(a1) | d(c1)]^T h2 in one GEMM, [dba1 | dbc1] in one column sum
-    if (wgrad(h, H2, H, B, h->d12, H2, h->h2, H, grad + L.wa1, H, grad + L.wc1, s)) return -2;
-    if (colsum(h, h->d12, H2, B, H2, grad + L.ba1, H, grad + L.bc1, s)) return -2;
-    // d(h2) = [d(a1) | d(c1)] [Wa1 ; Wc1] (.) (h2>0): K = 2H against the transposed copies
+    // side 0: [dWa1 ; dWc1] = [d(a1) | d(c1)]^T h2 in one GEMM, [dba1 | dbc1] in one column sum
+    HRP_CUDA_OK(after(2, s, s0));
+    if (wgrad(h, plan, h->part_w[0], H2, H, B, h->d12, H2, h->h2, H, grad + L.wa1, H, grad + L.wc1, s0)) return -2;
+    if (colsum(plan, h->part_b[0], h->d12, H2, B, H2, grad + L.ba1, H, grad + L.bc1, s0)) return -2;
+    // main: d(h2) = [d(a1) | d(c1)] [Wa1 ; Wc1] (.) (h2>0): K = 2H against the transposed copies
+    HRP_CUDA_OK(after(3, s1, s));
     if (gemm(false, true, Bi, H, H2, h->d12, H2, h->wt_ac, H2, h->dh2, H, nullptr, 0, h->h2, H, 0, 1, s) < 0) return -2;
-    if (wgrad(h, H, H, B, h->dh2, H, h->h1, H, grad + L.w2, H, nullptr, s)) return -2;
-    if (colsum(h, h->dh2, H, B, H, grad + L.b2, H, nullptr, s)) return -2;
-    // d(h1) = d(h2) W2 (.) (h1>0)
+    // side 1: dW2, db2
+    HRP_CUDA_OK(after(4, s, s1));
+    if (wgrad(h, plan, h->part_w[1], H, H, B, h->dh2, H, h->h1, H, grad + L.w2, H, nullptr, s1)) return -2;
+    if (colsum(plan, h->part_b[1], h->dh2, H, B, H, grad + L.b2, H, nullptr, s1)) return -2;
+    // main: d(h1) = d(h2) W2 (.) (h1>0), dW1; side 0: db1
     if (gemm(false, true, Bi, H, H, h->dh2, H, h->wt_2, H, h->dh1, H, nullptr, 0, h->h1, H, 0, 1, s) < 0) return -2;
-    if (wgrad(h, H, S, B, h->dh1, H, x, S, grad + L.w1, H, nullptr, s)) return -2;
-    if (colsum(h, h->dh1, H, B, H, grad + L.b1, H, nullptr, s)) return -2;
+    HRP_CUDA_OK(after(5, s, s0));
+    if (colsum(plan, h->part_b[2], h->dh1, H, B, H, grad + L.b1, H, nullptr, s0)) return -2;
+    if (wgrad(h, plan, h->part_w[2], H, S, B, h->dh1, H, x, S, grad + L.w1, H, nullptr, s)) return -2;
+    // join, then every second-stage reduction in one launch
+    HRP_CUDA_OK(after(6, s0, s));
+    HRP_CUDA_OK(after(7, s1, s));
+    final_reduce_kernel<<<plan.blocks, 256, 0, s>>>(plan);
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }
