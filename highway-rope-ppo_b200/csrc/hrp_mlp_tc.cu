@@ -24,6 +24,10 @@
 // tensor map accepts without extra copies.  The matrices are small (<= 4 MB) and L2-resident.
 #include "hrp_internal.cuh"
 
+// phase clocks of CTA (0,0,0), thread 0 (+ the MMA warp's lane 0): see hrp_debug_gemm_phases
+__device__ long long g_tc_phase[16];
+#define TC_PHASE(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == TC_THREADS)) g_tc_phase[(i)] = clock64(); } while (0)
+
 namespace {
 
 constexpr int BM = 128, BK = 32;                  // BK * 4 B = 128 B = one swizzle row; BN is 64 or 128
@@ -260,6 +264,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) TC_PHASE(0);
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     // N-segmented B operand: output columns >= nseg multiply the rows of a second matrix (two weight matrices that
     // are not adjacent in memory act as one [N, K] operand; tiles never straddle the boundary, see hrp_tc_gemm)
@@ -290,6 +295,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
     constexpr uint32_t idesc = make_idesc(BM, BN);
+    if (tid == 0) TC_PHASE(1);
 
     if (ASYNC && warp < TC_THREADS / 32) {
         // ===== loader warps, cp.async path (A: 16-byte, B: 8-byte aligned K-contiguous operands).
@@ -364,35 +370,46 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
     } else if (warp < TC_THREADS / 32) {
-        // ===== loader warps: global -> registers (two K-blocks ahead) -> swizzled shared stage -> bar_full
-        Stager<AMODE, BM> sa0, sa1;
-        Stager<BMODE, BN> sb0, sb1;
-        auto step = [&](int kb, Stager<AMODE, BM> &sa, Stager<BMODE, BN> &sb) {
+        // ===== loader warps: global -> registers (PF K-blocks ahead) -> swizzled shared stage -> bar_full.
+        // Measured (tools/gemm_one.py phase clocks, 4096 x 256 x 256): a K-block takes ~920 cycles with PF = 2 and
+        // with PF = 4 alike -- the 3xTF32 main loop is bound by shared-memory bandwidth (48 KB of tile writes plus
+        // 72 KB of operand reads by the 12 UMMAs per K-block at 128 B/cycle), not by the L2 round trip.
+        constexpr int PF = 2;
+        Stager<AMODE, BM> sa0, sa1, sa2, sa3;   // named, not an array: the register sets must never be indexed dynamically
+        Stager<BMODE, BN> sb0, sb1, sb2, sb3;
+        auto step = [&](int kb, Stager<AMODE, BM> &ra, Stager<BMODE, BN> &rb) {
             const int s = kb % STAGES;
             if (kb >= STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((kb / STAGES) - 1) & 1));  // MMAs of kb - STAGES retired
             uint8_t *a_hi = smem + s * STAGE_BYTES, *b_hi = a_hi + PARTS * A_TILE_BYTES;
-            sa.template stash<NSPLIT>(a_hi, A_TILE_BYTES, tid);
-            sb.template stash<NSPLIT>(b_hi, B_TILE_BYTES, tid);
-            if (kb + 2 < nkb) {                             // refill this register set: in flight for two blocks
-                const int k0 = kbeg + (kb + 2) * BK;
-                sa.fetch(A, sam, sak, m0, M, k0, kend, tid);
-                sb.fetch(Bp, sbn, sbk, bn0, bN, k0, kend, tid);
+            ra.template stash<NSPLIT>(a_hi, A_TILE_BYTES, tid);
+            rb.template stash<NSPLIT>(b_hi, B_TILE_BYTES, tid);
+            if (kb + PF < nkb) {                            // refill this register set: in flight for PF blocks
+                const int k0 = kbeg + (kb + PF) * BK;
+                ra.fetch(A, sam, sak, m0, M, k0, kend, tid);
+                rb.fetch(Bp, sbn, sbk, bn0, bN, k0, kend, tid);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
         };
-        if (nkb > 0) {
-            sa0.fetch(A, sam, sak, m0, M, kbeg, kend, tid);
-            sb0.fetch(Bp, sbn, sbk, bn0, bN, kbeg, kend, tid);
+#define HRP_TC_PREFETCH(j, ra, rb)                                               \
+        if (j < nkb) {                                                              \
+            ra.fetch(A, sam, sak, m0, M, kbeg + j * BK, kend, tid);                 \
+            rb.fetch(Bp, sbn, sbk, bn0, bN, kbeg + j * BK, kend, tid);              \
         }
-        if (nkb > 1) {
-            sa1.fetch(A, sam, sak, m0, M, kbeg + BK, kend, tid);
-            sb1.fetch(Bp, sbn, sbk, bn0, bN, kbeg + BK, kend, tid);
-        }
-        for (int kb = 0; kb < nkb; kb += 2) {
+        HRP_TC_PREFETCH(0, sa0, sb0)
+        HRP_TC_PREFETCH(1, sa1, sb1)
+        if (PF > 2) { HRP_TC_PREFETCH(2, sa2, sb2) }
+        if (PF > 3) { HRP_TC_PREFETCH(3, sa3, sb3) }
+#undef HRP_TC_PREFETCH
+        if (tid == 0) TC_PHASE(2);   // first loads issued
+        for (int kb = 0; kb < nkb; kb += PF) {
             step(kb, sa0, sb0);
             if (kb + 1 < nkb) step(kb + 1, sa1, sb1);
+            if (PF > 2 && kb + 2 < nkb) step(kb + 2, sa2, sb2);
+            if (PF > 3 && kb + 3 < nkb) step(kb + 3, sa3, sb3);
+            if (kb == 0 && tid == 0) TC_PHASE(3);
         }
+        if (tid == 0) TC_PHASE(4);   // loaders done
     } else {
         // ===== MMA warp: waits for a full stage, one elected lane issues the UMMAs, tcgen05.commit frees the stage
         for (int kb = 0; kb < nkb; ++kb) {
@@ -418,6 +435,8 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
                 }
                 umma_commit(&bar_empty[s]);
                 if (kb + 1 == nkb) umma_commit(&bar_done);  // accumulator complete
+                if (kb == 0) TC_PHASE(8);
+                if (kb + 1 == nkb) TC_PHASE(9);
             }
             __syncwarp();
         }
@@ -427,7 +446,8 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     // Warp w reads TMEM lanes 32 (w % 4) .., columns (BN / 2) (w / 4) ..; the operand stages are free by now.
     if (nkb > 0) mbar_wait(&bar_done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    constexpr int LDS = BN + 1;                       // odd row pitch: conflict-free column writes
+    if (tid == 0) TC_PHASE(5);   // accumulator ready
+    constexpr int LDS = BN + 4;   // row pitch: 16-byte aligned rows; 128-bit accesses of 8 consecutive rows or chunks hit 32 banks
     float *stage_c = (float *)smem;
     if (warp < TC_THREADS / 32) {
         const int trow = 32 * (warp & 3) + lane;
@@ -449,15 +469,50 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
                 for (int j = 0; j < 16; ++j) v[j] = 0u;
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) stage_c[trow * LDS + c0 + j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 16; j += 4)
+                *(uint4 *)(stage_c + trow * LDS + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
     }
     __syncthreads();
+    if (tid == 0) TC_PHASE(6);   // tile staged in shared memory
     float *Cz = C + (size_t)blockIdx.z * M * ldc;
-    {
-        // thread t always writes column t % BN: its bias is loaded once; rows advance by TC_THREADS / BN.
-        // Rows are handled eight at a time with the global reads (accumulate, mask) of all eight issued before
-        // the first is used: one memory round trip per eight rows instead of one per row.
+    const bool vec = n0 + BN <= N && ldc % 4 == 0 && ((uintptr_t)Cz & 15) == 0 &&
+                     (mask == nullptr || (ldm % 4 == 0 && ((uintptr_t)mask & 15) == 0));
+    if (vec && tid < TC_THREADS) {
+        // whole tile inside the matrix and 16-byte aligned rows: a warp writes 512 contiguous bytes per instruction.
+        // Thread t owns the column quad t % (BN / 4); rows advance by TC_THREADS / (BN / 4), four rows per round trip.
+        constexpr int CQ = BN / 4, RSTEP = TC_THREADS / CQ, GROUP = 4;
+        const int cq = tid % CQ, gn = n0 + 4 * cq;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (biasp) bv = make_float4(biasp[bn0 + 4 * cq], biasp[bn0 + 4 * cq + 1], biasp[bn0 + 4 * cq + 2], biasp[bn0 + 4 * cq + 3]);
+        float *crow = Cz + (size_t)(m0 + tid / CQ) * ldc + gn;
+        const float *mrow = mask ? mask + (size_t)(m0 + tid / CQ) * ldm + gn : nullptr;
+        const float *srow = stage_c + (tid / CQ) * LDS + 4 * cq;
+#pragma unroll 1
+        for (int rb = tid / CQ; rb < BM; rb += RSTEP * GROUP) {
+            float4 prev[GROUP], mk[GROUP];
+#pragma unroll
+            for (int j = 0; j < GROUP; ++j) {
+                const bool ok = m0 + rb + j * RSTEP < M;
+                prev[j] = (accumulate && ok) ? *(const float4 *)(crow + (size_t)j * RSTEP * ldc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                mk[j] = (mask && ok) ? __ldg((const float4 *)(mrow + (size_t)j * RSTEP * ldm)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+#pragma unroll
+            for (int j = 0; j < GROUP; ++j) {
+                float4 x = *(const float4 *)(srow + j * RSTEP * LDS);
+                x.x += bv.x + prev[j].x; x.y += bv.y + prev[j].y; x.z += bv.z + prev[j].z; x.w += bv.w + prev[j].w;
+                if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                x.x = mk[j].x > 0.f ? x.x : 0.f; x.y = mk[j].y > 0.f ? x.y : 0.f;
+                x.z = mk[j].z > 0.f ? x.z : 0.f; x.w = mk[j].w > 0.f ? x.w : 0.f;
+                if (m0 + rb + j * RSTEP < M) *(float4 *)(crow + (size_t)j * RSTEP * ldc) = x;
+            }
+            crow += (size_t)RSTEP * GROUP * ldc;
+            if (mask) mrow += (size_t)RSTEP * GROUP * ldm;
+            srow += RSTEP * GROUP * LDS;
+        }
+    } else if (!vec) {
+        // ragged or unaligned tile: thread t writes column t % BN, rows advance by TC_THREADS / BN, eight rows per
+        // memory round trip
         constexpr int RSTEP = TC_THREADS / BN, GROUP = 8;
         const int c = tid % BN, gn = n0 + c;
         const float bv = (biasp && gn < N) ? biasp[bn0 + c] : 0.f;
@@ -483,6 +538,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
             }
         }
     }
+    if (tid == 0) TC_PHASE(7);   // tile written
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -497,7 +553,7 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;
     constexpr int STAGES = tc_stages<NSPLIT, BN, ASYNC>();
     constexpr int OPERANDS = STAGES * PARTS * (A_TILE_BYTES + BN * BK * 4);
-    constexpr int EPILOGUE = BM * (BN + 1) * 4;
+    constexpr int EPILOGUE = BM * (BN + 4) * 4;
     constexpr int SMEM = (OPERANDS > EPILOGUE ? OPERANDS : EPILOGUE) + 1024;
     static bool configured = false;
     auto kern = tc_gemm_kernel<AMODE, BMODE, NSPLIT, BN, ASYNC>;
@@ -583,4 +639,12 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     else rc = HRP_TC_GO(ST_MN1, ST_MN1);
 #undef HRP_TC_GO
     return rc < 0 ? rc : splits;
+}
+
+// debugging aid (not part of include/hrp.h): SM clock at the phase boundaries of the last GEMM's first CTA
+extern "C" int hrp_debug_gemm_phases(long long *out16)
+{
+    HRP_CUDA_OK(cudaDeviceSynchronize());
+    HRP_CUDA_OK(cudaMemcpyFromSymbol(out16, g_tc_phase, sizeof(long long) * 16));
+    return 0;
 }
