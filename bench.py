@@ -372,6 +372,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ppo = {"value": world * E * T * iters / (float(t.cpu()) * 1e-3), "unit": "samples/s", "rollout_T": T,
                "epochs": 8, "minibatch": 4096, "last_loss": m["loss"],
+               "cuda_graphs": agent._graph_state is not None, "backend": dist.get_backend() if world > 1 else None,
                "definition": "T policy+env steps then PPOAgent.update (GAE, 8 epochs, clip+Adam), amortised"}
 
     cpu = None
@@ -393,7 +394,12 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
-        dist.destroy_process_group()
+        # graphs that captured NCCL work must go before the communicator does; leave without the communicator
+        # teardown (it was seen to hang after captured collectives) once every rank is done
+        agent.release_graphs()
+        barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

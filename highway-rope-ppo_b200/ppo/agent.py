@@ -18,6 +18,8 @@ format as the reference; the arithmetic runs in ``libhrp_b200.so``:
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import logging
 from collections import OrderedDict
@@ -414,6 +416,10 @@ class PPOAgent:
         self._stats = torch.zeros(3 + 512, dtype=torch.float64, device=self.device)
         self.launches = 0  # hrp_* calls enqueued by this agent (each is >= 1 kernel of this library)
         self.use_cuda_graphs = True
+        # capture the gradient all-reduce inside the minibatch graphs (NCCL only; gloo cannot be captured).  Call
+        # release_graphs() before torch.distributed.destroy_process_group(): graphs that hold NCCL work keep the
+        # communicator busy at teardown.
+        self.graph_collectives = os.environ.get("HRP_GRAPH_COLLECTIVES", "1") != "0" and distributed.backend() == "nccl"
         self._graph_state: Optional[Dict[str, Any]] = None
 
     # -- acting ----------------------------------------------------------------------------------
@@ -450,14 +456,21 @@ class PPOAgent:
             float(self.max_grad_norm), opt.scratch.data_ptr(), s), "hrp_clip_adam_step")
         self.launches += 2
 
+    def release_graphs(self) -> None:
+        """Drop the captured minibatch graphs (they are re-captured by the next update)."""
+        if self._graph_state is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph_state = None
+
     # -- the epochs x minibatches loop as CUDA graphs --------------------------------------------------
-    def _graphed_epochs(self, flat: Dict[str, torch.Tensor], perm_dev: torch.Tensor, n: int, bs: int) -> None:
+    def _graphed_epochs(self, flat: Dict[str, torch.Tensor], perm_dev: torch.Tensor, n: int, bs: int,
+                        world: int = 1) -> None:
         """One CUDA graph per minibatch (the ~40 launches of loss/backward/clip/Adam), replayed for every epoch
         and re-used by later updates of the same size.  The rollout is first copied into persistent buffers so
         that the captured pointers stay valid.  The first epoch of a new configuration runs eagerly (it also
         warms every kernel variant before anything is captured)."""
         ac = self.actor_critic
-        key = (n, bs, ac._h.value, float(self.eps_clip), float(self.value_coef), float(self.entropy_coef),
+        key = (n, bs, world, ac._h.value, float(self.eps_clip), float(self.value_coef), float(self.entropy_coef),
                float(self.max_grad_norm), self.optimizer.lr, self.optimizer.betas, self.optimizer.eps)
         st = self._graph_state
         if st is None or st["key"] != key:
@@ -474,7 +487,7 @@ class PPOAgent:
             if not st["warm"]:
                 for start in starts:
                     B = min(bs, n - start)
-                    self._minibatch_step(st["buf"], st["perm"][start:start + B], B, 1)
+                    self._minibatch_step(st["buf"], st["perm"][start:start + B], B, world)
                 st["warm"] = True
                 continue
             for i, start in enumerate(starts):
@@ -483,7 +496,7 @@ class PPOAgent:
                     B = min(bs, n - start)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        self._minibatch_step(st["buf"], st["perm"][start:start + B], B, 1)
+                        self._minibatch_step(st["buf"], st["perm"][start:start + B], B, world)
                     st["graphs"][i] = g
                 g.replay()
                 self.launches += 2
@@ -515,8 +528,9 @@ class PPOAgent:
         bs = int(mem.batch_size)
         ac._ensure_workspace(min(bs, n))
         self._metrics.zero_()
-        if self.use_cuda_graphs and world == 1:
-            self._graphed_epochs(flat, perm_dev, n, bs)
+        if self.use_cuda_graphs and (world == 1 or self.graph_collectives):
+            # with several ranks the NCCL all-reduce of the flat gradient is captured inside each minibatch graph
+            self._graphed_epochs(flat, perm_dev, n, bs, world)
         else:
             for _ in range(self.epochs):
                 for start in range(0, n, bs):
