@@ -23,7 +23,6 @@
 // flat parameter buffer and half of the backward operands are MN-contiguous, neither of which a 128B-swizzled
 // tensor map accepts without extra copies.  The matrices are small (<= 4 MB) and L2-resident.
 #include "hrp_internal.cuh"
-#include <stdlib.h>
 
 // phase clocks of CTA (0,0,0), thread 0 (+ the MMA warp's lane 0): see hrp_debug_gemm_phases
 __device__ long long g_tc_phase[16];
@@ -557,239 +556,10 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
 }
 
-// =====================================================================================================================
-// A-in-TMEM variant.  With both operands in shared memory the 3xTF32 main loop is bound by shared-memory bandwidth:
-// per K-block the loaders write 48 KB of hi/lo tiles and the 12 UMMAs read 72 KB, ~920 cycles at 128 B/cycle against
-// ~384 cycles of tensor-core time (measured with the phase clocks above).  Two thirds of that traffic is the A tile,
-// so here A never touches shared memory: loader thread t owns row t % 128 of the tile and the 16-element K half
-// t / 128, loads it global -> registers, splits it and writes hi / lo straight into tensor memory with tcgen05.st
-// (row = TMEM lane, k = TMEM column); the MMAs take A from TMEM (`tcgen05.mma [d], [a], b_desc`).  Only the B tile
-// (weights, BN rows) goes through the swizzled shared-memory stages.  TMEM columns: [0, BN) accumulator, then
-// STAGES x (hi[32] | lo[32]).
-//   AVEC = true : A is K-contiguous and 16-byte aligned (4 x float4 per thread)
-//   AVEC = false: any strides (16 scalars; lanes are consecutive rows, so an M-contiguous A coalesces)
-constexpr int TS_STAGES = 4, TS_PF = 4;
-
-template <bool AVEC>
-struct RowStager {
-    float v[16];
-    __device__ __forceinline__ void fetch(const float *__restrict__ A, long long sam, long long sak, int gr, int M, int gk,
-                                          int kend)
-    {
-        if (AVEC) {
-            const float4 *src = reinterpret_cast<const float4 *>(A + (long long)gr * sam + gk);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (gr < M && gk + 4 * i < kend) t = __ldg(src + i);
-                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                v[i] = (gr < M && gk + i < kend) ? __ldg(A + (long long)gr * sam + (long long)(gk + i) * sak) : 0.f;
-        }
-    }
-};
-
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-template <bool AVEC, int BMODE, int NSPLIT, int BN>
-__global__ void __launch_bounds__(TC_LAUNCH_THREADS)
-tc_gemm_ts_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, long long sak,
-                  const float *__restrict__ B, long long sbn, long long sbk, float *__restrict__ C, int ldc,
-                  const float *__restrict__ bias, int relu, const float *__restrict__ mask, int ldm, int accumulate,
-                  int k_chunk, int nseg, const float *__restrict__ B2, const float *__restrict__ bias2)
-{
-    constexpr int PARTS = NSPLIT == 3 ? 2 : 1;
-    constexpr int B_TILE_BYTES = BN * BK * 4;
-    constexpr int STAGE_BYTES = PARTS * B_TILE_BYTES;
-    constexpr int STAGES = TS_STAGES;
-    constexpr int A_COLS = PARTS * BK;                                         // TMEM columns of one A stage
-    constexpr int TM_COLS = BN + STAGES * A_COLS <= 256 ? 256 : 512;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_done;
-    __shared__ uint32_t tmem_base_s;
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) TC_PHASE(0);
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const bool seg2 = nseg > 0 && n0 >= nseg;
-    const float *__restrict__ Bp = seg2 ? B2 : B;
-    const float *__restrict__ biasp = seg2 ? bias2 : bias;
-    const int bn0 = seg2 ? n0 - nseg : n0;
-    const int bN = nseg > 0 ? (seg2 ? N - nseg : nseg) : N;
-    const int kbeg = blockIdx.z * k_chunk, kend = min(K, kbeg + k_chunk);
-    const int nkb = (kend - kbeg + BK - 1) / BK;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bar_full[s], TC_THREADS);
-            mbar_init(&bar_empty[s], 1);
-        }
-        mbar_init(&bar_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "n"(TM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = tmem_base_s;
-    constexpr uint32_t idesc = make_idesc(BM, BN);
-    if (tid == 0) TC_PHASE(1);
-
-    if (warp < TC_THREADS / 32) {
-        // ===== loader warps.  Warp w may touch TMEM lanes 32 (w % 4) .. + 31: thread t <-> tile row t % 128.
-        const int row = tid & 127, khalf = (tid >> 7) * 16;
-        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-        RowStager<AVEC> ra0, ra1, ra2, ra3;
-        Stager<BMODE, BN> rb0, rb1, rb2, rb3;
-        // a macro, not a lambda: the register sets must stay in registers, i.e. every use has to be inlined
-#define HRP_TS_STEP(kb_, ra, rb)                                                                                  \
-        {                                                                                                         \
-            const int kq = (kb_), sq = kq % STAGES;                                                                \
-            if (kq >= STAGES) {                                                                                   \
-                mbar_wait(&bar_empty[sq], (uint32_t)(((kq / STAGES) - 1) & 1)); /* MMAs of kq - STAGES retired */  \
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                   \
-            }                                                                                                     \
-            const uint32_t a_t = tmem_d + lane_base + (uint32_t)(BN + sq * A_COLS + khalf);                        \
-            uint32_t hi[16];                                                                                      \
-            _Pragma("unroll") for (int i = 0; i < 16; ++i)                                                        \
-                hi[i] = NSPLIT == 3 ? (__float_as_uint(ra.v[i]) & 0xFFFFE000u) : __float_as_uint(ra.v[i]);        \
-            tmem_st16(a_t, hi);                                                                   \
-            if (NSPLIT == 3) {                                                                                    \
-                uint32_t lo[16];                                                                                  \
-                _Pragma("unroll") for (int i = 0; i < 16; ++i)                                                    \
-                    lo[i] = __float_as_uint(ra.v[i] - __uint_as_float(hi[i]));                                    \
-                tmem_st16(a_t + BK, lo);                                                          \
-            }                                                                                                     \
-            rb.template stash<NSPLIT>(smem + sq * STAGE_BYTES, B_TILE_BYTES, tid);                 \
-            if (kq + TS_PF < nkb) {                                                                               \
-                const int k0 = kbeg + (kq + TS_PF) * BK;                                                          \
-                ra.fetch(A, sam, sak, m0 + row, M, k0 + khalf, kend);                                             \
-                rb.fetch(Bp, sbn, sbk, bn0, bN, k0, kend, tid);                                                   \
-            }                                                                                                     \
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");                                          \
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                          \
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                      \
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_full[sq])) : "memory");    \
-        }
-#define HRP_TS_PREFETCH(j, ra, rb)                                                     \
-        if (j < nkb) {                                                                 \
-            ra.fetch(A, sam, sak, m0 + row, M, kbeg + j * BK + khalf, kend);           \
-            rb.fetch(Bp, sbn, sbk, bn0, bN, kbeg + j * BK, kend, tid);                 \
-        }
-        HRP_TS_PREFETCH(0, ra0, rb0)
-        HRP_TS_PREFETCH(1, ra1, rb1)
-        HRP_TS_PREFETCH(2, ra2, rb2)
-        HRP_TS_PREFETCH(3, ra3, rb3)
-#undef HRP_TS_PREFETCH
-        if (tid == 0) TC_PHASE(2);
-        for (int kb = 0; kb < nkb; kb += TS_PF) {
-            HRP_TS_STEP(kb, ra0, rb0)
-            if (kb + 1 < nkb) HRP_TS_STEP(kb + 1, ra1, rb1)
-            if (kb + 2 < nkb) HRP_TS_STEP(kb + 2, ra2, rb2)
-            if (kb + 3 < nkb) HRP_TS_STEP(kb + 3, ra3, rb3)
-            if (kb == 0 && tid == 0) TC_PHASE(3);
-        }
-#undef HRP_TS_STEP
-        if (tid == 0) TC_PHASE(4);
-    } else {
-        // ===== MMA warp
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            mbar_wait(&bar_full[s], (uint32_t)((kb / STAGES) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint64_t db_hi = make_desc(smem_u32(smem + s * STAGE_BYTES));
-                const uint64_t db_lo = db_hi + (B_TILE_BYTES >> 4);
-                const uint32_t a_hi = tmem_d + (uint32_t)(BN + s * A_COLS), a_lo = a_hi + BK;
-#pragma unroll
-                for (int kk = 0; kk < BK / 8; ++kk) {       // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
-                    const uint64_t o = (uint64_t)(kk * 2);
-                    const uint32_t ac = (uint32_t)(kk * 8);
-                    const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-                    if (NSPLIT == 3) {
-                        umma_tf32_ts(tmem_d, a_lo + ac, db_hi + o, idesc, acc);
-                        umma_tf32_ts(tmem_d, a_hi + ac, db_lo + o, idesc, 1u);
-                        umma_tf32_ts(tmem_d, a_hi + ac, db_hi + o, idesc, 1u);
-                    } else {
-                        umma_tf32_ts(tmem_d, a_hi + ac, db_hi + o, idesc, acc);
-                    }
-                }
-                umma_commit(&bar_empty[s]);
-                if (kb + 1 == nkb) umma_commit(&bar_done);
-                if (kb == 0) TC_PHASE(8);
-                if (kb + 1 == nkb) TC_PHASE(9);
-            }
-            __syncwarp();
-        }
-    }
-    tc_epilogue<BN>(smem, &bar_done, tmem_d, nkb, M, N, m0, n0, bn0, C, ldc, biasp, relu, mask, ldm, accumulate);
-    if (tid == 0) TC_PHASE(7);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TM_COLS) : "memory");
-}
-
-template <bool AVEC, int BMODE, int NSPLIT, int BN>
-int launch_ts(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
-              const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias, int relu,
-              const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2, const float *bias2)
-{
-    constexpr int PARTS = NSPLIT == 3 ? 2 : 1;
-    constexpr int OPERANDS = TS_STAGES * PARTS * BN * BK * 4;
-    constexpr int EPILOGUE = BM * (BN + 4) * 4;
-    constexpr int SMEM = (OPERANDS > EPILOGUE ? OPERANDS : EPILOGUE) + 1024;
-    static bool configured = false;
-    auto kern = tc_gemm_ts_kernel<AVEC, BMODE, NSPLIT, BN>;
-    if (!configured) {
-        HRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        configured = true;
-    }
-    kern<<<grid, TC_LAUNCH_THREADS, SMEM, s>>>(M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate,
-                                              k_chunk, nseg, B2, bias2);
-    HRP_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-template <bool AVEC, int BMODE>
-int dispatch_ts(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
-                long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
-                int relu, const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2,
-                const float *bias2)
-{
-#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2
-    if (bn == 64) return nsplit == 3 ? launch_ts<AVEC, BMODE, 3, 64>(HRP_TC_ARGS) : launch_ts<AVEC, BMODE, 1, 64>(HRP_TC_ARGS);
-    return nsplit == 3 ? launch_ts<AVEC, BMODE, 3, 128>(HRP_TC_ARGS) : launch_ts<AVEC, BMODE, 1, 128>(HRP_TC_ARGS);
-#undef HRP_TC_ARGS
-}
+// A variant that kept the A operand in tensor memory (loader thread = tile row, tcgen05.st of the hi / lo halves,
+// TS-form `tcgen05.mma [d], [a], b_desc`) was built and is parity-green in the history of this file; it removes the
+// A tile's 80 KB per K-block from shared memory but forces row-per-thread global loads, and measured slower: 1030
+// vs 920 cycles per K-block for K-contiguous A, twice as slow for batch-major A (tools/gemm_one.py phase clocks).
 
 template <int AMODE, int BMODE, int NSPLIT, int BN, bool ASYNC = false>
 int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
@@ -872,17 +642,6 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     const bool b_mn4 = sbn == 1 && N % 4 == 0 && sbk % 4 == 0 && aligned(B, 16) && nseg == 0;
 #define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2)
     int rc;
-    static const bool use_ts = !(getenv("HRP_TC_TS") && getenv("HRP_TC_TS")[0] == '0');
-#define HRP_TS_GO(av, bm) dispatch_ts<av, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2)
-    if (use_ts && nsplit == 3) {
-        // A through tensor memory; B staged by the widest mode its strides and alignment allow
-        if (a_k4) rc = b_k4 ? HRP_TS_GO(true, ST_K4) : b_k2 ? HRP_TS_GO(true, ST_K2) : b_mn4 ? HRP_TS_GO(true, ST_MN4)
-                            : bkc ? HRP_TS_GO(true, ST_K1) : HRP_TS_GO(true, ST_MN1);
-        else rc = b_k4 ? HRP_TS_GO(false, ST_K4) : b_k2 ? HRP_TS_GO(false, ST_K2) : b_mn4 ? HRP_TS_GO(false, ST_MN4)
-                       : bkc ? HRP_TS_GO(false, ST_K1) : HRP_TS_GO(false, ST_MN1);
-        return rc < 0 ? rc : splits;
-    }
-#undef HRP_TS_GO
     // cp.async staging pays off for the single-pass mode only (measured: 3xTF32 hidden forward 12.6 us register-staged
     // vs 14.5 us cp.async -- the lo tiles need a second pass through shared memory; TF32 H=512 19.6 -> 16.6 us)
     if (a_k4 && b_k2 && nsplit == 1) rc = dispatch_async(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2);
