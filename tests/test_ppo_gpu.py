@@ -251,3 +251,41 @@ def test_in_kernel_sampling_is_standard_normal_and_self_consistent():
     torch.manual_seed(3)
     b = _agent(60, 2, 64, 8192)
     assert torch.equal(b.act(x)["pre_tanh"], out1["pre_tanh"])
+
+
+def test_loads_a_checkpoint_written_by_the_reference_agent():
+    """tests/golden/checkpoint_ref_s12_h16.pth was written by the reference's PPOAgent.save (agent.py:310-318) after
+    one update; dims are inferred the way visualize.py:53-58 does.  Outputs must match the reference network's, the
+    Adam state must land in the flat moment buffers."""
+    import os
+
+    from highway_rope_ppo_b200.ppo.agent import PPOAgent
+
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    g = golden("checkpoint_ref_s12_h16_outputs.npz")
+    chk = torch.load(os.path.join(here, "checkpoint_ref_s12_h16.pth"), map_location="cpu")
+    assert set(chk) >= {"model", "optimizer"}
+    sd = chk["model"]
+    hidden_dim, state_dim = sd["shared.0.weight"].shape
+    action_dim = sd["actor_mean.2.weight"].shape[0]
+    agent = PPOAgent(state_dim, action_dim, hidden_dim=hidden_dim, device="cuda:0")
+    cfg = agent.load(os.path.join(here, "checkpoint_ref_s12_h16.pth"))
+    assert cfg == {}
+    mean, std, value = agent.actor_critic.forward(torch.from_numpy(g["states"]).cuda())
+    np.testing.assert_allclose(mean.cpu().numpy(), g["mean"], atol=2e-5)
+    np.testing.assert_allclose(value.cpu().numpy().reshape(g["value"].shape), g["value"], atol=2e-5)
+    np.testing.assert_allclose(std.cpu().numpy().reshape(-1)[:action_dim], g["std"].reshape(-1)[:action_dim], rtol=1e-6)
+    opt = agent.optimizer
+    assert int(opt.step_dev.item()) == int(g["step"]) and opt.lr == pytest.approx(float(g["lr"]))
+    n0 = action_dim  # log_std comes first in the flat layout, shared.0.weight second
+    w1 = opt.exp_avg[n0:n0 + hidden_dim * state_dim].cpu().numpy().reshape(hidden_dim, state_dim)
+    np.testing.assert_array_equal(w1, g["exp_avg_w1"])
+    # and the round trip: what this agent saves, torch loads back with the reference's key names and shapes
+    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), "hrp_ckpt_roundtrip.pth")
+    agent.save(out)
+    back = torch.load(out, map_location="cpu")
+    assert list(back["model"]) == list(sd)
+    for k in sd:
+        assert torch.equal(back["model"][k], sd[k]), k
+    assert back["optimizer"]["param_groups"][0]["lr"] == chk["optimizer"]["param_groups"][0]["lr"]
+    os.remove(out)

@@ -1,0 +1,56 @@
+"""Sweep front-end against the reference's own experiment grid: tests/golden/sweep_experiments.json
+holds the names main.py:42-88 generates (tools/gen_golden.py:gen_sweep)."""
+import json
+import os
+
+import pytest
+
+from highway_rope_ppo_b200.experiments import sweep
+from highway_rope_ppo_b200.experiments.config import Condition
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sweep_experiments.json")))
+
+
+def test_experiment_grid_matches_the_reference_names_and_order():
+    ex = sweep.define_experiments(GOLD["seed"], 3)
+    assert len(ex) == GOLD["count"] == 540
+    assert [e.name for e in ex] == GOLD["names"]
+    assert sorted({e.seed for e in ex}) == GOLD["seeds"]
+    for k, v in GOLD["first_hp"].items():
+        assert getattr(ex[0].hp, k) == v, k
+    assert ex[0].condition is Condition.SORTED and ex[-1].condition is Condition.SHUFFLED_ROPE
+    assert all(not e.hp.sweep for e in ex)  # expanded entries carry no sweep of their own
+
+
+def test_selection_rules():
+    ex = sweep.define_experiments(42, 1)
+    n = len(ex)
+    # SLURM-array batches: contiguous ceil(n / tasks) slices that cover the list exactly once
+    tasks = 7
+    got = [e.name for t in range(tasks) for e in sweep.select_experiments(ex, array_task_id=t, num_tasks=tasks)]
+    assert got == [e.name for e in ex]
+    assert sweep.select_experiments(ex, array_task_id=tasks + 5, num_tasks=tasks) == []
+    # exact name first, then unique prefix
+    assert sweep.select_experiments(ex, single=ex[3].name) == [ex[3]]
+    prefix = ex[-1].name[:-len("seed42")]
+    assert sweep.select_experiments(ex, single=prefix) == [ex[-1]]
+    with pytest.raises(ValueError):
+        sweep.select_experiments(ex, single="sorted_")        # ambiguous
+    with pytest.raises(ValueError):
+        sweep.select_experiments(ex, single="no_such_run")    # missing
+    # round-robin shard over ranks: a partition
+    parts = [sweep.shard_for_rank(ex, r, 8) for r in range(8)]
+    assert sorted(e.name for p in parts for e in p) == sorted(e.name for e in ex)
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert n == 180
+
+
+def test_summarize_picks_the_best_final_average_per_condition():
+    res = [{"experiment_name": "sorted_lr0.0001_seed42", "avg_rewards": [1.0, 5.0]},
+           {"experiment_name": "sorted_lr0.0003_seed42", "avg_rewards": [9.0, 4.0]},
+           {"experiment_name": "shuffled_rope_lr0.0003_seed42", "avg_rewards": [2.0]},
+           {"experiment_name": "shuffled_lr0.0003_seed42", "status": "FAILED"}]
+    best = sweep.summarize(res)
+    assert best["sorted"] == (5.0, "sorted_lr0.0001_seed42")
+    assert best["shuffled"] == (2.0, "shuffled_rope_lr0.0003_seed42")  # the reference keys on the first name token
+    assert len(best) == 2

@@ -231,10 +231,70 @@ def gen_ppo():
     print("ppo fixtures written")
 
 
+def gen_sweep():
+    """Experiment names of the reference's full grid (main.py:42-88).  main.py builds a DevicePool and an
+    ExperimentRunner (gymnasium + highway_env) when imported, so define_experiments is executed from its source
+    text against the reference's own experiments.config."""
+    import json
+    import re
+
+    from experiments.config import CommonHP, Condition, ConditionHP, Experiment, expand_condition_hps
+
+    src = open(os.path.join(REF, "main.py")).read()
+    fn = re.search(r"def define_experiments\(.*?\n    return experiments\n", src, re.S).group(0)
+    seed = int(re.search(r"^SEED\s*=\s*(\d+)", open(os.path.join(REF, "utils", "reproducibility.py")).read(), re.M).group(1))
+    ns = dict(Experiment=Experiment, Condition=Condition, ConditionHP=ConditionHP, CommonHP=CommonHP,
+              expand_condition_hps=expand_condition_hps, SEED=seed)
+    exec(fn, ns)
+    ex = ns["define_experiments"](seed, 3)
+    keys = ("lr", "hidden_dim", "clip_eps", "entropy_coef", "epochs", "batch_size", "d_embed", "gamma", "lam",
+            "value_coef", "max_grad_norm", "steps_per_update")
+    out = {"seed": seed, "count": len(ex), "names": [e.name for e in ex],
+           "first_hp": {k: getattr(ex[0].hp, k) for k in keys}, "seeds": sorted(set(e.seed for e in ex))}
+    json.dump(out, open(os.path.join(OUT, "sweep_experiments.json"), "w"))
+    print("sweep fixture written:", len(ex), "experiments")
+
+
+def gen_checkpoint():
+    """A checkpoint written by the reference's PPOAgent.save after one update (agent.py:310-318), with the network
+    outputs on fixed states: pins the checkpoint wire format (model + optimizer state dicts)."""
+    import torch
+
+    from ppo.agent import PPOAgent
+
+    S, H, n = 12, 16, 64
+    torch.manual_seed(7)
+    np.random.seed(7)
+    agent = PPOAgent(S, 2, lr=1e-3, epochs=2, batch_size=32, hidden_dim=H, device="cpu")
+    rng = np.random.default_rng(7)
+    st = (rng.standard_normal((n, S)) * 0.5).astype(np.float32)
+    for t in range(n):
+        a, z, lp, v = agent.select_action(st[t])
+        agent.memory.store(st[t], a, z, float(rng.random()), st[t], lp, bool(rng.random() < 0.05), v)
+    agent.update(last_value=0.0)
+    path = os.path.join(OUT, "checkpoint_ref_s12_h16.pth")
+    agent.save(path)
+    with torch.no_grad():
+        mean, std, value = agent.actor_critic(torch.from_numpy(st))
+    opt = agent.optimizer.state_dict()
+    np.savez_compressed(os.path.join(OUT, "checkpoint_ref_s12_h16_outputs.npz"), states=st, mean=mean.numpy(),
+                        std=std.numpy(), value=value.numpy(), step=np.array(float(opt["state"][0]["step"])),
+                        exp_avg_w1=opt["state"][1]["exp_avg"].numpy(), lr=np.array(opt["param_groups"][0]["lr"]))
+    print("checkpoint fixture written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--extra-only" in sys.argv:
+        sys.path.insert(0, REF)
+        install_gymnasium_stub()
+        gen_sweep()
+        gen_checkpoint()
+        sys.exit(0)
     gym = install_gymnasium_stub()
     gen_embed(gym)
     gen_ppo()
+    gen_sweep()
+    gen_checkpoint()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
