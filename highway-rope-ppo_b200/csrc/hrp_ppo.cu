@@ -12,6 +12,7 @@
 // actor_mean.2.{weight[A,H],bias[A]}, critic.0.{weight[H,H],bias[H]}, critic.2.{weight[1,H],bias[1]}.
 // Gradients, Adam moments use the same layout, so the optimizer (and the multi-GPU
 // all-reduce) touch one contiguous range.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "hrp_internal.cuh"
@@ -141,8 +142,17 @@ __global__ void __launch_bounds__(256) final_reduce_kernel(const ReducePlan P)
     const ReduceSeg &g = P.seg[q];
     long long i = (long long)(blockIdx.x - g.block0) * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
+    // split order, eight loads in flight at a time (the longest segment sets the duration of the launch)
     float s = 0.f;
-    for (int z = 0; z < g.splits; ++z) s += g.part[(size_t)z * g.n + i];
+    int z = 0;
+    for (; z + 8 <= g.splits; z += 8) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = __ldcg(g.part + (size_t)(z + j) * g.n + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += t[j];
+    }
+    for (; z < g.splits; ++z) s += __ldcg(g.part + (size_t)z * g.n + i);
     if (i < g.n1) g.dst[i] = s;
     else g.dst2[i - g.n1] = s;
 }
@@ -448,6 +458,182 @@ ppo_loss_kernel(const float *__restrict__ mean, const float *__restrict__ value,
     }
 }
 
+// heads + PPO loss + the gradient of the hidden head layers in one launch (agent.py:76-84, 223-245): a CTA owns 16
+// rows.  Phase 0: a warp per row forms mean[A] and value from a1 | c1 (row pitch ld).  Phase 1: one thread per row
+// evaluates the loss terms, writes d(mean), d(value) (the head weight gradients need them) and keeps them in shared
+// memory.  Phase 2: the CTA writes d(a1) | d(c1) = (dmean Wa2 | dvalue Wc2) under the ReLU masks for its rows.
+// Every CTA leaves 8 partial sums in part[blockIdx.x][8]; the CTA that finishes last adds them in block order
+// (deterministic) and writes d(log_std) and the metrics.  `counter` returns to zero.
+constexpr int HLB_ROWS = 16;
+__global__ void __launch_bounds__(256)
+heads_loss_backward_kernel(const float *__restrict__ a1, const float *__restrict__ c1, int ld, int H,
+                           const float *__restrict__ wa2, const float *__restrict__ ba2,
+                           const float *__restrict__ wc2, const float *__restrict__ bc2,
+                           const float *__restrict__ log_std, const float *__restrict__ pre_tanh,
+                           const float *__restrict__ old_lp, const float *__restrict__ adv,
+                           const float *__restrict__ ret, long long B, int A, float eps_clip, float value_coef,
+                           float entropy_coef, float scale, float *__restrict__ dmean, float *__restrict__ dvalue,
+                           float *__restrict__ da1, float *__restrict__ dc1, float *__restrict__ dlog_std,
+                           float *__restrict__ metrics, float *__restrict__ part, unsigned *__restrict__ counter)
+{
+    __shared__ float out_s[HLB_ROWS][5], dmean_s[HLB_ROWS][4], dvalue_s[HLB_ROWS];
+    __shared__ float red[8][8];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long row0 = (long long)blockIdx.x * HLB_ROWS;
+    const int rows = (int)min((long long)HLB_ROWS, B - row0);
+    // ---- phase 0: heads.  The loads of a row's dot products are issued together (one memory round trip per row).
+    for (int r = w; r < rows; r += 8) {
+        const float *ra = a1 + (size_t)(row0 + r) * ld, *rc = c1 + (size_t)(row0 + r) * ld;
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int k = lane; k < H; k += 32) {
+            const float xa = ra[k], xc = rc[k];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                if (a < A) acc[a] = fmaf(xa, wa2[(size_t)a * H + k], acc[a]);
+            acc[4] = fmaf(xc, wc2[k], acc[4]);
+        }
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc[a] += __shfl_xor_sync(HRP_FULL, acc[a], d);
+        if (lane == 0) {
+            for (int a = 0; a < A; ++a) out_s[r][a] = acc[a] + ba2[a];
+            out_s[r][A] = acc[4] + bc2[0];
+        }
+    }
+    __syncthreads();
+    // ---- phase 1: loss terms, one thread per row (warps 0 and 1)
+    float vals[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // pol, val, clip, kl, dls[4]
+    float ls_[4];
+    for (int a = 0; a < A; ++a) ls_[a] = log_std[a];
+    if (threadIdx.x < rows) {
+        const int r = threadIdx.x;
+        const long long b = row0 + r;
+        float lp = 0.f;
+        float dmu[4], dls[4];
+        for (int a = 0; a < A; ++a) {
+            float mu = out_s[r][a], ls = ls_[a], sd = expf(ls);
+            float z = pre_tanh[b * A + a];
+            float t = tanhf(z);
+            float d = z - mu, var = sd * sd;
+            lp += -(d * d) / (2.f * var) - ls - 0.91893853320467274f;
+            lp -= log1pf(-(t * t) + 1e-6f);
+            dmu[a] = d / var;
+            dls[a] = d * d / var - 1.f;
+        }
+        float lr = lp - old_lp[b];
+        float ratio = expf(lr);
+        float ad = adv[b];
+        float surr1 = ratio * ad;
+        float rc2 = fminf(fmaxf(ratio, 1.f - eps_clip), 1.f + eps_clip);
+        float surr2 = rc2 * ad;
+        bool inr = ratio >= 1.f - eps_clip && ratio <= 1.f + eps_clip;
+        // d min(surr1, surr2) / d ratio with torch's tie rule (half each on equality)
+        float g;
+        if (surr1 < surr2) g = ad;
+        else if (surr1 == surr2) g = 0.5f * ad + (inr ? 0.5f * ad : 0.f);
+        else g = inr ? ad : 0.f;
+        float dlp = -g * ratio * scale;
+        for (int a = 0; a < 4; ++a) dmean_s[r][a] = 0.f;
+        for (int a = 0; a < A; ++a) {
+            float dm = dlp * dmu[a];
+            dmean[b * A + a] = dm;
+            dmean_s[r][a] = dm;
+            vals[4 + a] = dlp * dls[a];
+        }
+        float dv = out_s[r][A] - ret[b];
+        float dvv = value_coef * 2.f * dv * scale;
+        dvalue[b] = dvv;
+        dvalue_s[r] = dvv;
+        vals[0] = -fminf(surr1, surr2);
+        vals[1] = dv * dv;
+        vals[2] = fabsf(ratio - 1.f) > eps_clip ? 1.f : 0.f;
+        vals[3] = (ratio - 1.f) - lr;
+    }
+    if (w < 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float x = vals[i];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(HRP_FULL, x, d);
+            if (lane == 0) red[w][i] = x;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        part[blockIdx.x * 8 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x];
+        __threadfence();
+    }
+    // ---- phase 2: d(a1) | d(c1) for the CTA's rows.  A thread owns a column (its head weights stay in registers)
+    // and walks the rows with all mask loads in flight.
+    for (int k = threadIdx.x; k < H; k += 256) {
+        float wk[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) wk[a] = a < A ? wa2[(size_t)a * H + k] : 0.f;
+        const float wck = wc2[k];
+        float ma[HLB_ROWS], mc[HLB_ROWS];
+#pragma unroll
+        for (int r = 0; r < HLB_ROWS; ++r) {
+            const size_t o = (size_t)(row0 + r) * ld + k;
+            ma[r] = r < rows ? a1[o] : 0.f;
+            mc[r] = r < rows ? c1[o] : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < HLB_ROWS; ++r) {
+            if (r >= rows) break;
+            const size_t o = (size_t)(row0 + r) * ld + k;
+            float sacc = 0.f;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) sacc = fmaf(dmean_s[r][a], wk[a], sacc);
+            da1[o] = ma[r] > 0.f ? sacc : 0.f;
+            dc1[o] = mc[r] > 0.f ? dvalue_s[r] * wck : 0.f;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned prev = atomicAdd(counter, 1u);
+        last = prev == gridDim.x - 1;
+        if (last) *counter = 0u;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // thread t adds the sums of CTAs t, t + 256, ... in order; then warps, then the 8 warps, always in index order
+    float v8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (unsigned c = threadIdx.x; c < gridDim.x; c += 256)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v8[j] += __ldcg(part + c * 8 + j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float x = v8[j];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(HRP_FULL, x, d);
+        v8[j] = x;
+    }
+    if (lane == 0)
+        for (int j = 0; j < 8; ++j) red[w][j] = v8[j];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot[8];
+        for (int j = 0; j < 8; ++j) {
+            float x = 0.f;
+            for (int i = 0; i < 8; ++i) x += red[i][j];
+            tot[j] = x;
+        }
+        float ent = 0.f;
+        for (int a = 0; a < A; ++a) ent += 0.5f + 0.91893853320467274f + ls_[a];
+        float pol = tot[0] * scale, val = tot[1] * scale;
+        float frac = (float)B * scale;  // share of the global minibatch held by this shard
+        float loss = pol + value_coef * val - entropy_coef * ent * frac;
+        for (int a = 0; a < A; ++a) dlog_std[a] = tot[4 + a] - entropy_coef * frac;
+        if (metrics) {
+            metrics[0] += loss; metrics[1] += pol; metrics[2] += val; metrics[3] += ent * frac;
+            metrics[4] += tot[2] * scale; metrics[5] += tot[3] * scale; metrics[6] += frac;
+        }
+    }
+}
+
 // d(a1) = dmean Wa2 (.) (a1>0) and d(c1) = dvalue Wc2 (.) (c1>0): rank-A / rank-1 outer products
 __global__ void heads_backward_kernel(const float *__restrict__ dmean, const float *__restrict__ dvalue,
                                       const float *__restrict__ wa2, const float *__restrict__ wc2,
@@ -527,54 +713,62 @@ __global__ void adv_normalize_kernel(float *__restrict__ adv, long long n, const
     adv[i] = (adv[i] - m) / (sd + 1e-8f);
 }
 
-// clip_grad_norm_ + Adam (agent.py:249-252), two launches: partial sums of squares, then update
-__global__ void __launch_bounds__(256)
-gradnorm_kernel(const float *__restrict__ g, long long n, float *__restrict__ part)
+// clip_grad_norm_ + Adam.step (agent.py:249-252) in ONE cooperative launch: every CTA leaves the sum of squares of
+// its slice of the gradient in part[blockIdx.x], the grid synchronises, every CTA adds the partials in the same
+// fixed order (so the clip coefficient is identical everywhere and from run to run), then updates its slice and
+// CTA 0 advances the step counter.  ADAM_MAX_CTAS partials fit the caller's 128-float scratch buffer.
+constexpr int ADAM_MAX_CTAS = 120, ADAM_THREADS = 512;
+__global__ void __launch_bounds__(ADAM_THREADS)
+clip_adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                 float *__restrict__ v, int32_t *__restrict__ step, long long n, double lr, double beta1,
+                 double beta2, double eps, float max_norm, float *__restrict__ part)
 {
-    __shared__ float red[8];
+    __shared__ float red[ADAM_THREADS / 32];
+    __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float s = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        s = fmaf(g[i], g[i], s);
+    for (long long i = i0; i < n; i += stride) s = fmaf(g[i], g[i], s);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(HRP_FULL, s, d);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
-        for (int i = 0; i < 8; ++i) t += red[i];
+        for (int i = 0; i < ADAM_THREADS / 32; ++i) t += red[i];
         part[blockIdx.x] = t;
     }
-}
-__global__ void __launch_bounds__(256)
-clip_adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
-                 float *__restrict__ v, const int32_t *__restrict__ step, long long n, double lr, double beta1,
-                 double beta2, double eps, float max_norm, const float *__restrict__ part, int nparts)
-{
-    // torch.optim.Adam forms its scalars in Python doubles and hands float32 values to the kernels
-    __shared__ float s_coef, s_step_size, s_bc2_sqrt;
-    if (threadIdx.x == 0) {
+    const int k = step[0] + 1;   // read before the barrier, advanced after it
+    cooperative_groups::this_grid().sync();
+    if (threadIdx.x < 32) {
+        // partials in index order, four per lane, then a fixed shuffle tree
         float t = 0.f;
-        for (int i = 0; i < nparts; ++i) t += part[i];
-        float total_norm = sqrtf(t);
-        float c = max_norm / (total_norm + 1e-6f);
-        s_coef = max_norm > 0.f ? fminf(c, 1.f) : 1.f;
-        int k = step[0] + 1;
-        double bc1 = 1.0 - pow(beta1, (double)k), bc2 = 1.0 - pow(beta2, (double)k);
-        s_step_size = (float)(lr / bc1);
-        s_bc2_sqrt = (float)sqrt(bc2);
+        for (int i = threadIdx.x * 4; i < min((int)gridDim.x, threadIdx.x * 4 + 4); ++i) t += __ldcg(part + i);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(HRP_FULL, t, d);
+        if (threadIdx.x == 0) {
+            // torch.optim.Adam forms its scalars in Python doubles and hands float32 values to the kernels
+            float total_norm = sqrtf(t);
+            float c = max_norm / (total_norm + 1e-6f);
+            s_coef = max_norm > 0.f ? fminf(c, 1.f) : 1.f;
+            double bc1 = 1.0 - pow(beta1, (double)k), bc2 = 1.0 - pow(beta2, (double)k);
+            s_step_size = (float)(lr / bc1);
+            s_bc2_sqrt = (float)sqrt(bc2);
+            if (blockIdx.x == 0) step[0] = k;
+        }
     }
     __syncthreads();
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), ep = (float)eps;
-    float gi = g[i] * s_coef;
-    float mi = m[i] + w1 * (gi - m[i]);  // exp_avg.lerp_(grad, 1 - beta1)
-    float vi = v[i] * b2 + w2 * gi * gi;  // mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-    m[i] = mi; v[i] = vi;
-    float denom = sqrtf(vi) / s_bc2_sqrt + ep;
-    p[i] = p[i] - s_step_size * (mi / denom);
+    const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+    for (long long i = i0; i < n; i += stride) {
+        float gi = g[i] * coef;
+        float mi = m[i] + w1 * (gi - m[i]);  // exp_avg.lerp_(grad, 1 - beta1)
+        float vi = v[i] * b2 + w2 * gi * gi;  // mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+        m[i] = mi; v[i] = vi;
+        float denom = sqrtf(vi) / bc2_sqrt + ep;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
 }
-__global__ void bump_step_kernel(int32_t *step) { step[0] += 1; }
 
 }  // namespace
 
@@ -747,7 +941,7 @@ int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, in
     auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
     const size_t sizes[] = {B * S, B * A, B, B, B, B * H, B * H, 2 * B * H, B * A, B * A, B, B, 2 * B * H, B * H, B * H,
                             2 * H * H, H * H, cap * 2 * H * H, cap * H * H, cap * H * S, 64 * 2 * H, 64 * H, 64 * H,
-                            64 * ((A + 1) * H + A + 1), (size_t)LOSS_MAX_CTAS * 8, 32};
+                            64 * ((A + 1) * H + A + 1), ((B + HLB_ROWS - 1) / HLB_ROWS) * 8, 32};
     size_t n = 0;
     for (size_t q : sizes) n += pad(q);
     cudaError_t ce = cudaMalloc(&h->ws, n * sizeof(float));
@@ -867,6 +1061,7 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         dim3 grid((H + 31) / 32, (H + 31) / 32, 3);
         transpose_weights_kernel<<<grid, 256, 0, s1>>>(params + L.wa1, params + L.wc1, params + L.w2, H, h->wt_ac, h->wt_2);
         HRP_CUDA_OK(cudaGetLastError());
+        HRP_CUDA_OK(cudaEventRecord(h->ev[3], s1));   // the transposed copies are ready (waited for before d(h2))
     }
     if (idx) {
         const long long *ix = (const long long *)idx;
@@ -876,15 +1071,12 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         HRP_CUDA_OK(cudaGetLastError());
         x = h->x; z = h->z; olp = h->olp; ad = h->adv; rt = h->ret;
     }
-    if (int rc = forward_impl(h, params, x, B, h->mean, h->value, s)) return rc;
-    {
-        int ctas = (int)((B + 255) / 256);
-        if (ctas > LOSS_MAX_CTAS) ctas = LOSS_MAX_CTAS;
-        ppo_loss_kernel<<<ctas, 256, 0, s>>>(h->mean, h->value, params + L.log_std, z, olp, ad, rt, B, A, eps_clip,
-                                             value_coef, entropy_coef, loss_scale, h->dmean, h->dvalue, grad + L.log_std,
-                                             metrics, h->loss_part, h->loss_counter);
-        HRP_CUDA_OK(cudaGetLastError());
-    }
+    if (int rc = forward_impl(h, params, x, B, nullptr, nullptr, s)) return rc;   // trunk + hidden head layers
+    heads_loss_backward_kernel<<<(unsigned)((B + HLB_ROWS - 1) / HLB_ROWS), 256, 0, s>>>(
+        h->ac, h->ac + H, H2, H, params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2, params + L.log_std, z, olp,
+        ad, rt, B, A, eps_clip, value_coef, entropy_coef, loss_scale, h->dmean, h->dvalue, h->d12, h->d12 + H,
+        grad + L.log_std, metrics, h->loss_part, h->loss_counter);
+    HRP_CUDA_OK(cudaGetLastError());
     const float *a1 = h->ac, *c1 = h->ac + H;
     ReducePlan plan;
     plan.nseg = 0; plan.blocks = 0;
@@ -901,17 +1093,12 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         HRP_CUDA_OK(cudaGetLastError());
         plan_add(plan, h->part_h, (long long)A * H + A + H + 1, chunks, grad + L.wa2, (long long)A * H + A, grad + L.wc2);
     }
-    // main: d(a1) | d(c1) into d12 (ReLU masks applied)
-    heads_backward_kernel<<<(unsigned)((B * H + 255) / 256), 256, 0, s>>>(h->dmean, h->dvalue, params + L.wa2,
-                                                                        params + L.wc2, a1, c1, H2, B, H, A, h->d12,
-                                                                        h->d12 + H);
-    HRP_CUDA_OK(cudaGetLastError());
-    // side 0: [dWa1 ; dWc1] = [d(a1) | d(c1)]^T h2 in one GEMM, [dba1 | dbc1] in one column sum
-    HRP_CUDA_OK(after(2, s, s0));
-    if (wgrad(h, plan, h->part_w[0], H2, H, B, h->d12, H2, h->h2, H, grad + L.wa1, H, grad + L.wc1, s0)) return -2;
-    if (colsum(plan, h->part_b[0], h->d12, H2, B, H2, grad + L.ba1, H, grad + L.bc1, s0)) return -2;
+    // side 1: [dWa1 ; dWc1] = [d(a1) | d(c1)]^T h2 in one GEMM, [dba1 | dbc1] in one column sum
+    HRP_CUDA_OK(after(2, s, s1));
+    if (wgrad(h, plan, h->part_w[0], H2, H, B, h->d12, H2, h->h2, H, grad + L.wa1, H, grad + L.wc1, s1)) return -2;
+    if (colsum(plan, h->part_b[0], h->d12, H2, B, H2, grad + L.ba1, H, grad + L.bc1, s1)) return -2;
     // main: d(h2) = [d(a1) | d(c1)] [Wa1 ; Wc1] (.) (h2>0): K = 2H against the transposed copies
-    HRP_CUDA_OK(after(3, s1, s));
+    HRP_CUDA_OK(cudaStreamWaitEvent(s, h->ev[3], 0));
     if (gemm(false, true, Bi, H, H2, h->d12, H2, h->wt_ac, H2, h->dh2, H, nullptr, 0, h->h2, H, 0, 1, s) < 0) return -2;
     // side 1: dW2, db2
     HRP_CUDA_OK(after(4, s, s1));
@@ -939,13 +1126,20 @@ int hrp_clip_adam_step(float *params, const float *grad, float *exp_avg, float *
         return -1;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    int nparts = (int)((n + 255) / 256);
-    if (nparts > 128) nparts = 128;  // scratch_dev holds >= 128 floats
-    gradnorm_kernel<<<nparts, 256, 0, s>>>(grad, n, scratch);
-    clip_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params, grad, exp_avg, exp_avg_sq, step, n, lr, beta1,
-                                                                beta2, eps, max_grad_norm, scratch, nparts);
-    bump_step_kernel<<<1, 1, 0, s>>>(step);
-    HRP_CUDA_OK(cudaGetLastError());
+    static int max_ctas = 0;
+    if (max_ctas == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        HRP_CUDA_OK(cudaGetDevice(&dev));
+        HRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        HRP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_adam_kernel, ADAM_THREADS, 0));
+        max_ctas = sms * per_sm < ADAM_MAX_CTAS ? sms * per_sm : ADAM_MAX_CTAS;
+        if (max_ctas < 1) { hrp_set_error("hrp_clip_adam_step: kernel does not fit the device"); return -2; }
+    }
+    int ctas = (int)((n + ADAM_THREADS - 1) / ADAM_THREADS);
+    if (ctas > max_ctas) ctas = max_ctas;
+    long long n_ = n;
+    void *args[] = {&params, &grad, &exp_avg, &exp_avg_sq, &step, &n_, &lr, &beta1, &beta2, &eps, &max_grad_norm, &scratch};
+    HRP_CUDA_OK(cudaLaunchCooperativeKernel((const void *)clip_adam_kernel, dim3(ctas), dim3(ADAM_THREADS), args, 0, s));
     return 0;
 }
 
