@@ -336,9 +336,9 @@ def run_ours(args):
         def host_step():
             obs_d.copy_(obs_h.view(E, S), non_blocking=True)          # H2D observation
             agent.act(obs_d, out=out)
-            act_h.copy_(out["action"], non_blocking=True)             # D2H action
-            torch.cuda.current_stream().synchronize()
-            env.step_host(act_np, obs_np, rew_h, te_h, tr_h)          # H2D action, kernel, D2H obs/reward/flags
+            act_h.copy_(out["action"], non_blocking=True)             # D2H action (the host gets every result)
+            # the device action feeds the step directly; kernel, D2H obs / reward / flags, ONE synchronisation
+            env.step_host(out["action"], obs_np, rew_h, te_h, tr_h)
 
         for _ in range(5):
             host_step()
@@ -354,8 +354,8 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * E * Ke / float(t.cpu()), "unit": UNIT,
-               "h2d_bytes_per_step": E * S * 4 + E * 2 * 4, "d2h_bytes_per_step": E * 2 * 4 + E * S * 4 + E * 4 + 2 * E,
-               "steps": Ke, "api": "PPOAgent.act on a pinned-host observation + hrp_env_step_host"}
+               "h2d_bytes_per_step": E * S * 4, "d2h_bytes_per_step": E * 2 * 4 + E * S * 4 + E * 4 + 2 * E,
+               "steps": Ke, "api": "PPOAgent.act on a pinned-host observation + VecEnv.step_host (hrp_env_step_host_on): the device action feeds the step, the host receives action, observation, reward and flags"}
 
     # PPO iteration (rollout of T steps + update: 8 epochs of 4096-sample minibatches, gradient all-reduce if N > 1)
     ppo = None

@@ -279,23 +279,35 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-int hrp_env_step_host(hrp_env *h, const float *actions_host, float *obs_host, float *reward_host,
-                      uint8_t *terminated_host, uint8_t *truncated_host)
+// `actions` may be pageable host, page-locked host or device memory (a device action, e.g. the policy kernel's
+// output on `s`, is used in place: no H2D copy and no synchronisation between the policy and the step)
+static int step_host_impl(hrp_env *h, const float *actions, float *obs_host, float *reward_host,
+                          uint8_t *terminated_host, uint8_t *truncated_host, cudaStream_t s)
 {
-    if (!h || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) {
+    if (!h || !actions || !obs_host || !reward_host || !terminated_host || !truncated_host) {
         hrp_set_error("hrp_env_step_host: null argument");
         return -1;
     }
     if (int rc = ensure_host_path(h)) return rc;
     size_t E = h->P.E, no = E * h->P.N * h->P.Fout;
-    cudaStream_t s = h->host_stream;
-    const bool pin_a = is_pinned(actions_host), pin_o = is_pinned(obs_host);
+    cudaPointerAttributes pa;
+    bool dev_a = false, pin_a = false;
+    if (cudaPointerGetAttributes(&pa, actions) == cudaSuccess) {
+        dev_a = pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged;
+        pin_a = pa.type == cudaMemoryTypeHost;
+    } else {
+        cudaGetLastError();
+    }
+    const bool pin_o = is_pinned(obs_host);
     const bool pin_r = is_pinned(reward_host) && is_pinned(terminated_host) && is_pinned(truncated_host);
-    if (!pin_a) memcpy(h->h_actions, actions_host, E * 2 * sizeof(float));
-    HRP_CUDA_OK(cudaMemcpyAsync(h->d_actions, pin_a ? actions_host : h->h_actions, E * 2 * sizeof(float),
-                                cudaMemcpyHostToDevice, s));
-    if (int rc = hrp_launch_step(h->P, h->d_actions, h->d_obs, h->d_reward, h->d_term, h->d_trunc, nullptr,
-                                 nullptr, s))
+    const float *d_act = actions;
+    if (!dev_a) {
+        if (!pin_a) memcpy(h->h_actions, actions, E * 2 * sizeof(float));
+        HRP_CUDA_OK(cudaMemcpyAsync(h->d_actions, pin_a ? actions : h->h_actions, E * 2 * sizeof(float),
+                                    cudaMemcpyHostToDevice, s));
+        d_act = h->d_actions;
+    }
+    if (int rc = hrp_launch_step(h->P, d_act, h->d_obs, h->d_reward, h->d_term, h->d_trunc, nullptr, nullptr, s))
         return rc;
     HRP_CUDA_OK(cudaMemcpyAsync(pin_o ? obs_host : h->h_obs, h->d_obs, no * sizeof(float), cudaMemcpyDeviceToHost, s));
     HRP_CUDA_OK(cudaMemcpyAsync(pin_r ? reward_host : h->h_reward, h->d_reward, E * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -309,6 +321,20 @@ int hrp_env_step_host(hrp_env *h, const float *actions_host, float *obs_host, fl
         memcpy(truncated_host, h->h_trunc, E);
     }
     return 0;
+}
+
+int hrp_env_step_host(hrp_env *h, const float *actions_host, float *obs_host, float *reward_host,
+                      uint8_t *terminated_host, uint8_t *truncated_host)
+{
+    if (!h) { hrp_set_error("hrp_env_step_host: null argument"); return -1; }
+    if (int rc = ensure_host_path(h)) return rc;
+    return step_host_impl(h, actions_host, obs_host, reward_host, terminated_host, truncated_host, h->host_stream);
+}
+
+int hrp_env_step_host_on(hrp_env *h, const float *actions, float *obs_host, float *reward_host,
+                         uint8_t *terminated_host, uint8_t *truncated_host, void *stream)
+{
+    return step_host_impl(h, actions, obs_host, reward_host, terminated_host, truncated_host, (cudaStream_t)stream);
 }
 
 int hrp_env_reset_host(hrp_env *h, uint64_t seed, float *obs_host)

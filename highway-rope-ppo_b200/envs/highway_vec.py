@@ -233,8 +233,20 @@ class HighwayVecEnv:
         return obs
 
     # host-buffer entry points (what a CPU training loop binds): numpy in, numpy out
-    def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, terminated: np.ndarray,
+    def step_host(self, actions, obs: np.ndarray, reward: np.ndarray, terminated: np.ndarray,
                   truncated: np.ndarray) -> None:
+        """Host-buffer step: results land in the numpy arrays.  ``actions`` is a numpy array, or a CUDA tensor
+        produced on the current stream (the policy's device output: no host round trip, no extra synchronisation)."""
+        if isinstance(actions, torch.Tensor) and actions.is_cuda:
+            a = actions.contiguous()
+            if a.dtype != torch.float32 or a.numel() != 2 * self.num_envs:
+                raise ValueError(f"actions must hold {self.num_envs} x 2 float32 values")
+            _lib.check(self._lib.hrp_env_step_host_on(self._h, a.data_ptr(), obs.ctypes.data, reward.ctypes.data,
+                                                      terminated.ctypes.data, truncated.ctypes.data,
+                                                      torch.cuda.current_stream(self.device).cuda_stream),
+                       "hrp_env_step_host_on")
+            self.launches += 1
+            return
         a = np.ascontiguousarray(actions, dtype=np.float32)
         if a.size != 2 * self.num_envs:
             raise ValueError(f"actions must hold {self.num_envs} x 2 floats")

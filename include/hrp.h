@@ -131,6 +131,11 @@ int hrp_env_observe(hrp_env *env, float *obs_dev, const int32_t *perm_dev, int32
 int hrp_env_step_host(hrp_env *env, const float *actions_host, float *obs_host, float *reward_host,
                       uint8_t *terminated_host, uint8_t *truncated_host);
 int hrp_env_reset_host(hrp_env *env, uint64_t seed, float *obs_host);
+/* the same on the caller's stream (synchronised before returning); `actions` may also be DEVICE memory produced
+ * earlier on that stream -- the policy's output goes into the step without a host round trip while the host still
+ * receives every result.  Page-locked host buffers are copied to and from directly, pageable ones are staged. */
+int hrp_env_step_host_on(hrp_env *env, const float *actions, float *obs_host, float *reward_host,
+                         uint8_t *terminated_host, uint8_t *truncated_host, void *stream);
 
 /* state injection / extraction; synchronous */
 int hrp_env_get_state(hrp_env *env, hrp_state *dst_host);

@@ -301,4 +301,16 @@ def test_host_buffer_entry_points_match_device_path(highway_config):
         o, r, t1, t2 = b_env.step(torch.from_numpy(act).cuda())
         assert np.array_equal(obs_h, o.cpu().numpy()) and np.array_equal(rew, r.cpu().numpy())
         assert np.array_equal(te, t1.cpu().numpy()) and np.array_equal(tr, t2.cpu().numpy())
+    # device actions on the caller's stream and page-locked result buffers (hrp_env_step_host_on): same results
+    obs_p = torch.zeros((E, 15, 4)).pin_memory()
+    rew_p, te_p, tr_p = torch.zeros(E).pin_memory(), torch.zeros(E, dtype=torch.uint8).pin_memory(), \
+        torch.zeros(E, dtype=torch.uint8).pin_memory()
+    for _ in range(5):
+        act = torch.from_numpy(rng.uniform(-1, 1, (E, 2)).astype(np.float32)).cuda()
+        a_env.step_host(act, obs_p.numpy(), rew_p.numpy(), te_p.numpy(), tr_p.numpy())
+        o, r, t1, t2 = b_env.step(act)
+        assert torch.equal(obs_p, o.cpu()) and torch.equal(rew_p, r.cpu())
+        assert torch.equal(te_p.bool(), t1.cpu().bool()) and torch.equal(tr_p.bool(), t2.cpu().bool())
+    with pytest.raises(ValueError):
+        a_env.step_host(torch.zeros(3, device="cuda:0"), obs_h, rew, te, tr)
     a_env.close(); b_env.close()
