@@ -376,6 +376,7 @@ def run_ours(args):
         ppo = {"value": world * E * T * iters / (float(t.cpu()) * 1e-3), "unit": "samples/s", "rollout_T": T,
                "epochs": 8, "minibatch": 4096, "last_loss": m["loss"],
                "cuda_graphs": agent._graph_state is not None, "backend": dist.get_backend() if world > 1 else None,
+               "gradient_exchange": ("peer-memory kernel (hrp_clip_adam_step_p2p)" if agent._comm is not None else "nccl all_reduce") if world > 1 else None,
                "definition": "T policy+env steps then PPOAgent.update (GAE, 8 epochs, clip+Adam), amortised"}
 
     cpu = None
@@ -399,7 +400,7 @@ def run_ours(args):
     if world > 1:
         # graphs that captured NCCL work must go before the communicator does; leave without the communicator
         # teardown (it was seen to hang after captured collectives) once every rank is done
-        agent.release_graphs()
+        agent.close()
         barrier()
         sys.stdout.flush()
         os._exit(0)

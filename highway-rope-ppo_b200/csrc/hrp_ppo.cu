@@ -358,106 +358,6 @@ heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, con
     value[b] = out[A];
 }
 
-// PPO loss for one minibatch (agent.py:223-245) and its gradient w.r.t. mean, value, log_std.
-// Grid-stride over the rows; every CTA leaves its 8 partial sums in part[blockIdx.x][8] and the CTA that
-// finishes last adds them in block order (deterministic) and writes d(log_std) and the metrics:
-// metrics += (loss, policy, value, entropy, clipfrac, kl, 1, 0).  `counter` returns to zero.
-constexpr int LOSS_MAX_CTAS = 64;
-__global__ void __launch_bounds__(256)
-ppo_loss_kernel(const float *__restrict__ mean, const float *__restrict__ value,
-                const float *__restrict__ log_std, const float *__restrict__ pre_tanh,
-                const float *__restrict__ old_lp, const float *__restrict__ adv, const float *__restrict__ ret,
-                long long B, int A, float eps_clip, float value_coef, float entropy_coef, float scale,
-                float *__restrict__ dmean, float *__restrict__ dvalue, float *__restrict__ dlog_std,
-                float *__restrict__ metrics, float *__restrict__ part, unsigned *__restrict__ counter)
-{
-    __shared__ float red[8][8];
-    __shared__ bool last;
-    float s_pol = 0.f, s_val = 0.f, s_clip = 0.f, s_kl = 0.f, s_dls[4] = {0.f, 0.f, 0.f, 0.f};
-    float ls_[4], sd_[4];
-    for (int a = 0; a < A; ++a) { ls_[a] = log_std[a]; sd_[a] = expf(ls_[a]); }
-    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-        float lp = 0.f;
-        float dmu[4], dls[4];
-        for (int a = 0; a < A; ++a) {
-            float mu = mean[b * A + a], ls = ls_[a], sd = sd_[a];
-            float z = pre_tanh[b * A + a];
-            float t = tanhf(z);
-            float d = z - mu, var = sd * sd;
-            lp += -(d * d) / (2.f * var) - ls - 0.91893853320467274f;
-            lp -= log1pf(-(t * t) + 1e-6f);
-            dmu[a] = d / var;
-            dls[a] = d * d / var - 1.f;
-        }
-        float lr = lp - old_lp[b];
-        float ratio = expf(lr);
-        float ad = adv[b];
-        float surr1 = ratio * ad;
-        float rc = fminf(fmaxf(ratio, 1.f - eps_clip), 1.f + eps_clip);
-        float surr2 = rc * ad;
-        bool inr = ratio >= 1.f - eps_clip && ratio <= 1.f + eps_clip;
-        // d min(surr1, surr2) / d ratio with torch's tie rule (half each on equality)
-        float g;
-        if (surr1 < surr2) g = ad;
-        else if (surr1 == surr2) g = 0.5f * ad + (inr ? 0.5f * ad : 0.f);
-        else g = inr ? ad : 0.f;
-        float dlp = -g * ratio * scale;
-        for (int a = 0; a < A; ++a) {
-            dmean[b * A + a] = dlp * dmu[a];
-            s_dls[a] += dlp * dls[a];
-        }
-        float v = value[b], dv = v - ret[b];
-        dvalue[b] = value_coef * 2.f * dv * scale;
-        s_pol += -fminf(surr1, surr2);
-        s_val += dv * dv;
-        s_clip += fabsf(ratio - 1.f) > eps_clip ? 1.f : 0.f;
-        s_kl += (ratio - 1.f) - lr;
-    }
-    float vals[8] = {s_pol, s_val, s_clip, s_kl, s_dls[0], s_dls[1], s_dls[2], s_dls[3]};
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float x = vals[i];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(HRP_FULL, x, d);
-        if (lane == 0) red[w][i] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        float x = 0.f;
-        for (int i = 0; i < 8; ++i) x += red[i][threadIdx.x];
-        part[blockIdx.x * 8 + threadIdx.x] = x;
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned prev = atomicAdd(counter, 1u);
-        last = prev == gridDim.x - 1;
-        if (last) *counter = 0u;
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    if (threadIdx.x < 8) {
-        float x = 0.f;
-        for (unsigned i = 0; i < gridDim.x; ++i) x += __ldcg(part + i * 8 + threadIdx.x);
-        red[0][threadIdx.x] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float ent = 0.f;
-        for (int a = 0; a < A; ++a) ent += 0.5f + 0.91893853320467274f + ls_[a];
-        float pol = red[0][0] * scale, val = red[0][1] * scale;
-        float frac = (float)B * scale;  // share of the global minibatch held by this shard
-        float loss = pol + value_coef * val - entropy_coef * ent * frac;
-        for (int a = 0; a < A; ++a) dlog_std[a] = red[0][4 + a] - entropy_coef * frac;
-        if (metrics) {
-            metrics[0] += loss; metrics[1] += pol; metrics[2] += val; metrics[3] += ent * frac;
-            metrics[4] += red[0][2] * scale; metrics[5] += red[0][3] * scale; metrics[6] += frac;
-        }
-    }
-}
-
 // heads + PPO loss + the gradient of the hidden head layers in one launch (agent.py:76-84, 223-245): a CTA owns 16
 // rows.  Phase 0: a warp per row forms mean[A] and value from a1 | c1 (row pitch ld).  Phase 1: one thread per row
 // evaluates the loss terms, writes d(mean), d(value) (the head weight gradients need them) and keeps them in shared
@@ -634,23 +534,6 @@ heads_loss_backward_kernel(const float *__restrict__ a1, const float *__restrict
     }
 }
 
-// d(a1) = dmean Wa2 (.) (a1>0) and d(c1) = dvalue Wc2 (.) (c1>0): rank-A / rank-1 outer products
-__global__ void heads_backward_kernel(const float *__restrict__ dmean, const float *__restrict__ dvalue,
-                                      const float *__restrict__ wa2, const float *__restrict__ wc2,
-                                      const float *__restrict__ a1, const float *__restrict__ c1, int ld, long long B,
-                                      int H, int A, float *__restrict__ da1, float *__restrict__ dc1)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * H) return;
-    long long b = i / H;
-    int k = (int)(i - b * H);
-    size_t o = (size_t)b * ld + k;   // a1 | c1 and d(a1) | d(c1) share the [B, 2H] row pitch
-    float s = 0.f;
-    for (int a = 0; a < A; ++a) s = fmaf(dmean[b * A + a], wa2[(size_t)a * H + k], s);
-    da1[o] = a1[o] > 0.f ? s : 0.f;
-    dc1[o] = c1[o] > 0.f ? dvalue[b] * wc2[k] : 0.f;
-}
-
 // PPOMemory.compute_advantages (agent.py:126-138): fp64 arithmetic, float32 store of every A_t
 __global__ void gae_kernel(const float *__restrict__ reward, const float *__restrict__ value,
                            const uint8_t *__restrict__ done, const float *__restrict__ last_value, long long T,
@@ -788,7 +671,7 @@ struct hrp_ppo {
     float *part_w[3];                        // split-K partials of the three weight-gradient GEMMs
     float *part_b[3];                        // column-sum partials of the three bias gradients (<= 64 chunks)
     float *part_h;                           // head-gradient partials (<= 64 chunks)
-    float *loss_part;                        // ppo_loss_kernel partial sums [LOSS_MAX_CTAS][8]
+    float *loss_part;                        // heads_loss_backward_kernel partial sums [CTAs][8]
     unsigned *loss_counter;
     int splits_cap;
     // fork / join inside one backward pass: the weight- and bias-gradient kernels of a layer do not depend on the

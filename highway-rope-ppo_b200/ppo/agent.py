@@ -421,6 +421,11 @@ class PPOAgent:
         # communicator busy at teardown.
         self.graph_collectives = os.environ.get("HRP_GRAPH_COLLECTIVES", "1") != "0" and distributed.backend() == "nccl"
         self._graph_state: Optional[Dict[str, Any]] = None
+        # peer-memory gradient exchange fused with clip + Adam (csrc/hrp_comm.cu); set up lazily by the first sharded
+        # update.  HRP_P2P=0 keeps the NCCL all-reduce + hrp_clip_adam_step pair.
+        self.use_p2p = os.environ.get("HRP_P2P", "1") != "0" and distributed.backend() == "nccl"
+        self._comm = None
+        self._comm_keep = None
 
     # -- acting ----------------------------------------------------------------------------------
     def select_action(self, state, deterministic: bool = False):
@@ -440,6 +445,57 @@ class PPOAgent:
     def _allreduce(self, t: torch.Tensor) -> None:
         distributed.allreduce_sum_(t)
 
+    # -- peer-memory exchange -------------------------------------------------------------------------
+    def _ensure_comm(self, world: int) -> bool:
+        """Create and connect this rank's ``hrp_comm`` (once): every rank exports its gradient buffer through
+        cudaIpc, the 64-byte handles are all-gathered, and ``self.grad`` becomes a view of the exported buffer.
+        Returns False (and keeps the NCCL path) when the devices cannot map each other's memory."""
+        if self._comm is not None:
+            return True
+        if not self.use_p2p or world > 8:
+            return False
+        import torch.distributed as dist
+
+        lib, P = self._lib, self.actor_critic.num_params
+        handle = (C.c_ubyte * 64)()
+        comm = C.c_void_p()
+        rc = lib.hrp_comm_create(world, distributed.rank(), P, self.device.index, C.byref(comm), handle)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        if rc == 0:
+            blob = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
+            rc = lib.hrp_comm_connect(comm, blob)
+            ok[0] = 1 if rc == 0 else 0
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
+        if int(ok.item()) != 1:
+            self.logger.warning("peer-memory gradient exchange unavailable (%s); using the NCCL all-reduce",
+                                _lib.last_error() if hasattr(_lib, "last_error") else "cudaIpc")
+            if comm:
+                lib.hrp_comm_destroy(comm)
+            self.use_p2p = False
+            return False
+        ptr = lib.hrp_comm_grad(comm)
+
+        class _Raw:  # torch.as_tensor wraps a raw device pointer through the CUDA array interface
+            __cuda_array_interface__ = {"shape": (P,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+        self._comm_keep = _Raw()
+        self.grad = torch.as_tensor(self._comm_keep, device=self.device)
+        assert self.grad.data_ptr() == int(ptr)
+        self._comm = comm
+        return True
+
+    def close(self) -> None:
+        """Release the captured graphs and the peer-memory exchange (before the process group is destroyed)."""
+        self.release_graphs()
+        if self._comm is not None:
+            torch.cuda.synchronize(self.device)
+            self.grad = torch.zeros(self.actor_critic.num_params, dtype=torch.float32, device=self.device)
+            self._lib.hrp_comm_destroy(self._comm)
+            self._comm, self._comm_keep = None, None
+
     # -- one optimizer step on minibatch ``idx`` (device int64) ----------------------------------
     def _minibatch_step(self, flat: Dict[str, torch.Tensor], idx: Optional[torch.Tensor], B: int, world: int) -> None:
         ac, opt, s = self.actor_critic, self.optimizer, self.actor_critic._stream()
@@ -448,6 +504,14 @@ class PPOAgent:
             flat["log_prob"].data_ptr(), flat["adv"].data_ptr(), flat["ret"].data_ptr(), _lib.ptr(idx), B,
             float(self.eps_clip), float(self.value_coef), float(self.entropy_coef), distributed.loss_scale(B, world),
             self.grad.data_ptr(), self._metrics.data_ptr(), s), "hrp_ppo_loss_grad")
+        if world > 1 and self._comm is not None:
+            # all_reduce + clip + Adam as one kernel over peer memory
+            _lib.check(self._lib.hrp_clip_adam_step_p2p(
+                self._comm, ac.flat.data_ptr(), opt.exp_avg.data_ptr(), opt.exp_avg_sq.data_ptr(),
+                opt.step_dev.data_ptr(), opt.lr, opt.betas[0], opt.betas[1], opt.eps, float(self.max_grad_norm),
+                opt.scratch.data_ptr(), s), "hrp_clip_adam_step_p2p")
+            self.launches += 2
+            return
         if world > 1:
             self._allreduce(self.grad)
         _lib.check(self._lib.hrp_clip_adam_step(
@@ -528,6 +592,8 @@ class PPOAgent:
         bs = int(mem.batch_size)
         ac._ensure_workspace(min(bs, n))
         self._metrics.zero_()
+        if world > 1:
+            self._ensure_comm(world)
         if self.use_cuda_graphs and (world == 1 or self.graph_collectives):
             # with several ranks the NCCL all-reduce of the flat gradient is captured inside each minibatch graph
             self._graphed_epochs(flat, perm_dev, n, bs, world)

@@ -219,6 +219,23 @@ int hrp_clip_adam_step(float *params_dev, const float *grad_dev, float *exp_avg_
                        double beta2, double eps, float max_grad_norm, float *scratch_dev /* >=128 floats */,
                        void *stream);
 
+/* ---- the gradient exchange of the sharded PPO update, fused with clip + Adam (csrc/hrp_comm.cu) --------------
+ * One process per GPU on one box.  hrp_comm_create allocates this rank's peer-readable gradient buffer and returns
+ * its 64-byte cudaIpc handle; the caller gathers the handles of all ranks (rank-major) and passes them to
+ * hrp_comm_connect.  hrp_ppo_loss_grad then writes hrp_comm_grad(), and hrp_clip_adam_step_p2p replaces
+ * all_reduce(grad) + hrp_clip_adam_step: ONE cooperative kernel that waits for every rank's gradient, sums the W
+ * gradients in rank order over NVLink (bit-identical on every rank), clips, applies Adam and signals completion.
+ * Every rank must call it once per optimizer step; ranks must own different devices. */
+typedef struct hrp_comm hrp_comm;
+int hrp_comm_create(int32_t world, int32_t rank, int64_t n_floats, int32_t device, hrp_comm **out,
+                    void *ipc_handle_out64);
+int hrp_comm_connect(hrp_comm *comm, const void *ipc_handles /* world x 64 bytes */);
+float *hrp_comm_grad(hrp_comm *comm);
+int hrp_clip_adam_step_p2p(hrp_comm *comm, float *params_dev, float *exp_avg_dev, float *exp_avg_sq_dev,
+                           int32_t *step_dev, double lr, double beta1, double beta2, double eps,
+                           float max_grad_norm, float *scratch_dev /* >=128 floats */, void *stream);
+int hrp_comm_destroy(hrp_comm *comm);
+
 #ifdef __cplusplus
 }
 #endif
