@@ -289,3 +289,51 @@ def test_loads_a_checkpoint_written_by_the_reference_agent():
         assert torch.equal(back["model"][k], sd[k]), k
     assert back["optimizer"]["param_groups"][0]["lr"] == chk["optimizer"]["param_groups"][0]["lr"]
     os.remove(out)
+
+
+def test_peer_memory_adam_step_with_one_rank_equals_the_plain_step():
+    """hrp_clip_adam_step_p2p (csrc/hrp_comm.cu) with a world of one rank: the cross-GPU barriers see only their own
+    flags and the rank-ordered sum has one term, so parameters and moments must equal hrp_clip_adam_step bit for bit,
+    step after step (epoch counter, flag reuse)."""
+    import ctypes as C
+
+    from highway_rope_ppo_b200 import _lib
+
+    lib = _lib.load()
+    n = 213765
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    comm, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    _lib.check(lib.hrp_comm_create(1, 0, n, 0, C.byref(comm), handle))
+    _lib.check(lib.hrp_comm_connect(comm, bytes(handle)))
+    ptr = lib.hrp_comm_grad(comm)
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+    keep = _Raw()
+    grad_c = torch.as_tensor(keep, device="cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    pa = torch.randn(n, generator=g, device="cuda:0") * 0.1
+    pb = pa.clone()
+    ma, va, mb, vb = (torch.zeros(n, device="cuda:0") for _ in range(4))
+    sa, sb = torch.zeros(1, dtype=torch.int32, device="cuda:0"), torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    scr_a, scr_b = torch.zeros(128, device="cuda:0"), torch.zeros(128, device="cuda:0")
+    try:
+        for it in range(5):
+            grad = torch.randn(n, generator=g, device="cuda:0") * (0.5 if it % 2 else 5e-4)  # clipped and unclipped steps
+            grad_c.copy_(grad)
+            _lib.check(lib.hrp_clip_adam_step_p2p(comm, pa.data_ptr(), ma.data_ptr(), va.data_ptr(), sa.data_ptr(), 3e-4, 0.9,
+                                                  0.999, 1e-8, 0.5, scr_a.data_ptr(), st))
+            _lib.check(lib.hrp_clip_adam_step(pb.data_ptr(), grad.data_ptr(), mb.data_ptr(), vb.data_ptr(), sb.data_ptr(), n,
+                                              3e-4, 0.9, 0.999, 1e-8, 0.5, scr_b.data_ptr(), st))
+            torch.cuda.synchronize()
+            assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb), it
+            assert int(sa.item()) == int(sb.item()) == it + 1
+    finally:
+        torch.cuda.synchronize()
+        del grad_c
+        lib.hrp_comm_destroy(comm)
+    # error paths
+    assert lib.hrp_comm_create(9, 0, n, 0, C.byref(comm), handle) == -1      # more ranks than one box holds
+    assert lib.hrp_clip_adam_step_p2p(None, pa.data_ptr(), ma.data_ptr(), va.data_ptr(), sa.data_ptr(), 3e-4, 0.9, 0.999,
+                                      1e-8, 0.5, scr_a.data_ptr(), st) == -1
