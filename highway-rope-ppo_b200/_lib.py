@@ -99,6 +99,7 @@ SIGNATURES: Dict[str, Any] = {
     "hrp_comm_connect": (C.c_int, [_vp, _vp]),
     "hrp_comm_grad": (_vp, [_vp]),
     "hrp_clip_adam_step_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _f64, _f32, _vp, _vp]),
+    "hrp_comm_status": (C.c_int, [_vp]),
     "hrp_comm_destroy": (C.c_int, [_vp]),
 }
 

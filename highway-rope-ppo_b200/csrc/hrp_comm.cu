@@ -28,7 +28,7 @@ struct hrp_comm {
     void *peer_base[HRP_MAX_RANKS];
     float *peer_grad[HRP_MAX_RANKS];
     unsigned *peer_flags[HRP_MAX_RANKS];   // each rank's flag block: ready[HRP_MAX_RANKS], done[HRP_MAX_RANKS]
-    unsigned *epoch;         // device counter of completed steps (own allocation)
+    unsigned *epoch;         // device: [0] counter of completed steps, [1] timeout bits of the cross-GPU waits
     bool connected;
 };
 
@@ -52,8 +52,11 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
     return v;
 }
 
-// flag block of a rank: ready[q] / done[q] are written by rank q
-__device__ __forceinline__ void cross_gpu_barrier(const PeerTable &T, int world, int rank, int which, unsigned epoch)
+// flag block of a rank: ready[q] / done[q] are written by rank q.  The wait is bounded (about fifteen seconds of SM
+// clock): a rank that never arrives -- a crashed peer -- must not leave this GPU spinning; the timeout is recorded in
+// *status (bit `which`) and the step goes on with whatever the peer buffers hold, for the host to detect.
+__device__ __forceinline__ void cross_gpu_barrier(const PeerTable &T, int world, int rank, int which, unsigned epoch,
+                                                  unsigned *status)
 {
     // called by the first `world` threads of CTA 0
     const int q = threadIdx.x;
@@ -61,7 +64,11 @@ __device__ __forceinline__ void cross_gpu_barrier(const PeerTable &T, int world,
         __threadfence_system();
         st_release_sys(T.flags[q] + which * HRP_MAX_RANKS + rank, epoch);
         const unsigned *mine = T.flags[rank] + which * HRP_MAX_RANKS + q;
-        while ((int)(ld_acquire_sys(mine) - epoch) < 0) __nanosleep(64);
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > 30000000000ll) { atomicOr(status, 1u << which); break; }
+        }
     }
 }
 
@@ -77,7 +84,7 @@ clip_adam_p2p_kernel(const PeerTable T, int world, int rank, unsigned *__restric
     __shared__ float s_coef, s_step_size, s_bc2_sqrt;
     const unsigned epoch = *epoch_dev + 1u;
     const int k = step[0] + 1;
-    if (blockIdx.x == 0) cross_gpu_barrier(T, world, rank, 0, epoch);   // every gradient is complete
+    if (blockIdx.x == 0) cross_gpu_barrier(T, world, rank, 0, epoch, epoch_dev + 1);   // every gradient is complete
     grid.sync();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,7 +105,7 @@ clip_adam_p2p_kernel(const PeerTable T, int world, int rank, unsigned *__restric
         part[blockIdx.x] = t;
     }
     grid.sync();
-    if (blockIdx.x == 0) cross_gpu_barrier(T, world, rank, 1, epoch);   // nobody reads my gradient any more
+    if (blockIdx.x == 0) cross_gpu_barrier(T, world, rank, 1, epoch, epoch_dev + 1);   // nobody reads my gradient any more
     if (threadIdx.x < 32) {
         float t = 0.f;
         for (int i = threadIdx.x * 4; i < min((int)gridDim.x, threadIdx.x * 4 + 4); ++i) t += __ldcg(part + i);
@@ -147,8 +154,8 @@ int hrp_comm_create(int32_t world, int32_t rank, int64_t n, int32_t device, hrp_
     size_t bytes = comm_floats(n) * sizeof(float);
     cudaError_t ce = cudaMalloc(&c->local, bytes);
     if (ce == cudaSuccess) ce = cudaMemset(c->local, 0, bytes);
-    if (ce == cudaSuccess) ce = cudaMalloc(&c->epoch, sizeof(unsigned));
-    if (ce == cudaSuccess) ce = cudaMemset(c->epoch, 0, sizeof(unsigned));
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->epoch, 2 * sizeof(unsigned));
+    if (ce == cudaSuccess) ce = cudaMemset(c->epoch, 0, 2 * sizeof(unsigned));
     cudaIpcMemHandle_t hd;
     if (ce == cudaSuccess) ce = cudaIpcGetMemHandle(&hd, c->local);
     if (ce != cudaSuccess) {
@@ -216,6 +223,18 @@ int hrp_clip_adam_step_p2p(hrp_comm *c, float *params, float *exp_avg, float *ex
                     &max_grad_norm, &scratch};
     HRP_CUDA_OK(cudaLaunchCooperativeKernel((const void *)clip_adam_p2p_kernel, dim3(ctas), dim3(P2P_THREADS), args, 0,
                                             (cudaStream_t)stream));
+    return 0;
+}
+
+/* synchronises the device; 0 = every cross-GPU wait so far was answered, -4 = a peer did not arrive within the
+ * timeout of some step (its results are not to be trusted) */
+int hrp_comm_status(hrp_comm *c)
+{
+    if (!c) { hrp_set_error("hrp_comm_status: null argument"); return -1; }
+    HRP_CUDA_OK(cudaSetDevice(c->device));
+    unsigned st[2] = {0, 0};
+    HRP_CUDA_OK(cudaMemcpy(st, c->epoch, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[1] != 0) { hrp_set_error("hrp_comm: a peer rank did not reach the gradient exchange (wait bits %u) after %u steps", st[1], st[0]); return -4; }
     return 0;
 }
 

@@ -602,6 +602,8 @@ class PPOAgent:
                 for start in range(0, n, bs):
                     B = min(bs, n - start)
                     self._minibatch_step(flat, perm_dev[start:start + B], B, world)
+        if self._comm is not None:
+            _lib.check(self._lib.hrp_comm_status(self._comm), "hrp_comm_status")   # a peer that never arrived
         # explained variance of the value predictions (agent.py:276-285)
         y_pred, y_true = r["value"].reshape(n), ret.view(n)
         if world > 1:

@@ -234,6 +234,8 @@ float *hrp_comm_grad(hrp_comm *comm);
 int hrp_clip_adam_step_p2p(hrp_comm *comm, float *params_dev, float *exp_avg_dev, float *exp_avg_sq_dev,
                            int32_t *step_dev, double lr, double beta1, double beta2, double eps,
                            float max_grad_norm, float *scratch_dev /* >=128 floats */, void *stream);
+/* synchronous: 0, or -4 when some cross-GPU wait timed out (a peer never arrived; ~15 s bound per wait) */
+int hrp_comm_status(hrp_comm *comm);
 int hrp_comm_destroy(hrp_comm *comm);
 
 #ifdef __cplusplus
