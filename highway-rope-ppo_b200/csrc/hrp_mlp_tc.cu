@@ -98,7 +98,9 @@ __device__ __forceinline__ uint32_t swz(int r, int k)
 // MODE 0: scalar, K-contiguous (a warp reads one 128-byte row)      1: scalar, MN-contiguous (32 rows at one k)
 // MODE 2: 16-byte vectors along K (needs 16 B alignment)           3: 8-byte vectors along K (flat-buffer weights)
 // MODE 4: 16-byte vectors along MN (4 rows at one k; batch-major operands of the weight gradient)
-enum { ST_K1 = 0, ST_MN1 = 1, ST_K4 = 2, ST_K2 = 3, ST_MN4 = 4 };
+// MODE 5: MN-contiguous, lanes along MN and 4 consecutive k per thread: four coalesced scalar loads, then ONE
+//         16-byte shared-memory store per part (MODE 4 needs four scalar stores per part for the same data)
+enum { ST_K1 = 0, ST_MN1 = 1, ST_K4 = 2, ST_K2 = 3, ST_MN4 = 4, ST_MNK4 = 5 };
 
 template <int MODE, int ROWS>
 struct Stager {
@@ -157,7 +159,7 @@ struct Stager {
                 if (gr < nrows && gk < kend) t = __ldg(reinterpret_cast<const float2 *>(P + (long long)gr * srow + gk));
                 v[2 * i] = t.x; v[2 * i + 1] = t.y;
             }
-        } else {  // ST_MN4
+        } else if (MODE == ST_MN4) {
 #pragma unroll
             for (int i = 0; i < ELEMS / 4; ++i) {
                 int r, k;
@@ -166,6 +168,17 @@ struct Stager {
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (gr < nrows && gk < kend) t = __ldg(reinterpret_cast<const float4 *>(P + (long long)gk * sk + gr));
                 v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
+        } else {  // ST_MNK4: thread-slot idx -> row idx % ROWS, k chunk idx / ROWS
+#pragma unroll
+            for (int i = 0; i < ELEMS / 4; ++i) {
+                const int idx = tid + i * TC_THREADS, r = idx % ROWS, k = (idx / ROWS) * 4;
+                const int gr = row0 + r;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int gk = k0 + k + j;
+                    v[4 * i + j] = (gr < nrows && gk < kend) ? __ldg(P + (long long)gk * sk + (long long)gr * srow) : 0.f;
+                }
             }
         }
     }
@@ -227,13 +240,31 @@ struct Stager {
                     *(float2 *)(hi_tile + o) = x;
                 }
             }
-        } else {  // ST_MN4: four rows at one k
+        } else if (MODE == ST_MN4) {  // four rows at one k
 #pragma unroll
             for (int i = 0; i < ELEMS / 4; ++i) {
                 int r, k;
                 coord_mn4(tid + i * TC_THREADS, r, k);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) put<NSPLIT>(hi_tile, part_bytes, swz(r + j, k), v[4 * i + j]);
+            }
+        } else {  // ST_MNK4: one whole 16-byte chunk of row r; 8 consecutive rows hit 8 different bank groups
+#pragma unroll
+            for (int i = 0; i < ELEMS / 4; ++i) {
+                const int idx = tid + i * TC_THREADS;
+                const uint32_t o = swz(idx % ROWS, (idx / ROWS) * 4);
+                float4 x = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                if (NSPLIT == 3) {
+                    float4 h;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    *(float4 *)(hi_tile + o) = h;
+                    *(float4 *)(hi_tile + part_bytes + o) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                } else {
+                    *(float4 *)(hi_tile + o) = x;
+                }
             }
         }
     }
@@ -638,8 +669,6 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     const bool a_k4 = akc && K % 4 == 0 && sam % 4 == 0 && aligned(A, 16);
     const bool b_k2 = bkc && K % 2 == 0 && sbn % 2 == 0 && aligned(B, 8) && (nseg == 0 || aligned(B2, 8));
     const bool b_k4 = bkc && K % 4 == 0 && sbn % 4 == 0 && aligned(B, 16) && (nseg == 0 || aligned(B2, 16));
-    const bool a_mn4 = sam == 1 && M % 4 == 0 && sak % 4 == 0 && aligned(A, 16);
-    const bool b_mn4 = sbn == 1 && N % 4 == 0 && sbk % 4 == 0 && aligned(B, 16) && nseg == 0;
 #define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2)
     int rc;
     // cp.async staging pays off for the single-pass mode only (measured: 3xTF32 hidden forward 12.6 us register-staged
@@ -648,7 +677,7 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     else if (a_k4 && b_k4) rc = HRP_TC_GO(ST_K4, ST_K4);
     else if (a_k4 && b_k2) rc = HRP_TC_GO(ST_K4, ST_K2);
     else if (a_k4 && sbn == 1) rc = HRP_TC_GO(ST_K4, ST_MN1);
-    else if (a_mn4 && b_mn4) rc = HRP_TC_GO(ST_MN4, ST_MN4);
+    else if (sam == 1 && sbn == 1 && nseg == 0) rc = HRP_TC_GO(ST_MNK4, ST_MNK4);
     else if (akc && bkc) rc = HRP_TC_GO(ST_K1, ST_K1);
     else if (akc) rc = HRP_TC_GO(ST_K1, ST_MN1);
     else if (bkc) rc = HRP_TC_GO(ST_MN1, ST_K1);
