@@ -41,8 +41,7 @@ def define_experiments(base_seed: int = SEED, num_seeds: int = 3) -> List[Experi
         for hp in expand_condition_hps(template):
             for i in range(num_seeds):
                 seed = base_seed + i * 1000
-                parts = [cond.name.lower()] + [f"{k}{getattr(hp, k)}" for k in template.sweep] + [f"seed{seed}"]
-                experiments.append(Experiment("_".join(parts), cond, hp, seed))
+                experiments.append(Experiment(Experiment.make_name(cond, hp, seed, tuple(template.sweep)), cond, hp, seed))
     return experiments
 
 

@@ -54,3 +54,35 @@ def test_summarize_picks_the_best_final_average_per_condition():
     assert best["sorted"] == (5.0, "sorted_lr0.0001_seed42")
     assert best["shuffled"] == (2.0, "shuffled_rope_lr0.0003_seed42")  # the reference keys on the first name token
     assert len(best) == 2
+
+
+def test_run_name_codec_round_trips_every_experiment_of_the_grid():
+    from highway_rope_ppo_b200.experiments.config import ConditionHP, Experiment
+
+    for name in GOLD["names"][::7]:
+        f = Experiment.parse_name(name)
+        hp = ConditionHP(**{k: f[k] for k in ("lr", "hidden_dim", "clip_eps", "entropy_coef", "epochs", "batch_size", "d_embed")})
+        assert Experiment.make_name(f["condition"], hp, f["seed"]) == name
+    f = Experiment.parse_name("shuffled_rope_lr0.0003_hidden_dim256_clip_eps0.2_entropy_coef0.005_epochs8_batch_size64_d_embed16_seed2042")
+    assert f["condition"] is Condition.SHUFFLED_ROPE and f["hidden_dim"] == 256 and f["d_embed"] == 16 and f["seed"] == 2042
+    assert isinstance(f["epochs"], int) and isinstance(f["lr"], float)
+    with pytest.raises(ValueError):
+        Experiment.parse_name("ppo_highway_best_sorted.pth")
+
+
+def test_hyper_parameter_records_validate_and_expand():
+    from highway_rope_ppo_b200.experiments.config import CommonHP, ConditionHP, expand_condition_hps
+
+    assert [c.value for c in Condition] == [1, 2, 3, 4, 5]   # enum.auto() numbering of the reference
+    with pytest.raises(ValueError):
+        ConditionHP(lr=0.0)
+    with pytest.raises(ValueError):
+        CommonHP(gamma=1.5)
+    with pytest.raises(ValueError):
+        ConditionHP(sweep={"learning_rate": [1e-3]})
+    hp = ConditionHP(sweep={"lr": [1e-4, 3e-4], "epochs": [6, 8, 10]})
+    got = expand_condition_hps(hp)
+    assert [(h.lr, h.epochs) for h in got] == [(1e-4, 6), (1e-4, 8), (1e-4, 10), (3e-4, 6), (3e-4, 8), (3e-4, 10)]
+    assert all(h.sweep == {} and h.hidden_dim == hp.hidden_dim for h in got)
+    plain = ConditionHP()
+    assert expand_condition_hps(plain) == [plain]
