@@ -138,6 +138,20 @@ def test_experiment_runner_result_schema(highway_config, tmp_path):
     assert res["status"] == "COMPLETED", res.get("error_traceback")
     assert set(res) >= {"experiment_name", "status", "rewards", "avg_rewards", "metrics_history", "duration_seconds"}
     assert len(res["rewards"]) == 2 and res["metrics_history"]["experiment_name"] == name
+    # the artifacts are what the reference's offline tools read (tests/golden/result_schema.json, extracted from
+    # results.py / training/routine.py by tools/gen_golden.py): name regex, metrics JSON keys, summary CSV header
+    import json
+    import re
+
+    schema = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "result_schema.json")))
+    data = json.load(open(tmp_path / f"training_metrics_{name}.json"))
+    assert list(data) == schema["metrics_keys"]
+    meta = re.match(schema["exp_rx"], data["experiment_name"]).groupdict()
+    assert meta["prefix"] == "sorted" and meta["pe_type"] is None and int(meta["hidden_dim"]) == 64 and int(meta["seed"]) == 42
+    assert len(data["eval_episode_numbers"]) == len(data["avg_eval_rewards"]) >= 1
+    lines = (tmp_path / f"summary_{name}.csv").read_text().splitlines()
+    assert lines[0] == schema["summary_header"] and lines[1].split(",")[0] == name and len(lines[1].split(",")) == 6
+    assert lines[1].split(",")[4].endswith(f"ppo_highway_best_{name}.pth")
     bad = runner.launch(Experiment("bad", Condition.SHUFFLED_ROPE, ConditionHP(d_embed=16), seed=1, max_episodes=1))
     assert bad["status"] == "FAILED" and "rotate_dim" in bad["error_message"] and "error_traceback" in bad
 

@@ -86,3 +86,24 @@ def test_hyper_parameter_records_validate_and_expand():
     assert all(h.sweep == {} and h.hidden_dim == hp.hidden_dim for h in got)
     plain = ConditionHP()
     assert expand_condition_hps(plain) == [plain]
+
+
+def test_every_run_name_is_readable_by_the_reference_offline_tools():
+    """results.py:33-44 / analysis.py:21-32 parse run names with one regular expression (fixture: result_schema.json)."""
+    import re
+
+    from highway_rope_ppo_b200.experiments.config import Experiment
+
+    schema = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "result_schema.json")))
+    rx = re.compile(schema["exp_rx"])
+    pe = {"SORTED": ("sorted", None), "SHUFFLED": ("shuffled", None), "SHUFFLED_RANKPE": ("shuffled", "rankpe"),
+          "SHUFFLED_DISTPE": ("shuffled", "distpe"), "SHUFFLED_ROPE": ("shuffled", "rope")}
+    for e in sweep.define_experiments(42, 3):
+        m = rx.match(e.name)
+        assert m, e.name
+        d = m.groupdict()
+        assert (d["prefix"], d["pe_type"]) == pe[e.condition.name]
+        mine = Experiment.parse_name(e.name)
+        assert float(d["lr"]) == mine["lr"] == e.hp.lr and int(d["hidden_dim"]) == mine["hidden_dim"] == e.hp.hidden_dim
+        assert int(d["epochs"]) == e.hp.epochs and int(d["batch_size"]) == e.hp.batch_size and int(d["seed"]) == e.seed
+        assert int(d["d_embed"]) == e.hp.d_embed and float(d["clip_eps"]) == e.hp.clip_eps

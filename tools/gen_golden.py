@@ -255,6 +255,31 @@ def gen_sweep():
     print("sweep fixture written:", len(ex), "experiments")
 
 
+def gen_result_schema():
+    """What the reference's offline tools expect of a run's artifacts, extracted from its sources: the run-name
+    regular expression of results.py:33-44 (analysis.py:21-32 holds the same one), the keys of the metrics JSON
+    (training/routine.py:88-97) and the header of the summary CSV (training/routine.py:285)."""
+    import ast
+    import json
+    import re
+
+    res = open(os.path.join(REF, "results.py")).read()
+    tree = ast.parse(res)
+    pattern = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", "") == "EXP_RX":
+            pattern = ast.literal_eval(node.value.args[0])
+    assert pattern, "EXP_RX not found in results.py"
+    rt = open(os.path.join(REF, "training", "routine.py")).read()
+    block = re.search(r"metrics_history = \{(.*?)\n    \}", rt, re.S).group(1)
+    keys = re.findall(r'"(\w+)":', block)
+    header = re.search(r'f\.write\("(experiment,[^"]*)\\n"\)', rt).group(1)
+    used = sorted(set(re.findall(r'data\["(\w+)"\]', res)))
+    json.dump({"exp_rx": pattern, "metrics_keys": keys, "summary_header": header, "keys_read_by_results_py": used},
+              open(os.path.join(OUT, "result_schema.json"), "w"), indent=1)
+    print("result schema fixture written:", keys, header, used)
+
+
 def gen_checkpoint():
     """A checkpoint written by the reference's PPOAgent.save after one update (agent.py:310-318), with the network
     outputs on fixed states: pins the checkpoint wire format (model + optimizer state dicts)."""
@@ -290,11 +315,13 @@ if __name__ == "__main__":
         install_gymnasium_stub()
         gen_sweep()
         gen_checkpoint()
+        gen_result_schema()
         sys.exit(0)
     gym = install_gymnasium_stub()
     gen_embed(gym)
     gen_ppo()
     gen_sweep()
     gen_checkpoint()
+    gen_result_schema()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
