@@ -1,6 +1,7 @@
 // hrp_api.cu -- the extern "C" boundary of the simulator half (include/hrp.h).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -9,6 +10,12 @@
 #include "hrp_internal.cuh"
 
 static thread_local char g_err[512] = "";
+
+bool hrp_pdl_enabled()
+{
+    static const bool on = !(getenv("HRP_PDL") && getenv("HRP_PDL")[0] == '0');
+    return on;
+}
 
 void hrp_set_error(const char *fmt, ...)
 {

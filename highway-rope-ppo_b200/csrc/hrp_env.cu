@@ -810,6 +810,10 @@ hrp_step_kernel(const EnvDev P, const float *__restrict__ actions, float *__rest
     load_env(P, S, u, e, lane, xref);
     rank_full(S, P.V, lane);
 
+    // Launched with programmatic stream serialisation: everything above needs the simulator state only, so it may
+    // overlap the tail of the policy kernel that is still producing the actions.  No hrp_pdl_release() in this
+    // kernel: a following step would read the state before this one has stored it.
+    hrp_pdl_wait();
     // ActionType.act on the first frame
     float a0 = actions[2 * e], a1 = actions[2 * e + 1];
     if (lane == 0) {
@@ -936,9 +940,8 @@ int hrp_launch_step(const EnvDev &P, const float *actions, float *obs, float *re
                     uint8_t *trunc, const int32_t *perm, int32_t *row_vehicle, cudaStream_t s)
 {
     int grid = (P.E + HRP_WARPS_PER_CTA - 1) / HRP_WARPS_PER_CTA;
-    hrp_step_kernel<<<grid, 32 * HRP_WARPS_PER_CTA, 0, s>>>(P, actions, obs, reward, term, trunc, perm,
-                                                           row_vehicle);
-    HRP_CUDA_OK(cudaGetLastError());
+    HRP_CUDA_OK(hrp_launch_pdl(hrp_step_kernel, dim3(grid), dim3(32 * HRP_WARPS_PER_CTA), 0, s, P, actions, obs, reward, term,
+                               trunc, perm, row_vehicle));
     return 0;
 }
 int hrp_launch_observe(const EnvDev &P, float *obs, const int32_t *perm, int32_t *row_vehicle,

@@ -72,6 +72,27 @@ void hrp_set_error(const char *fmt, ...);
         }                                                                                   \
     } while (0)
 
+// Programmatic dependent launch (PDL): a kernel launched through hrp_launch_pdl may be scheduled while its
+// predecessor in the stream is still running -- its prologue (barrier init, TMEM allocation, index arithmetic) then
+// overlaps the predecessor's tail.  Such a kernel MUST call hrp_pdl_wait() before it reads or writes anything the
+// predecessor touches; hrp_pdl_release() at its top lets ITS successor be scheduled early in turn.  Both are no-ops
+// in a kernel that was launched the ordinary way.  HRP_PDL=0 disables the attribute.
+__device__ __forceinline__ void hrp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void hrp_pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool hrp_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t hrp_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = hrp_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // launchers implemented in hrp_env.cu
 int hrp_launch_step(const EnvDev &P, const float *actions, float *obs, float *reward, uint8_t *term,
                     uint8_t *trunc, const int32_t *perm, int32_t *row_vehicle, cudaStream_t s);

@@ -402,6 +402,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    hrp_pdl_release();   // the next kernel of the stream may set itself up while this one runs
     if (tid == 0) TC_PHASE(0);
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     // N-segmented B operand: output columns >= nseg multiply the rows of a second matrix (two weight matrices that
@@ -433,6 +434,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
     constexpr uint32_t idesc = make_idesc(BM, BN);
+    hrp_pdl_wait();      // everything above overlapped the previous kernel's tail; its results are visible from here
     if (tid == 0) TC_PHASE(1);
 
     if (ASYNC && warp < TC_THREADS / 32) {
@@ -608,9 +610,8 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
         HRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
     }
-    kern<<<grid, TC_LAUNCH_THREADS, SMEM, s>>>(M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate,
-                                       k_chunk, nseg, B2, bias2);
-    HRP_CUDA_OK(cudaGetLastError());
+    HRP_CUDA_OK(hrp_launch_pdl(kern, grid, dim3(TC_LAUNCH_THREADS), (size_t)SMEM, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc,
+                               bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2));
     return 0;
 }
 

@@ -311,6 +311,8 @@ heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, con
                  float *__restrict__ action, float *__restrict__ pre_tanh, float *__restrict__ log_prob,
                  float *__restrict__ value)
 {
+    hrp_pdl_release();
+    hrp_pdl_wait();
     long long b = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -379,6 +381,8 @@ heads_loss_backward_kernel(const float *__restrict__ a1, const float *__restrict
     __shared__ float out_s[HLB_ROWS][5], dmean_s[HLB_ROWS][4], dvalue_s[HLB_ROWS];
     __shared__ float red[8][8];
     __shared__ bool last;
+    hrp_pdl_release();
+    hrp_pdl_wait();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long row0 = (long long)blockIdx.x * HLB_ROWS;
     const int rows = (int)min((long long)HLB_ROWS, B - row0);
@@ -770,10 +774,10 @@ static int act_impl(hrp_ppo *h, const float *params, const float *states, const 
 {
     const Layout &L = h->L;
     if (int rc = forward_impl(h, params, states, batch, nullptr, nullptr, s)) return rc;
-    heads_act_kernel<<<(unsigned)((batch + 7) / 8), 256, 0, s>>>(
-        h->ac, h->ac + L.H, params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2, params + L.log_std, noise, mode,
-        seed, draw, 2 * L.H, batch, L.H, L.A, action, pre_tanh, log_prob, value);
-    HRP_CUDA_OK(cudaGetLastError());
+    HRP_CUDA_OK(hrp_launch_pdl(heads_act_kernel, dim3((unsigned)((batch + 7) / 8)), dim3(256), 0, s, (const float *)h->ac,
+                               (const float *)(h->ac + L.H), params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2,
+                               params + L.log_std, noise, mode, seed, draw, 2 * L.H, (long long)batch, L.H, L.A, action,
+                               pre_tanh, log_prob, value));
     return 0;
 }
 
@@ -955,11 +959,11 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         x = h->x; z = h->z; olp = h->olp; ad = h->adv; rt = h->ret;
     }
     if (int rc = forward_impl(h, params, x, B, nullptr, nullptr, s)) return rc;   // trunk + hidden head layers
-    heads_loss_backward_kernel<<<(unsigned)((B + HLB_ROWS - 1) / HLB_ROWS), 256, 0, s>>>(
-        h->ac, h->ac + H, H2, H, params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2, params + L.log_std, z, olp,
-        ad, rt, B, A, eps_clip, value_coef, entropy_coef, loss_scale, h->dmean, h->dvalue, h->d12, h->d12 + H,
-        grad + L.log_std, metrics, h->loss_part, h->loss_counter);
-    HRP_CUDA_OK(cudaGetLastError());
+    HRP_CUDA_OK(hrp_launch_pdl(heads_loss_backward_kernel, dim3((unsigned)((B + HLB_ROWS - 1) / HLB_ROWS)), dim3(256), 0, s,
+                               (const float *)h->ac, (const float *)(h->ac + H), H2, H, params + L.wa2, params + L.ba2,
+                               params + L.wc2, params + L.bc2, params + L.log_std, z, olp, ad, rt, B, A, eps_clip, value_coef,
+                               entropy_coef, loss_scale, h->dmean, h->dvalue, h->d12, h->d12 + H, grad + L.log_std, metrics,
+                               h->loss_part, h->loss_counter));
     const float *a1 = h->ac, *c1 = h->ac + H;
     ReducePlan plan;
     plan.nseg = 0; plan.blocks = 0;
