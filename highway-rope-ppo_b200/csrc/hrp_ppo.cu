@@ -261,6 +261,7 @@ __global__ void gather_batch_kernel(const float *__restrict__ states, const floa
                                     int A, float *__restrict__ x, float *__restrict__ z, float *__restrict__ o_olp,
                                     float *__restrict__ o_adv, float *__restrict__ o_ret)
 {
+    hrp_pdl_release();   // the first GEMM of the step sets itself up meanwhile (it waits before it reads x)
     const int W = S + A + 3;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * W) return;
