@@ -300,10 +300,11 @@ heads_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const f
     }
 }
 
-// heads + ActorCritic.get_action (agent.py:56-74) in one pass for the rollout: one warp per row computes
-// mean[A] and value from the two hidden activations, lane 0 then samples z = mean + std * n with
-// n ~ N(0,1) from Philox4x32-10(counter = (row, draw), key = seed) through Box-Muller (or takes n from
-// noise[], or n = 0 when deterministic), and writes tanh(z), z, log-prob and value.
+// heads + ActorCritic.get_action (agent.py:56-74) in one pass for the rollout: one warp per row forms mean[A] and
+// value from the two hidden activations (all loads of the row in flight together), then lane a < A samples
+// z_a = mean_a + std_a * n_a with n ~ N(0,1) from Philox4x32-10(counter = (row, draw), key = seed) through
+// Box-Muller (or takes n from noise[], or n = 0 when deterministic) and writes tanh(z_a), z_a; the log-prob terms of
+// the A lanes are added by shuffles.
 __global__ void __launch_bounds__(256)
 heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const float *__restrict__ wa2,
                  const float *__restrict__ ba2, const float *__restrict__ wc2, const float *__restrict__ bc2,
@@ -318,47 +319,55 @@ heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, con
     int lane = threadIdx.x & 31;
     if (b >= B) return;
     const float *ra = a1 + (size_t)b * ld, *rc = c1 + (size_t)b * ld;
-    float out[5];
-    for (int a = 0; a <= A; ++a) {
-        const float *w = a < A ? wa2 + (size_t)a * H : wc2;
-        const float *x = a < A ? ra : rc;
-        float s = 0.f;
-        for (int k = lane; k < H; k += 32) s = fmaf(x[k], w[k], s);
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < H; k += 32) {
+        const float xa = ra[k], xc = rc[k];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(HRP_FULL, s, d);
-        out[a] = s + (a < A ? ba2[a] : bc2[0]);
+        for (int a = 0; a < 4; ++a)
+            if (a < A) acc[a] = fmaf(xa, wa2[(size_t)a * H + k], acc[a]);
+        acc[4] = fmaf(xc, wc2[k], acc[4]);
     }
-    if (lane != 0) return;
-    float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[a] += __shfl_xor_sync(HRP_FULL, acc[a], d);
+    // lane a owns action dimension a (lanes >= A compute on dimension 0 and discard)
+    const int a = lane < A ? lane : 0;
+    float mu = acc[0];
+#pragma unroll
+    for (int q = 1; q < 4; ++q) mu = a == q ? acc[q] : mu;
+    mu += ba2[a];
+    float nrm = 0.f;
     if (mode == 2) {
         uint32_t r[4];
         hrp_philox((uint32_t)b, (uint32_t)((unsigned long long)b >> 32), (uint32_t)draw, (uint32_t)(draw >> 32),
                    (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5A5A5A5Au, r);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float u1 = ((float)(r[2 * q] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            float u2 = ((float)(r[2 * q + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            float rad = sqrtf(-2.f * logf(u1)), sn, cs;
-            sincospif(2.f * u2, &sn, &cs);
-            nrm[2 * q] = rad * cs;
-            nrm[2 * q + 1] = rad * sn;
-        }
+        const uint32_t r1 = a < 2 ? r[0] : r[2], r2 = a < 2 ? r[1] : r[3];
+        float u1 = ((float)(r1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float u2 = ((float)(r2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float rad = sqrtf(-2.f * logf(u1)), sn, cs;
+        sincospif(2.f * u2, &sn, &cs);
+        nrm = rad * ((a & 1) ? sn : cs);
     } else if (mode == 1) {
-        for (int a = 0; a < A; ++a) nrm[a] = noise[b * A + a];
+        nrm = noise[b * A + a];
     }
-    float lp = 0.f;
-    for (int a = 0; a < A; ++a) {
-        float mu = out[a], ls = log_std[a], sd = expf(ls);
-        float z = mode ? mu + sd * nrm[a] : mu;
-        float t = tanhf(z);
-        pre_tanh[b * A + a] = z;
-        action[b * A + a] = t;
-        float d = z - mu;
-        lp += -(d * d) / (2.f * sd * sd) - ls - 0.91893853320467274f;
-        lp -= log1pf(-(t * t) + 1e-6f);
+    const float ls = log_std[a], sd = expf(ls);
+    const float z = mode ? mu + sd * nrm : mu;
+    const float t = tanhf(z);
+    const float d = z - mu;
+    float lp = -(d * d) / (2.f * sd * sd) - ls - 0.91893853320467274f;
+    lp -= log1pf(-(t * t) + 1e-6f);
+    lp = lane < A ? lp : 0.f;
+    lp += __shfl_xor_sync(HRP_FULL, lp, 1);
+    lp += __shfl_xor_sync(HRP_FULL, lp, 2);
+    if (lane < A) {
+        pre_tanh[b * A + lane] = z;
+        action[b * A + lane] = t;
     }
-    if (log_prob) log_prob[b] = mode ? lp : 0.f;
-    value[b] = out[A];
+    if (lane == 0) {
+        if (log_prob) log_prob[b] = mode ? lp : 0.f;
+        value[b] = acc[4] + bc2[0];
+    }
 }
 
 // heads + PPO loss + the gradient of the hidden head layers in one launch (agent.py:76-84, 223-245): a CTA owns 16
