@@ -4,21 +4,26 @@
 //
 // with the same fused epilogue as the SIMT kernel in hrp_ppo.cu (+C, +bias[n], ReLU, ReLU-mask) and the same
 // deterministic split-K (gridDim.z partial tiles).  Arbitrary element strides cover every GEMM of the
-// forward and backward pass without transposed copies: nn.Linear forward (A = activations [B,K], B = weight
-// [N,K], both K-contiguous), dX = dY W (B = weight read with n-stride 1), dW = dY^T X (both operands
-// batch-major, i.e. "MN-contiguous").
+// forward and backward pass without transposed activation copies: nn.Linear forward (A = activations [B,K], B =
+// weight [N,K], both K-contiguous), dX = dY W^T-copy (K-contiguous against the transposed weight copies of
+// hrp_ppo.cu), dW = dY^T X (both operands batch-major, i.e. "MN-contiguous").  An N-segmented B operand lets two
+// weight matrices that are not adjacent in the flat parameter buffer act as one [N, K] operand.
 //
-// Structure (one CTA = one 128 x 128 output tile, 256 threads):
+// Structure (one CTA = one 128 x {64, 128} output tile; 8 loader / epilogue warps + 1 MMA warp):
 //   * operands are fp32 in HBM and are multiplied as TF32 on the tensor cores (kind::tf32); in the default
-//     3xTF32 mode every operand is split into hi = tf32(x) and lo = x - hi while it is staged, and
-//     D += Ahi*Bhi + Ahi*Blo + Alo*Bhi is accumulated in fp32 in TMEM, which recovers fp32-level accuracy
-//     (the dropped Alo*Blo term is ~2^-22 relative) -- the MMA time is negligible for these shapes;
-//   * tiles are staged global -> registers -> shared memory in the canonical K-major SWIZZLE_128B layout
-//     (8-row x 128-byte atoms, 16-byte chunk index XOR row%8), software-pipelined one K-block ahead,
-//     2 (3xTF32) or 4 (TF32) shared-memory stages recycled through mbarriers signalled by tcgen05.commit,
-//     sized so that two CTAs are resident per SM and overlap each other's load and MMA phases;
-//   * one elected thread issues the tcgen05.mma instructions (UMMA 128 x 128 x 8); the accumulator lives in
-//     128 TMEM columns; the epilogue reads it with tcgen05.ld (32 lanes x 32 columns per warp).
+//     3xTF32 mode every operand is split into hi = trunc_tf32(x) and lo = x - hi while it is staged, and
+//     D += Alo*Bhi + Ahi*Blo + Ahi*Bhi is accumulated in fp32 in TMEM, which recovers fp32-level accuracy
+//     (the dropped Alo*Blo term is ~2^-22 relative);
+//   * tiles are staged global -> registers (two K-blocks ahead) -> shared memory in the canonical K-major
+//     SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row%8); 2 (3xTF32) or 4 (TF32)
+//     shared-memory stages, full / empty mbarrier rings, the empty side signalled by tcgen05.commit; the
+//     single-pass TF32 mode stages with cp.async instead;
+//   * one elected lane of the MMA warp issues the tcgen05.mma instructions (UMMA 128 x BN x 8); the accumulator
+//     lives in BN TMEM columns; the epilogue reads it with tcgen05.ld (32 lanes x 16 columns at a time), stages the
+//     tile in shared memory and writes 128-bit coalesced rows;
+//   * launched with programmatic stream serialisation: the prologue overlaps the previous kernel's tail.
+// Where the time goes (phase clocks below): the 3xTF32 main loop is bound by shared-memory
+// bandwidth (48 KB of tile writes + 72 KB of UMMA operand reads per K-block), not by tensor-pipe time.
 // Plain ld.global staging (no TMA) is deliberate: the weight matrices live at 8-byte-aligned offsets of the
 // flat parameter buffer and half of the backward operands are MN-contiguous, neither of which a 128B-swizzled
 // tensor map accepts without extra copies.  The matrices are small (<= 4 MB) and L2-resident.

@@ -212,8 +212,9 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params_dev, const float *states_d
                       const float *ret_dev, const int64_t *idx_dev, int64_t batch, float eps_clip,
                       float value_coef, float entropy_coef, float loss_scale, float *grad_dev,
                       float *metrics_dev, void *stream);
-/* clip_grad_norm_ + Adam.step (agent.py:247-252) fused over the flat buffers.
- * step_dev[1] int32 is incremented on device (bias correction). */
+/* clip_grad_norm_ + Adam.step (agent.py:247-252) fused over the flat buffers: ONE cooperative launch (per-CTA
+ * sums of squares, grid synchronisation, clip coefficient, Adam).  step_dev[1] int32 is incremented on device
+ * (bias correction).  The launch is capturable in a CUDA graph. */
 int hrp_clip_adam_step(float *params_dev, const float *grad_dev, float *exp_avg_dev,
                        float *exp_avg_sq_dev, int32_t *step_dev, int64_t n, double lr, double beta1,
                        double beta2, double eps, float max_grad_norm, float *scratch_dev /* >=128 floats */,
