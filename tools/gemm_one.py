@@ -22,7 +22,8 @@ import ctypes as ct
 ph = (ct.c_longlong * 16)()
 lib.hrp_debug_gemm_phases.argtypes = [ct.POINTER(ct.c_longlong)]
 names = ["start", "setup done", "first loads issued", "first stage full", "loaders done", "accumulator ready",
-         "tile staged", "tile written", "mma kb0 issued", "mma last issued"]
+         "tile staged", "tile written", "mma kb0 issued", "mma last issued", "L4 before wait", "L4 stage free", "L4 stashed",
+         "L4 arrived", "M4 stage full", "M4 committed"]
 for rep in range(3):
     _lib.check(lib.hrp_gemm_strided(M, N, K, A.data_ptr(), sam, sak, B.data_ptr(), sbn, sbk, C.data_ptr(), N, bias.data_ptr(), 1, mode, st))
     lib.hrp_debug_gemm_phases(ph)
