@@ -28,7 +28,6 @@
 // flat parameter buffer and half of the backward operands are MN-contiguous, neither of which a 128B-swizzled
 // tensor map accepts without extra copies.  The matrices are small (<= 4 MB) and L2-resident.
 #include "hrp_internal.cuh"
-#include <stdlib.h>
 
 // phase clocks of CTA (0,0,0), thread 0 (+ the MMA warp's lane 0): see hrp_debug_gemm_phases
 __device__ long long g_tc_phase[16];
@@ -601,209 +600,14 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
 }
 
-// =====================================================================================================================
-// A-in-TMEM variant for K-contiguous A (forward and input-gradient GEMMs).  With both operands in shared memory the
-// 3xTF32 main loop is bound by shared-memory bandwidth: per K-block the loaders write 48 KB of hi/lo tiles and the 12
-// UMMAs read 72 KB (~920 cycles at 128 B/cycle against ~384 cycles of tensor-pipe time); two thirds of that is the A
-// tile.  Here the MMAs take A from tensor memory (`tcgen05.mma [d], [a], b_desc`): the loaders fetch the A tile with
-// the same coalesced 16-byte loads as before, pass the RAW fp32 tile through a small transposition buffer in shared
-// memory (16 KB written + 16 KB read instead of 32 + 48), after which thread t holds 16 consecutive k of tile row
-// t % 128, splits them and writes hi / lo into TMEM with tcgen05.st (row = lane, k = column).  Only the B tile goes
-// through the swizzled stages.  (A first version that loaded rows directly, one row per thread, was slower than the
-// SS path: uncoalesced.)  TMEM columns: [0, BN) accumulator, then STAGES x (hi[32] | lo[32]).
-template <int BN>
-__host__ __device__ constexpr int ts_stages() { return BN == 64 ? 3 : 2; }   // BN + 64 STAGES <= 256 columns
-constexpr int TS_PITCH = 36;   // floats per row of the transposition buffer: 16-byte aligned, conflict-free both ways
-
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-template <int BMODE, int BN>
-__global__ void __launch_bounds__(TC_LAUNCH_THREADS)
-tc_gemm_ts_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, long long sak,
-                  const float *__restrict__ B, long long sbn, long long sbk, float *__restrict__ C, int ldc,
-                  const float *__restrict__ bias, int relu, const float *__restrict__ mask, int ldm, int accumulate,
-                  int k_chunk, int nseg, const float *__restrict__ B2, const float *__restrict__ bias2)
-{
-    constexpr int NSPLIT = 3, PARTS = 2;
-    constexpr int B_TILE_BYTES = BN * BK * 4;
-    constexpr int STAGE_BYTES = PARTS * B_TILE_BYTES;
-    constexpr int STAGES = ts_stages<BN>();
-    constexpr int A_COLS = PARTS * BK;                       // TMEM columns of one A stage
-    constexpr int TM_COLS = 256;
-    constexpr int T_BYTES = BM * TS_PITCH * 4;               // one transposition buffer
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_done;
-    __shared__ uint32_t tmem_base_s;
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    float *tbuf = (float *)(smem + STAGES * STAGE_BYTES);    // 2 x [BM][TS_PITCH]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    hrp_pdl_release();
-    if (tid == 0) TC_PHASE(0);
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const bool seg2 = nseg > 0 && n0 >= nseg;
-    const float *__restrict__ Bp = seg2 ? B2 : B;
-    const float *__restrict__ biasp = seg2 ? bias2 : bias;
-    const int bn0 = seg2 ? n0 - nseg : n0;
-    const int bN = nseg > 0 ? (seg2 ? N - nseg : nseg) : N;
-    const int kbeg = blockIdx.z * k_chunk, kend = min(K, kbeg + k_chunk);
-    const int nkb = (kend - kbeg + BK - 1) / BK;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bar_full[s], TC_THREADS);
-            mbar_init(&bar_empty[s], 1);
-        }
-        mbar_init(&bar_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "n"(TM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = tmem_base_s;
-    constexpr uint32_t idesc = make_idesc(BM, BN);
-    hrp_pdl_wait();
-    if (tid == 0) TC_PHASE(1);
-
-    if (warp < TC_THREADS / 32) {
-        // ===== loader warps.  Warp w may touch TMEM lanes 32 (w % 4) .. + 31: thread t <-> tile row t % 128.
-        const int row = tid & 127, khalf = (tid >> 7) * 16;
-        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-        Stager<ST_K4, BM> ra0, ra1;
-        Stager<BMODE, BN> rb0, rb1;
-#define HRP_TS_STEP(kb_, ra, rb)                                                                                  \
-        {                                                                                                         \
-            const int kq = (kb_), sq = kq % STAGES;                                                               \
-            float *tb = tbuf + (kq & 1) * (BM * TS_PITCH);                                                        \
-            /* raw tile -> transposition buffer (coalesced-load layout: row idx / 8, 16-byte chunk idx % 8) */    \
-            _Pragma("unroll") for (int i = 0; i < 4; ++i) {                                                       \
-                const int idx = tid + i * TC_THREADS;                                                             \
-                *(float4 *)(tb + (idx >> 3) * TS_PITCH + (idx & 7) * 4) =                                         \
-                    make_float4(ra.v[4 * i], ra.v[4 * i + 1], ra.v[4 * i + 2], ra.v[4 * i + 3]);                  \
-            }                                                                                                     \
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");                                         \
-            if (kq >= STAGES) {                                                                                   \
-                mbar_wait(&bar_empty[sq], (uint32_t)(((kq / STAGES) - 1) & 1)); /* MMAs of kq - STAGES retired */ \
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                   \
-            }                                                                                                     \
-            const uint32_t a_t = tmem_d + lane_base + (uint32_t)(BN + sq * A_COLS + khalf);                       \
-            uint32_t hi[16], lo[16];                                                                              \
-            _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                       \
-                const float4 x = *(const float4 *)(tb + row * TS_PITCH + khalf + 4 * j);                          \
-                const float xs[4] = {x.x, x.y, x.z, x.w};                                                         \
-                _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                   \
-                    hi[4 * j + e] = __float_as_uint(xs[e]) & 0xFFFFE000u;                                         \
-                    lo[4 * j + e] = __float_as_uint(xs[e] - __uint_as_float(hi[4 * j + e]));                      \
-                }                                                                                                 \
-            }                                                                                                     \
-            tmem_st16(a_t, hi);                                                                                   \
-            tmem_st16(a_t + BK, lo);                                                                              \
-            rb.template stash<NSPLIT>(smem + sq * STAGE_BYTES, B_TILE_BYTES, tid);                                \
-            if (kq + 2 < nkb) {                                                                                   \
-                const int k0 = kbeg + (kq + 2) * BK;                                                              \
-                ra.fetch(A, sam, sak, m0, M, k0, kend, tid);                                                      \
-                rb.fetch(Bp, sbn, sbk, bn0, bN, k0, kend, tid);                                                   \
-            }                                                                                                     \
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");                                          \
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                          \
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                      \
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_full[sq])) : "memory");   \
-        }
-        if (nkb > 0) {
-            ra0.fetch(A, sam, sak, m0, M, kbeg, kend, tid);
-            rb0.fetch(Bp, sbn, sbk, bn0, bN, kbeg, kend, tid);
-        }
-        if (nkb > 1) {
-            ra1.fetch(A, sam, sak, m0, M, kbeg + BK, kend, tid);
-            rb1.fetch(Bp, sbn, sbk, bn0, bN, kbeg + BK, kend, tid);
-        }
-        if (tid == 0) TC_PHASE(2);
-        for (int kb = 0; kb < nkb; kb += 2) {
-            HRP_TS_STEP(kb, ra0, rb0)
-            if (kb == 0 && tid == 0) TC_PHASE(3);
-            if (kb + 1 < nkb) HRP_TS_STEP(kb + 1, ra1, rb1)
-        }
-#undef HRP_TS_STEP
-        if (tid == 0) TC_PHASE(4);
-    } else {
-        // ===== MMA warp
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            mbar_wait(&bar_full[s], (uint32_t)((kb / STAGES) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint64_t db_hi = make_desc(smem_u32(smem + s * STAGE_BYTES));
-                const uint64_t db_lo = db_hi + (B_TILE_BYTES >> 4);
-                const uint32_t a_hi = tmem_d + (uint32_t)(BN + s * A_COLS), a_lo = a_hi + BK;
-#pragma unroll
-                for (int kk = 0; kk < BK / 8; ++kk) {       // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
-                    const uint64_t o = (uint64_t)(kk * 2);
-                    const uint32_t ac = (uint32_t)(kk * 8);
-                    const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-                    umma_tf32_ts(tmem_d, a_lo + ac, db_hi + o, idesc, acc);
-                    umma_tf32_ts(tmem_d, a_hi + ac, db_lo + o, idesc, 1u);
-                    umma_tf32_ts(tmem_d, a_hi + ac, db_hi + o, idesc, 1u);
-                }
-                umma_commit(&bar_empty[s]);
-                if (kb + 1 == nkb) umma_commit(&bar_done);
-                if (kb == 0) TC_PHASE(8);
-                if (kb + 1 == nkb) TC_PHASE(9);
-            }
-            __syncwarp();
-        }
-    }
-
-    tc_epilogue<BN>(smem, &bar_done, tmem_d, nkb, M, N, m0, n0, bn0, C, ldc, biasp, relu, mask, ldm, accumulate);
-    if (tid == 0) TC_PHASE(7);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TM_COLS) : "memory");
-}
-
-template <int BMODE, int BN>
-int launch_ts(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
-              const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias, int relu,
-              const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2, const float *bias2)
-{
-    constexpr int OPERANDS = ts_stages<BN>() * 2 * BN * BK * 4 + 2 * BM * TS_PITCH * 4;
-    constexpr int EPILOGUE = BM * (BN + 4) * 4;
-    constexpr int SMEM = (OPERANDS > EPILOGUE ? OPERANDS : EPILOGUE) + 1024;
-    static bool configured = false;
-    auto kern = tc_gemm_ts_kernel<BMODE, BN>;
-    if (!configured) {
-        HRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        configured = true;
-    }
-    HRP_CUDA_OK(hrp_launch_pdl(kern, grid, dim3(TC_LAUNCH_THREADS), (size_t)SMEM, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc,
-                               bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2));
-    return 0;
-}
+// Two variants that kept the A operand in tensor memory (tcgen05.st of the hi / lo halves, TS-form
+// `tcgen05.mma [d], [a], b_desc`) were built and are parity-green in the history of this file: one with row-per-
+// thread global loads (1030 vs 920 cycles per K-block, twice as slow for batch-major A) and one that kept the
+// coalesced loads and passed the raw tile through a shared-memory transposition buffer (7.97k vs 7.29k main-loop
+// cycles at 4096 x 256 x 256).  Neither beat the SS path: the per-K-block phase clocks (slots 10-15 of
+// hrp_debug_gemm_phases) show that the MMA warp needs ~1050 cycles to push the 12 UMMAs of a K-block through the
+// tensor pipe (~88 cycles per 128 x 64 x 8 instruction) while a stash takes ~580 and the stage hand-over ~430, i.e.
+// the main loop is paced by the UMMA stream itself, whichever memory the A operand comes from.
 
 template <int AMODE, int BMODE, int NSPLIT, int BN, bool ASYNC = false>
 int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
@@ -883,14 +687,6 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     const bool b_k4 = bkc && K % 4 == 0 && sbn % 4 == 0 && aligned(B, 16) && (nseg == 0 || aligned(B2, 16));
 #define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2)
     int rc;
-    static const bool use_ts = getenv("HRP_TC_TS") && getenv("HRP_TC_TS")[0] == '1';
-    if (use_ts && nsplit == 3 && a_k4 && (b_k4 || b_k2)) {
-#define HRP_TS_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2
-        if (b_k4) rc = bn == 64 ? launch_ts<ST_K4, 64>(HRP_TS_ARGS) : launch_ts<ST_K4, 128>(HRP_TS_ARGS);
-        else rc = bn == 64 ? launch_ts<ST_K2, 64>(HRP_TS_ARGS) : launch_ts<ST_K2, 128>(HRP_TS_ARGS);
-#undef HRP_TS_ARGS
-        return rc < 0 ? rc : splits;
-    }
     // cp.async staging pays off for the single-pass mode only (measured: 3xTF32 hidden forward 12.6 us register-staged
     // vs 14.5 us cp.async -- the lo tiles need a second pass through shared memory; TF32 H=512 19.6 -> 16.6 us)
     if (a_k4 && b_k2 && nsplit == 1) rc = dispatch_async(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2);
