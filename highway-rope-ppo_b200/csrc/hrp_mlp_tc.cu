@@ -284,7 +284,7 @@ __host__ __device__ constexpr int tc_stages()
 }
 
 // ---- epilogue shared by both main loops: TMEM -> registers -> shared (row-major, padded) -> coalesced global rows
-template <int BN>
+template <int BN, bool DUAL>
 __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *bar_done_p, uint32_t tmem_d, int nkb, int M, int N,
                                             int m0, int n0, int bn0, float *__restrict__ C, int ldc,
                                             const float *__restrict__ biasp, int relu, const float *__restrict__ mask,
@@ -312,7 +312,21 @@ __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *bar_done_p,
                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
                       "=r"(v[15])
                     : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (DUAL) {   // 3xTF32: columns [BN, 2 BN) hold the A_hi x B_lo part of the same tile
+                    uint32_t u[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                        "%13, %14, %15}, [%16];"
+                        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]),
+                          "=r"(u[15])
+                        : "r"(taddr + (uint32_t)BN));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0u;
@@ -401,6 +415,10 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     constexpr int B_TILE_BYTES = BN * BK * 4;
     constexpr int STAGE_BYTES = PARTS * (A_TILE_BYTES + B_TILE_BYTES);
     constexpr int STAGES = tc_stages<NSPLIT, BN, ASYNC>();
+    // 3xTF32 accumulates in 2 BN columns: [0, BN) <- A_hi B_hi + A_lo B_hi, [BN, 2 BN) <- A_hi B_lo (summed in the
+    // epilogue).  The hi and lo tiles of B are adjacent in a stage, so ONE UMMA with N = 2 BN multiplies A_hi by both:
+    // two instructions per k-step instead of three (the UMMA stream paces the main loop, ~88 cycles per instruction)
+    constexpr int TM_COLS = NSPLIT == 3 ? 2 * BN : BN;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar_full[4], bar_empty[4], bar_done;
     __shared__ uint32_t tmem_base_s;
@@ -430,7 +448,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "n"(BN)
+                     "n"(TM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -439,6 +457,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
     constexpr uint32_t idesc = make_idesc(BM, BN);
+    constexpr uint32_t idesc2 = make_idesc(BM, 2 * BN);   // A_hi against the stacked [B_hi ; B_lo] tile
     hrp_pdl_wait();      // everything above overlapped the previous kernel's tail; its results are visible from here
     if (tid == 0) TC_PHASE(1);
 
@@ -570,15 +589,14 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
                 const uint32_t a_s = smem_u32(smem + s * STAGE_BYTES), b_s = a_s + PARTS * A_TILE_BYTES;
                 // descriptors differ only in the start-address field (bits 0-13, units of 16 bytes)
                 const uint64_t da_hi = make_desc(a_s), db_hi = make_desc(b_s);
-                const uint64_t da_lo = da_hi + (A_TILE_BYTES >> 4), db_lo = db_hi + (B_TILE_BYTES >> 4);
+                const uint64_t da_lo = da_hi + (A_TILE_BYTES >> 4);   // B_lo follows B_hi: rows BN .. 2 BN - 1 of the stacked tile
 #pragma unroll
                 for (int kk = 0; kk < BK / 8; ++kk) {       // UMMA_K = 8 tf32 = 32 bytes = 2 address units
                     const uint64_t o = (uint64_t)(kk * 2);
                     const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
                     if (NSPLIT == 3) {
-                        umma_tf32(tmem_d, da_lo + o, db_hi + o, idesc, acc);
-                        umma_tf32(tmem_d, da_hi + o, db_lo + o, idesc, 1u);
-                        umma_tf32(tmem_d, da_hi + o, db_hi + o, idesc, 1u);
+                        umma_tf32(tmem_d, da_hi + o, db_hi + o, idesc2, acc);   // [A_hi B_hi | A_hi B_lo]
+                        umma_tf32(tmem_d, da_lo + o, db_hi + o, idesc, 1u);     // + A_lo B_hi into the first half
                     } else {
                         umma_tf32(tmem_d, da_hi + o, db_hi + o, idesc, acc);
                     }
@@ -593,11 +611,11 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
         }
     }
 
-    tc_epilogue<BN>(smem, &bar_done, tmem_d, nkb, M, N, m0, n0, bn0, C, ldc, biasp, relu, mask, ldm, accumulate);
+    tc_epilogue<BN, NSPLIT == 3>(smem, &bar_done, tmem_d, nkb, M, N, m0, n0, bn0, C, ldc, biasp, relu, mask, ldm, accumulate);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TM_COLS) : "memory");
 }
 
 // Two variants that kept the A operand in tensor memory (tcgen05.st of the hi / lo halves, TS-form
