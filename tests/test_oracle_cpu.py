@@ -282,3 +282,123 @@ def test_sim_observation_sorted_and_shuffled(highway_config):
         assert rows2[1 + perm[k]] == 1 + k
     p = oh.shuffle_perm(3, 5, 2, 14)
     assert sorted(p) == list(range(14))
+
+
+def test_sim_reward_extremes(highway_config):
+    """A.9: the normalised reward reaches 1 on the rightmost lane at >= 30 m/s and 2/3 on lane 0 at <= 20 m/s; it is
+    scaled by the forward speed v cos(h), and zeroed off the road."""
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config))
+    cases = [  # (lane, speed, heading, reward after a zero-acceleration, zero-steering step)
+        (3, 30.0, 0.0, 1.0),
+        (0, 20.0, 0.0, (0.0 + 0.0 + 1.0) / 1.5),
+        (3, 35.0, 0.0, 1.0),                                   # speed term clipped at 1
+        (1, 25.0, 0.0, (0.1 / 3 + 0.4 * 0.5 + 1.0) / 1.5),
+    ]
+    for lane, speed, heading, want in cases:
+        env.reset(1)
+        st = env.get_state()
+        st["x"][0], st["y"][0], st["speed"][0], st["heading"][0] = 100.0, 4.0 * lane, speed, heading
+        st["lane"][0] = st["target_lane"][0] = lane
+        env.set_state(st)
+        r, term, trunc = env.step([0.0, 0.0])   # a0 = 0 -> acceleration 0, a1 = 0 -> steering 0
+        assert abs(r - want) < 1e-12 and not term and not trunc, (lane, speed, r, want)
+
+
+def test_sim_mobil_rejects_a_lane_whose_follower_would_brake_hard(highway_config):
+    """A.6 MOBIL: the candidate lane's new follower may not be forced below -LANE_CHANGE_MAX_BRAKING_IMPOSED = -2 m/s^2.
+    Vehicle 1 sits behind a slow leader on lane 1; lane 2 has a fast vehicle 8 m behind it (unsafe), lane 0 is free."""
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config, vehicles=3))
+    env.reset(5)
+    st = env.get_state()
+    #              ego    v1     leader  fast follower on lane 2
+    st["x"][:] = [0.0, 200.0, 235.0, 192.0]
+    st["y"][:] = [12.0, 4.0, 4.0, 8.0]
+    st["lane"][:] = st["target_lane"][:] = [3, 1, 1, 2]
+    st["speed"][:] = [0.0, 25.0, 18.0, 30.0]
+    st["target_speed"][:] = [0.0, 30.0, 18.0, 30.0]
+    st["delta"][:] = 4.0
+    st["timer"][:] = [0.0, 1.0 + 1e-9, 0.0, 0.0]   # v1 decides on the first frame
+    st["heading"][:] = 0.0
+    env.set_state(st)
+    # by hand: new follower (v = 30) behind v1 (v = 25) at 8 m: gap* = 10 + 45 + 30 * 5 / (2 sqrt 15) = 74.4,
+    # a = 3 (1 - 1) - 3 (74.4 / 8)^2 << -2  -> lane 2 refused; lane 0: no follower, no leader, jerk = cur - 0 >= 0.2
+    gap = 10.0 + 25.0 * 1.5 + 25.0 * 7.0 / (2 * math.sqrt(15.0))
+    assert 3.0 * (gap / 35.0) ** 2 >= 0.2
+    env.step([0.0, 0.0])
+    assert env.get_state()["target_lane"][1] == 0
+    # without the fast follower lane 2 (the later candidate) wins, as in the timer test
+    st["x"][3] = 1000.0
+    env.set_state(st)
+    env.step([0.0, 0.0])
+    assert env.get_state()["target_lane"][1] == 2
+
+
+def test_sim_rectangle_contact_thresholds(highway_config):
+    """A.7: two 5 x 2 m rectangles at equal speed (no relative displacement): contact iff both axis gaps are closed."""
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config, vehicles=1))
+    for dx, dy, hit in ((5.05, 0.0, False), (4.95, 0.0, True), (4.0, 2.05, False), (4.0, 1.95, True), (0.0, 1.99, True),
+                        (6.0, 3.0, False)):
+        env.reset(5)
+        st = env.get_state()
+        st["x"][:] = [100.0, 100.0 + dx]
+        st["y"][:] = [4.0, 4.0 + dy]
+        st["lane"][:] = st["target_lane"][:] = [1, 1 if dy < 2 else 2]
+        st["speed"][:] = [20.0, 20.0]
+        st["target_speed"][:] = [20.0, 20.0]
+        st["heading"][:] = 0.0
+        st["timer"][:] = 0.0
+        env.set_state(st)
+        # keep the ego at constant speed (a0 = 0); the other vehicle's IDM acceleration is the same on the first frame
+        # only, so test the flags after ONE policy step but derive the verdict from the initial geometry: with equal
+        # speeds the follower only falls back, which never closes a longitudinal gap that was open
+        r, term, trunc = env.step([0.0, 0.0])
+        s1 = env.get_state()
+        assert bool(s1["crashed"][0]) == hit and term == hit, (dx, dy, s1["crashed"], term)
+
+
+def test_sim_meta_action_ego(highway_config):
+    """DiscreteMetaAction / MDPVehicle (A.5): FASTER / SLOWER move the target speed over [20, 25, 30]; lane changes are
+    clamped to the road; IDLE keeps both."""
+    cfg = _lone_ego_cfg(highway_config)
+    cfg["action"] = {"type": "DiscreteMetaAction"}
+    env = oh.OracleEnv(cfg)
+
+    def run(action, lane=1, speed=25.0):
+        env.reset(2)
+        st = env.get_state()
+        st["x"][0], st["y"][0], st["speed"][0], st["heading"][0] = 100.0, 4.0 * lane, speed, 0.0
+        st["lane"][0] = st["target_lane"][0] = lane
+        st["target_speed"][0] = speed
+        env.set_state(st)
+        env.step([float(action), 0.0])
+        return env.get_state()
+
+    assert run(3)["target_speed"][0] == 30.0 and run(4)["target_speed"][0] == 20.0      # FASTER, SLOWER
+    assert run(3, speed=30.0)["target_speed"][0] == 30.0 and run(4, speed=20.0)["target_speed"][0] == 20.0
+    assert run(1)["target_speed"][0] == 25.0 and run(1)["target_lane"][0] == 1          # IDLE
+    assert run(0)["target_lane"][0] == 0 and run(2)["target_lane"][0] == 2              # LANE_LEFT, LANE_RIGHT
+    assert run(0, lane=0)["target_lane"][0] == 0 and run(2, lane=3)["target_lane"][0] == 3
+    s = run(3)
+    assert s["speed"][0] > 25.0 and abs(s["y"][0] - 4.0) < 1e-9                          # speeds up, stays on its lane
+    s = run(2)
+    assert 4.0 < s["y"][0] <= 8.0 + 1e-6 and s["heading"][0] >= 0.0                     # steers towards lane 2
+
+
+def test_sim_observation_normalisation_and_clip(highway_config):
+    """A.8: the ego row is absolute, the others relative to it; x, y / 100 and vx, vy / 30, clipped to [-1, 1];
+    vehicles further than the row budget or behind by more than 10 m (see_behind False) are left out; zero padding."""
+    env = oh.OracleEnv(_lone_ego_cfg(highway_config, vehicles=3))
+    env.reset(5)
+    st = env.get_state()
+    st["x"][:] = [300.0, 450.0, 320.0, 280.0]      # +150 m (clipped), +20 m, -20 m (behind: dropped)
+    st["y"][:] = [4.0, 8.0, 0.0, 4.0]
+    st["lane"][:] = st["target_lane"][:] = [1, 2, 0, 1]
+    st["speed"][:] = [25.0, 22.0, 28.0, 20.0]
+    st["heading"][:] = 0.0
+    env.set_state(st)
+    obs = env.observe()
+    assert obs.shape == (15, 4) and obs.dtype == np.float32
+    np.testing.assert_allclose(obs[0], [1.0, 0.04, 25.0 / 30.0, 0.0], atol=1e-7)           # ego: x = 300 / 100 clipped
+    np.testing.assert_allclose(obs[1], [0.2, -0.04, 3.0 / 30.0, 0.0], atol=1e-7)           # nearest first (sorted)
+    np.testing.assert_allclose(obs[2], [1.0, 0.04, -3.0 / 30.0, 0.0], atol=1e-7)           # 150 m ahead: clipped
+    assert np.all(obs[3:] == 0.0)
