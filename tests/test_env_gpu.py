@@ -314,3 +314,122 @@ def test_host_buffer_entry_points_match_device_path(highway_config):
     with pytest.raises(ValueError):
         a_env.step_host(torch.zeros(3, device="cuda:0"), obs_h, rew, te, tr)
     a_env.close(); b_env.close()
+
+
+class _KernelEnv:
+    """One GPU env behind the OracleEnv interface, so that the hand-derived scenarios of tests/test_oracle_cpu.py can
+    be replayed on the kernel itself (no oracle involved)."""
+
+    def __init__(self, cfg):
+        self.env = _vec(cfg, 1, autoreset=False)
+        self.N = cfg["observation"]["vehicles_count"]
+
+    def reset(self, seed):
+        self.env.reset(seed)
+
+    def get_state(self):
+        st = self.env.get_state()
+        out = {k: st[k][0].copy() for k in oh.STATE_F64 + oh.STATE_I32}
+        out["time"] = float(st["time"][0])
+        self._extra = {k: st[k] for k in ("episode", "obs_draw")}
+        return out
+
+    def set_state(self, st):
+        full = {k: np.asarray(st[k])[None] for k in oh.STATE_F64 + oh.STATE_I32}
+        full["time"] = np.array([st["time"]])
+        full.update(self._extra)
+        self.env.set_state(full)
+
+    def step(self, action):
+        obs, r, te, tr = self.env.step(torch.tensor([action], dtype=torch.float32, device="cuda:0"))
+        self.obs = obs[0].cpu().numpy()
+        return float(r[0]), bool(te[0]), bool(tr[0])
+
+    def close(self):
+        self.env.close()
+
+
+def test_kernel_reward_extremes_by_hand(highway_config):
+    """The scenario of test_oracle_cpu.test_sim_reward_extremes on the CUDA kernel (fp32: 2e-6)."""
+    env = _KernelEnv(_cfg(highway_config, vehicles_count=0))
+    for lane, speed, want in ((3, 30.0, 1.0), (0, 20.0, 1.0 / 1.5), (3, 35.0, 1.0), (1, 25.0, (0.1 / 3 + 0.2 + 1.0) / 1.5)):
+        env.reset(1)
+        st = env.get_state()
+        st["x"][0], st["y"][0], st["speed"][0], st["heading"][0] = 100.0, 4.0 * lane, speed, 0.0
+        st["lane"][0] = st["target_lane"][0] = lane
+        env.set_state(st)
+        r, term, trunc = env.step([0.0, 0.0])
+        assert abs(r - want) < 2e-6 and not term and not trunc, (lane, speed, r, want)
+    env.close()
+
+
+def test_kernel_mobil_safety_and_timer_by_hand(highway_config):
+    """MOBIL on the kernel: the unsafe lane is refused, the later candidate wins otherwise, and a timer reset to zero
+    fires on the 16th frame (fp64 timer: 15 x 1/15 < 1)."""
+    env = _KernelEnv(_cfg(highway_config, vehicles_count=3))
+    env.reset(5)
+    st = env.get_state()
+    st["x"][:] = [0.0, 200.0, 235.0, 192.0]
+    st["y"][:] = [12.0, 4.0, 4.0, 8.0]
+    st["lane"][:] = st["target_lane"][:] = [3, 1, 1, 2]
+    st["speed"][:] = [0.0, 25.0, 18.0, 30.0]
+    st["target_speed"][:] = [0.0, 30.0, 18.0, 30.0]
+    st["delta"][:] = 4.0
+    st["timer"][:] = [0.0, 1.0 + 1e-9, 0.0, 0.0]
+    st["heading"][:] = 0.0
+    st["crashed"][:] = 0
+    st["has_impact"][:] = 0
+    env.set_state(st)
+    env.step([0.0, 0.0])
+    assert env.get_state()["target_lane"][1] == 0          # lane 2 would force its follower below -2 m/s^2
+    st["x"][3] = 1000.0
+    env.set_state(st)
+    env.step([0.0, 0.0])
+    assert env.get_state()["target_lane"][1] == 2          # both lanes acceptable: the later candidate overwrites
+    st["timer"][1] = 0.0
+    env.set_state(st)
+    env.step([0.0, 0.0])
+    assert env.get_state()["target_lane"][1] == 1          # 15 frames of 1/15: 1.0 < timer never true
+    env.step([0.0, 0.0])
+    assert env.get_state()["target_lane"][1] == 2          # fires on the first frame of the next step
+    env.close()
+
+
+def test_kernel_rectangle_contact_thresholds_by_hand(highway_config):
+    """5 x 2 m rectangles at equal speed: contact iff both axis gaps are closed (kernel SAT, rank-neighbour search)."""
+    env = _KernelEnv(_cfg(highway_config, vehicles_count=1))
+    for dx, dy, hit in ((5.05, 0.0, False), (4.95, 0.0, True), (4.0, 2.05, False), (4.0, 1.95, True), (0.0, 1.99, True),
+                        (6.0, 3.0, False)):
+        env.reset(5)
+        st = env.get_state()
+        st["x"][:] = [100.0, 100.0 + dx]
+        st["y"][:] = [4.0, 4.0 + dy]
+        st["lane"][:] = st["target_lane"][:] = [1, 1 if dy < 2 else 2]
+        st["speed"][:] = [20.0, 20.0]
+        st["target_speed"][:] = [20.0, 20.0]
+        st["heading"][:] = 0.0
+        st["timer"][:] = 0.0
+        env.set_state(st)
+        r, term, trunc = env.step([0.0, 0.0])
+        s1 = env.get_state()
+        assert bool(s1["crashed"][0]) == hit and term == hit, (dx, dy, s1["crashed"], term)
+    env.close()
+
+
+def test_kernel_observation_clip_by_hand(highway_config):
+    """Relative rows, / 100 and / 30 normalisation, clip to [-1, 1], vehicles more than 10 m behind dropped, padding."""
+    env = _KernelEnv(_cfg(highway_config, vehicles_count=3))
+    env.reset(5)
+    st = env.get_state()
+    st["x"][:] = [300.0, 450.0, 320.0, 280.0]
+    st["y"][:] = [4.0, 8.0, 0.0, 4.0]
+    st["lane"][:] = st["target_lane"][:] = [1, 2, 0, 1]
+    st["speed"][:] = [25.0, 22.0, 28.0, 20.0]
+    st["heading"][:] = 0.0
+    env.set_state(st)
+    obs = env.env.observe()[0].cpu().numpy()
+    np.testing.assert_allclose(obs[0], [1.0, 0.04, 25.0 / 30.0, 0.0], atol=1e-6)
+    np.testing.assert_allclose(obs[1], [0.2, -0.04, 3.0 / 30.0, 0.0], atol=1e-6)
+    np.testing.assert_allclose(obs[2], [1.0, 0.04, -3.0 / 30.0, 0.0], atol=1e-6)
+    assert np.all(obs[3:] == 0.0)
+    env.close()
