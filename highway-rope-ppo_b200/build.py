@@ -17,8 +17,13 @@ LIB_PATH = os.path.join(LIB_DIR, "libhrp_b200.so")
 SOURCES = ["hrp_env.cu", "hrp_api.cu", "hrp_ppo.cu", "hrp_mlp_tc.cu", "hrp_comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC",
 ]
+# per-file additions.  hrp_env.cu: approximate division / sqrt / transcendental intrinsics and flush-to-zero in the
+# fused step kernel (164 -> 152 us per 4096-env launch); the embedding epilogue's float32 operation order is kept by
+# explicit __f*_rn intrinsics, and the parity tests (tests/test_env_gpu.py, tests/test_embed_gpu.py, 52 k injected
+# env-steps of tools/long_parity.py) hold at unchanged tolerances.  The PPO files stay IEEE.
+EXTRA_FLAGS = {"hrp_env.cu": ["--use_fast_math"]}
 
 
 def _sources():
@@ -39,15 +44,34 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    base = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH] + _sources() + ["-lcuda"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        base += ["-Xptxas", "-v"]
+    jobs = []
+    for src in _sources():   # one translation unit per process, in parallel
+        name = os.path.basename(src)
+        obj = os.path.join(obj_dir, name[:-3] + ".o")
+        cmd = base + EXTRA_FLAGS.get(name, []) + ["-c", src, "-o", obj]
+        jobs.append((name, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for name, obj, proc in jobs:
+        out, _ = proc.communicate()
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(out)
+        failed |= proc.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed building libhrp_b200.so")
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-o", LIB_PATH]
+    res = subprocess.run(link + [obj for _, obj, _ in jobs] + ["-lcuda"], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libhrp_b200.so")
+        raise RuntimeError("nvcc failed linking libhrp_b200.so")
+    for _, obj, _ in jobs:   # the objects are intermediates: only the .so ships
+        os.remove(obj)
+    os.rmdir(obj_dir)
     return LIB_PATH
 
 
