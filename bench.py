@@ -318,16 +318,16 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": "hrp_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one 4096-env launch, ncu --set full
-                # (profiles/r01_step_kernel_v2_ncu_full.csv): the 64-slot state arena is read once, writes stay in L2
-                "traffic": int(12_762_000 * E / 4096), "peak_source": peak_src,
+                # (profiles/r01_step_kernel_v3_ncu_full.csv): the 64-slot state arena is read once, writes stay in L2
+                "traffic": int(12_756_000 * E / 4096), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_us": env_kernel_s * 1e6,
                 "share_of_step": env_ms / (env_ms + act_ms),
-                # the binding resource: warp-instruction issue slots.  1.116e8 warp instructions per 4096-env launch
+                # the binding resource: warp-instruction issue slots.  1.018e8 warp instructions per 4096-env launch
                 # (ncu smsp__inst_executed.sum, profiles/r01_step_kernel_*), 4 schedulers x 148 SMs x sm clock
-                "issue": {"warp_instructions_per_launch": 1.116e8 * E / 4096,
-                          "achieved_ginst_s": 1.116e8 * E / 4096 / env_kernel_s / 1e9,
+                "issue": {"warp_instructions_per_launch": 1.018e8 * E / 4096,
+                          "achieved_ginst_s": 1.018e8 * E / 4096 / env_kernel_s / 1e9,
                           "peak_ginst_s": 4 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6 / 1e9,
-                          "frac": 1.116e8 * E / 4096 / env_kernel_s / (4 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6)},
+                          "frac": 1.018e8 * E / 4096 / env_kernel_s / (4 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6)},
                 "note": "instruction-issue-bound kernel (15 fused substeps per launch), not HBM-bound; see DESIGN.md 3.1"}
 
     # e2e: the same step through the host-buffer API (pinned host obs -> policy -> host actions -> env -> host obs)
