@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- policy env-steps/s of the lock-step highway-v0 + PPO hot path on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E] [--hidden H]
+                    [--condition rope|sorted|shuffled|rankpe|distpe] [--obs-vehicles N] [--d-embed D]
+
+BASELINE.json configs (the default is configs[1]):
+    configs[2]: --condition rankpe --d-embed 16 --obs-vehicles 30 --envs 16384      (also distpe, d 4 / 8 / 16)
+    configs[3]: --hidden 512 --envs 8192 under torchrun with 8 ranks (65536 envs)
 
 Workload (BASELINE.json configs[1]): shuffled Kinematics observation + RoPE, hidden_dim 256, 4096 lock-step envs
 per GPU, V = 51 vehicles, N = 15 rows, F = 4.  RoPE rotates rotate_dim = 4 features: the d_embed 16 of the config
@@ -46,6 +51,11 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     p.add_argument("--hidden", type=int, default=256)
+    p.add_argument("--condition", default="rope", choices=["rope", "sorted", "shuffled", "rankpe", "distpe"])
+    p.add_argument("--obs-vehicles", type=int, default=15, help="observed vehicles N (rows of the observation)")
+    p.add_argument("--d-embed", type=int, default=None, help="rotate_dim (rope, default 4) / d_embed (rankpe, distpe)")
+    p.add_argument("--minibatch", type=int, default=4096)
+    p.add_argument("--epochs", type=int, default=8)
     p.add_argument("--rollout", type=int, default=32, help="T of the PPO iteration measured beside the headline")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-ppo", action="store_true")
@@ -54,10 +64,29 @@ def parse():
     return p.parse_args()
 
 
+def condition_of(args):
+    """(Condition name, d_embed, env overrides) of the command line."""
+    d = args.d_embed
+    if args.condition == "rope":
+        d = 4 if d is None else d
+    elif args.condition in ("rankpe", "distpe") and d is None:
+        d = 16
+    over = {"observation": {"order": "sorted" if args.condition == "sorted" else "shuffled",
+                            "vehicles_count": args.obs_vehicles}}
+    name = {"rope": "SHUFFLED_ROPE", "sorted": "SORTED", "shuffled": "SHUFFLED", "rankpe": "SHUFFLED_RANKPE",
+            "distpe": "SHUFFLED_DISTPE"}[args.condition]
+    return name, d, over
+
+
 def workload_config(args):
-    return {"workload": "highway-v0 shuffled obs + RoPE(rotate_dim 4; d_embed 16 invalid at F=4, SURVEY F4), "
-                        f"hidden_dim {args.hidden}, {args.envs} lock-step envs/GPU, V=51, N=15, F=4, 15 substeps/step",
-            "envs_per_gpu": args.envs, "hidden_dim": args.hidden,
+    _, d, _ = condition_of(args)
+    emb = {"rope": f"shuffled obs + RoPE(rotate_dim {d}; d_embed 16 invalid at F=4, SURVEY F4)", "sorted": "sorted obs",
+           "shuffled": "shuffled obs", "rankpe": f"shuffled obs + RankPE(d_embed {d})",
+           "distpe": f"shuffled obs + DistPE(d_embed {d})"}[args.condition]
+    return {"workload": f"highway-v0 {emb}, hidden_dim {args.hidden}, {args.envs} lock-step envs/GPU, V=51, "
+                        f"N={args.obs_vehicles}, F=4, 15 substeps/step",
+            "envs_per_gpu": args.envs, "hidden_dim": args.hidden, "condition": args.condition, "d_embed": d,
+            "obs_vehicles": args.obs_vehicles, "ppo_minibatch": args.minibatch, "ppo_epochs": args.epochs,
             "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)"}
 
 
@@ -128,46 +157,81 @@ def algorithmic_bytes_per_env_step(V=51, N=15, Fout=4):
 
 
 # ---------------------------------------------------------------------------------------------
+def _cpu_setup(args):
+    """Config, embedding function and policy parameters of the CPU arms (the oracle's restatements)."""
+    import numpy as np
+    import torch
+    import torch.nn as nn
+
+    from highway_rope_ppo_b200.config.base_config import HIGHWAY_CONFIG
+    from oracle import embed as oe
+
+    _, d, over = condition_of(args)
+    cfg = copy.deepcopy(HIGHWAY_CONFIG)
+    cfg["observation"].update(over["observation"])
+    N, F = args.obs_vehicles, 4
+    if args.condition == "rope":
+        inv = oe.rope_inv_freq(d, 100.0)
+
+        def embed(obs):   # vectorised numpy restatement of rope_embed.py:64-74
+            E = obs.shape[0]
+            rel = obs[:, :, :2] - obs[:, :1, :2]
+            dn = np.clip(np.linalg.norm(rel, axis=-1) / 100.0, 0.0, 1.0).astype(np.float32)
+            theta = (2 * np.pi * dn[..., None] * inv[None, None, :]).astype(np.float32)
+            sn, cs = np.sin(theta), np.cos(theta)
+            pair = obs[:, :, :d].reshape(E, N, d // 2, 2)
+            rot = np.stack([pair[..., 0] * cs - pair[..., 1] * sn, pair[..., 0] * sn + pair[..., 1] * cs], axis=-1)
+            return np.concatenate([rot.reshape(E, N, d), obs[:, :, d:]], axis=-1).reshape(E, -1)
+        Fout = F
+    elif args.condition == "distpe":
+        fr = oe.dist_freqs(d, 100.0)
+
+        def embed(obs):   # dist_embed.py:76-96
+            rel = obs[:, :, :2] - obs[:, :1, :2]
+            dn = np.clip(np.linalg.norm(rel, axis=-1) / 100.0, 0.0, 1.0).astype(np.float32)
+            ang = 2 * np.pi * dn[..., None] * fr[None, None, :]
+            return np.concatenate([obs, np.sin(ang), np.cos(ang)], axis=-1).astype(np.float32).reshape(obs.shape[0], -1)
+        Fout = F + d
+    elif args.condition == "rankpe":
+        tag = np.tanh(np.random.default_rng(0).uniform(-0.05, 0.05, (N, d))).astype(np.float32)
+
+        def embed(obs):   # rank_embed.py:45-51 (intended semantics, SURVEY F5)
+            return np.concatenate([obs, np.broadcast_to(tag, (obs.shape[0], N, d))], axis=-1).reshape(obs.shape[0], -1)
+        Fout = F + d
+    else:
+        def embed(obs):
+            return obs.reshape(obs.shape[0], -1)
+        Fout = F
+    S, A, H = N * Fout, 2, args.hidden
+    torch.manual_seed(0)
+    flat = torch.cat([torch.zeros(A)] + [p.detach().reshape(-1) for layer in
+                                         (nn.Linear(S, H), nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, A),
+                                          nn.Linear(H, H), nn.Linear(H, 1)) for p in layer.parameters()])
+    return cfg, embed, flat, S, A, H, N
+
+
 def cpu_policy_env_steps(args, seconds, n_envs, steps=None, warmup=1):
     """Oracle arm: C restatement of highway-v0 (OpenMP over envs, all host cores) + torch CPU MLP policy."""
     import numpy as np
     import torch
 
-    from highway_rope_ppo_b200.config.base_config import HIGHWAY_CONFIG
-    from oracle import embed as oe
     from oracle import highway as oh
     from oracle import ppo_ref
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = copy.deepcopy(HIGHWAY_CONFIG)
-    cfg["observation"]["order"] = "shuffled"
+    cfg, embed, flat, S, A, H, N = _cpu_setup(args)
     vec = oh.OracleVecEnv(cfg, n_envs, seed=42, nthreads=cores)
-    S, A, H = 60, 2, args.hidden
-    torch.manual_seed(0)
-    import torch.nn as nn
-
-    flat = torch.cat([torch.zeros(A)] + [p.detach().reshape(-1) for layer in
-                                         (nn.Linear(S, H), nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, A),
-                                          nn.Linear(H, H), nn.Linear(H, 1)) for p in layer.parameters()])
-    inv = oe.rope_inv_freq(4, 100.0)
-    obs = np.zeros((n_envs, 15, 4), dtype=np.float32)
+    obs = np.zeros((n_envs, N, 4), dtype=np.float32)
 
     def one_step(obs):
-        # RoPE wrapper (vectorised numpy restatement of rope_embed.py:64-74) + policy forward + env step
-        rel = obs[:, :, :2] - obs[:, :1, :2]
-        dn = np.clip(np.linalg.norm(rel, axis=-1) / 100.0, 0.0, 1.0).astype(np.float32)
-        theta = (2 * np.pi * dn[..., None] * inv[None, None, :]).astype(np.float32)
-        s, c = np.sin(theta), np.cos(theta)
-        pair = obs.reshape(n_envs, 15, 2, 2)
-        rot = np.stack([pair[..., 0] * c - pair[..., 1] * s, pair[..., 0] * s + pair[..., 1] * c], axis=-1)
-        x = torch.from_numpy(rot.reshape(n_envs, S).astype(np.float32))
+        # observation wrapper + policy forward + env step
+        x = torch.from_numpy(np.ascontiguousarray(embed(obs), dtype=np.float32))
         with torch.no_grad():
             mean, log_std, value = ppo_ref.forward(flat, x, S, A, H)
             act = torch.tanh(mean + log_std.exp() * torch.randn_like(mean))
         return vec.step(act.numpy())[0]
 
-    t_env = 0.0
     for _ in range(warmup):
         obs = one_step(obs)
     n, t0 = 0, time.perf_counter()
@@ -183,19 +247,65 @@ def cpu_policy_env_steps(args, seconds, n_envs, steps=None, warmup=1):
     return {"value": n * n_envs / el, "steps": n, "envs": n_envs, "seconds": el, "cores": cores}
 
 
+def cpu_ppo_update(args, n_samples, repeats=1):
+    """The reference's PPOAgent.update arithmetic (ppo/agent.py:196-252) on the host cores: oracle/ppo_ref.py, the
+    torch-fp32 autograd restatement that tests/test_oracle_cpu.py pins to fixtures produced by the reference's own
+    agent.  `n_samples` stored transitions, minibatches of args.minibatch, args.epochs epochs (a bounded sample of
+    the GPU arm's update: the cost per sample-pass does not depend on the buffer length).  Returns seconds per
+    sample of the rollout buffer (one update = epochs passes over it)."""
+    import numpy as np
+    import torch
+
+    from oracle import ppo_ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, _, flat, S, A, H, _ = _cpu_setup(args)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n_samples, S, generator=g)
+    z = torch.randn(n_samples, A, generator=g) * 0.5
+    olp = -torch.rand(n_samples, generator=g) - 1.0
+    adv, ret = torch.randn(n_samples, generator=g), torch.rand(n_samples, generator=g)
+    bs = min(args.minibatch, n_samples)
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    step, best = 0, float("inf")
+    for rep in range(repeats + 1):   # the first pass warms the allocator and the thread pool
+        t0 = time.perf_counter()
+        perm = torch.randperm(n_samples, generator=g)
+        for _ in range(args.epochs):
+            for start in range(0, n_samples, bs):
+                idx = perm[start:start + bs]
+                r = ppo_ref.loss_and_grad(flat, x[idx], z[idx], olp[idx], adv[idx], ret[idx], S, A, H)
+                step += 1
+                flat, m, v, _ = ppo_ref.clip_adam(flat, r["grad"], m, v, step)
+        el = time.perf_counter() - t0
+        if rep > 0:
+            best = min(best, el)
+    return {"s_per_sample": best / n_samples, "samples": n_samples, "optimizer_steps": args.epochs * ((n_samples + bs - 1) // bs),
+            "seconds": best, "cores": cores, "state_dim": S, "hidden_dim": H}
+
+
+def cpu_ppo_samples_per_s(args, env_steps_per_s, upd):
+    """PPO samples/s of the CPU arm: one sample costs one policy+env step plus its share of the update."""
+    return 1.0 / (1.0 / env_steps_per_s + upd["s_per_sample"])
+
+
 def run_reference(args):
     """`--impl reference`: the reference path on the host cores.  The simulator the reference calls
-    (highway-env 1.10.1) is a third-party package absent from this image, so this arm times the oracle's
-    C restatement of it (kind "port") with every host thread, plus a torch CPU policy forward."""
+    (highway-env 1.10.1) is a third-party package absent from this image (profiles/r02_highway_env_probe.txt), so
+    this arm times the oracle's C restatement of it (kind "port") with every host thread, plus a torch CPU policy
+    forward; the PPO half is the reference's update arithmetic (oracle/ppo_ref.py, pinned to the reference's agent)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    budget = 150.0  # seconds for the whole --steps/--warmup run
+    budget = 120.0  # seconds for the whole --steps/--warmup run
     probe = cpu_policy_env_steps(args, 2.0, 256, steps=2, warmup=1)
     per_env_step = 1.0 / probe["value"]
     total = max(1, args.steps + args.warmup)
     n_envs = int(min(args.envs, max(64, budget / (total * per_env_step))))
     res = cpu_policy_env_steps(args, 0.0, n_envs, steps=args.steps, warmup=max(1, args.warmup))
+    upd = cpu_ppo_update(args, 2 * args.minibatch)
+    ppo = cpu_ppo_samples_per_s(args, res["value"], upd)
     cfg = workload_config(args)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / res["steps"],
@@ -204,7 +314,14 @@ def run_reference(args):
             "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
                              "sample": f"{res['envs']} envs x {res['steps']} policy steps, oracle C restatement "
                                        "(OpenMP) + torch CPU policy forward"},
-            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "ppo_samples_per_s": {"value": ppo, "unit": "samples/s", "kind": "port", "cores": upd["cores"],
+                                  "update_s_per_sample": upd["s_per_sample"],
+                                  "sample": f"update: {upd['samples']} stored samples, {upd['optimizer_steps']} optimizer steps of "
+                                            f"{min(args.minibatch, upd['samples'])} ({upd['seconds']:.2f} s), torch fp32 autograd "
+                                            f"restatement of ppo/agent.py:196-252 (S={upd['state_dim']}, H={upd['hidden_dim']}); "
+                                            "rollout: the env-steps/s of this line",
+                                  "definition": "1 / (1 / policy-env-steps/s + update seconds per stored sample)"}}
     print(json.dumps(line), flush=True)
 
 

@@ -67,6 +67,7 @@ SIGNATURES: Dict[str, Any] = {
     "hrp_version": (C.c_int, []),
     "hrp_device_count": (C.c_int, []),
     "hrp_env_create": (C.c_int, [C.POINTER(HrpCfg), _vp, _i64, _i32, _u64, _i32, C.POINTER(_vp)]),
+    "hrp_env_create_ex": (C.c_int, [C.POINTER(HrpCfg), _vp, _i64, _i32, _u64, _i32, C.c_uint32, C.POINTER(_vp)]),
     "hrp_env_destroy": (C.c_int, [_vp]),
     "hrp_env_obs_dim": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "hrp_env_num_vehicles": (C.c_int, [_vp]),

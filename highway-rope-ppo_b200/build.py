@@ -19,11 +19,12 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
-# per-file additions.  hrp_env.cu: approximate division / sqrt / transcendental intrinsics and flush-to-zero in the
-# fused step kernel (164 -> 152 us per 4096-env launch); the embedding epilogue's float32 operation order is kept by
-# explicit __f*_rn intrinsics, and the parity tests (tests/test_env_gpu.py, tests/test_embed_gpu.py, 52 k injected
-# env-steps of tools/long_parity.py) hold at unchanged tolerances.  The PPO files stay IEEE.
-EXTRA_FLAGS = {"hrp_env.cu": ["--use_fast_math"]}
+# per-file additions.  hrp_env.cu: approximate fp32 division / sqrt and flush-to-zero in the fused step kernel --
+# NOT --use_fast_math, which would also turn the sinf / cosf / sincosf of the embedding epilogue into SFU
+# approximations that lose their error bound at the 2 pi angles RoPE / DistPE reach.  The epilogue's float32 operation
+# order is kept by explicit __f*_rn intrinsics (exact whatever these flags say); the fp64 validation instantiation is
+# not affected by them.  The PPO files stay IEEE.
+EXTRA_FLAGS = {"hrp_env.cu": ["-ftz=true", "-prec-div=false", "-prec-sqrt=false"]}
 
 
 def _sources():

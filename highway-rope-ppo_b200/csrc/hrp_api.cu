@@ -54,7 +54,22 @@ static int push(T *dst_dev, const std::vector<T> &src)
     HRP_CUDA_OK(cudaMemcpy(dst_dev, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
     return 0;
 }
-
+// a vehicle field of the working type (float, or double for the fp64 validation instantiation) <-> host doubles
+static int pull_real(std::vector<double> &dst, const void *src_dev, size_t n, bool real64)
+{
+    if (real64) return pull(dst, (const double *)src_dev, n);
+    std::vector<float> t;
+    if (pull(t, (const float *)src_dev, n)) return -2;
+    dst.assign(t.begin(), t.end());
+    return 0;
+}
+static int push_real(void *dst_dev, const std::vector<double> &src, bool real64)
+{
+    if (real64) return push((double *)dst_dev, src);
+    std::vector<float> t(src.size());
+    for (size_t i = 0; i < src.size(); ++i) t[i] = (float)src[i];
+    return push((float *)dst_dev, t);
+}
 
 extern "C" {
 
@@ -135,7 +150,14 @@ static int validate_cfg(const hrp_cfg *c, int64_t table_len)
 int hrp_env_create(const hrp_cfg *cfg, const float *embed_table_host, int64_t embed_table_len,
                    int32_t num_envs, uint64_t env_id_base, int32_t device, hrp_env **out)
 {
+    return hrp_env_create_ex(cfg, embed_table_host, embed_table_len, num_envs, env_id_base, device, 0u, out);
+}
+
+int hrp_env_create_ex(const hrp_cfg *cfg, const float *embed_table_host, int64_t embed_table_len,
+                      int32_t num_envs, uint64_t env_id_base, int32_t device, uint32_t flags, hrp_env **out)
+{
     if (!cfg || !out || num_envs < 1) { hrp_set_error("hrp_env_create: bad arguments"); return -1; }
+    if (flags & ~(uint32_t)HRP_ENV_REAL64) { hrp_set_error("hrp_env_create_ex: unknown flags 0x%x", flags); return -1; }
     if (cfg->embed_kind != HRP_EMBED_NONE && !embed_table_host) { hrp_set_error("embedding table missing"); return -1; }
     if (int rc = validate_cfg(cfg, cfg->embed_kind == HRP_EMBED_NONE ? 0 : embed_table_len)) return rc;
     int ndev = hrp_device_count();
@@ -152,11 +174,12 @@ int hrp_env_create(const hrp_cfg *cfg, const float *embed_table_host, int64_t em
     P.frames = cfg->simulation_frequency / cfg->policy_frequency;
     P.ego_mode = cfg->ego_mode; P.autoreset = cfg->autoreset;
     P.normalize_reward = cfg->normalize_reward; P.offroad_terminal = cfg->offroad_terminal;
-    P.dt64 = 1.0 / cfg->simulation_frequency; P.dt = (float)P.dt64;
+    P.real64 = (flags & HRP_ENV_REAL64) ? 1 : 0;
+    P.dt64 = 1.0 / cfg->simulation_frequency;
     P.dtime = 1.0 / cfg->policy_frequency; P.duration = cfg->duration;
-    P.collision_reward = (float)cfg->collision_reward; P.right_lane_reward = (float)cfg->right_lane_reward;
-    P.high_speed_reward = (float)cfg->high_speed_reward;
-    P.rs_lo = (float)cfg->reward_speed_lo; P.rs_hi = (float)cfg->reward_speed_hi;
+    P.collision_reward = cfg->collision_reward; P.right_lane_reward = cfg->right_lane_reward;
+    P.high_speed_reward = cfg->high_speed_reward;
+    P.rs_lo = cfg->reward_speed_lo; P.rs_hi = cfg->reward_speed_hi;
     P.N = cfg->obs_vehicles; P.F = cfg->obs_nfeat;
     P.Fout = (cfg->embed_kind == HRP_EMBED_DIST || cfg->embed_kind == HRP_EMBED_RANK) ? P.F + cfg->embed_dim : P.F;
     for (int f = 0; f < HRP_MAX_FEATURES; ++f) {
@@ -173,7 +196,8 @@ int hrp_env_create(const hrp_cfg *cfg, const float *embed_table_host, int64_t em
     P.env_id_base = env_id_base; P.seed = 0;
 
     size_t n = (size_t)num_envs * HRP_VS, ne = (size_t)num_envs;
-    size_t bytes = n * (2 * sizeof(double) + 7 * sizeof(float) + sizeof(uint32_t)) +
+    const size_t rsz = P.real64 ? sizeof(double) : sizeof(float);
+    size_t bytes = n * (2 * sizeof(double) + 7 * rsz + sizeof(uint32_t)) +
                    ne * (sizeof(double) + 2 * sizeof(uint32_t));
     h->arena_bytes = bytes;
     cudaError_t ce = cudaMalloc(&h->arena, bytes);
@@ -183,13 +207,13 @@ int hrp_env_create(const hrp_cfg *cfg, const float *embed_table_host, int64_t em
     P.x = (double *)p; p += n * sizeof(double);
     P.timer = (double *)p; p += n * sizeof(double);
     P.time = (double *)p; p += ne * sizeof(double);
-    P.y = (float *)p; p += n * sizeof(float);
-    P.heading = (float *)p; p += n * sizeof(float);
-    P.speed = (float *)p; p += n * sizeof(float);
-    P.tspeed = (float *)p; p += n * sizeof(float);
-    P.delta = (float *)p; p += n * sizeof(float);
-    P.impx = (float *)p; p += n * sizeof(float);
-    P.impy = (float *)p; p += n * sizeof(float);
+    P.y = p; p += n * rsz;
+    P.heading = p; p += n * rsz;
+    P.speed = p; p += n * rsz;
+    P.tspeed = p; p += n * rsz;
+    P.delta = p; p += n * rsz;
+    P.impx = p; p += n * rsz;
+    P.impy = p; p += n * rsz;
     P.flags = (uint32_t *)p; p += n * sizeof(uint32_t);
     P.episode = (uint32_t *)p; p += ne * sizeof(uint32_t);
     P.obs_draw = (uint32_t *)p; p += ne * sizeof(uint32_t);
@@ -366,13 +390,13 @@ int hrp_env_get_state(hrp_env *h, hrp_state *d)
     HRP_CUDA_OK(cudaDeviceSynchronize());
     const EnvDev &P = h->P;
     size_t E = P.E, V = P.V, n = E * HRP_VS;
-    std::vector<double> x, timer, time;
-    std::vector<float> y, hd, sp, ts, de, ix, iy;
+    std::vector<double> x, timer, time, y, hd, sp, ts, de, ix, iy;
     std::vector<uint32_t> fl, ep, dr;
-    if (pull(x, P.x, n) || pull(timer, P.timer, n) || pull(time, P.time, E) || pull(y, P.y, n) ||
-        pull(hd, P.heading, n) || pull(sp, P.speed, n) || pull(ts, P.tspeed, n) || pull(de, P.delta, n) ||
-        pull(ix, P.impx, n) || pull(iy, P.impy, n) || pull(fl, P.flags, n) || pull(ep, P.episode, E) ||
-        pull(dr, P.obs_draw, E))
+    const bool r64 = P.real64 != 0;
+    if (pull(x, P.x, n) || pull(timer, P.timer, n) || pull(time, P.time, E) || pull_real(y, P.y, n, r64) ||
+        pull_real(hd, P.heading, n, r64) || pull_real(sp, P.speed, n, r64) || pull_real(ts, P.tspeed, n, r64) ||
+        pull_real(de, P.delta, n, r64) || pull_real(ix, P.impx, n, r64) || pull_real(iy, P.impy, n, r64) ||
+        pull(fl, P.flags, n) || pull(ep, P.episode, E) || pull(dr, P.obs_draw, E))
         return -2;
     for (size_t e = 0; e < E; ++e) {
         for (size_t k = 0; k < V; ++k) {
@@ -412,8 +436,9 @@ int hrp_env_set_state(hrp_env *h, const hrp_state *s)
     const EnvDev &P = h->P;
     size_t E = P.E, V = P.V, n = E * HRP_VS;
     std::vector<double> x(n, 0.0), timer(n, 0.0), time(E, 0.0);
-    std::vector<float> y(n, 0.f), hd(n, 0.f), sp(n, 0.f), ts(n, 0.f), de(n, 0.f), ix(n, 0.f), iy(n, 0.f);
+    std::vector<double> y(n, 0.0), hd(n, 0.0), sp(n, 0.0), ts(n, 0.0), de(n, 0.0), ix(n, 0.0), iy(n, 0.0);
     std::vector<uint32_t> fl(n, 0u);
+    const bool r64 = P.real64 != 0;
     for (size_t e = 0; e < E; ++e) {
         for (size_t k = 0; k < V; ++k) {
             size_t d = e * HRP_VS + k, o = e * V + k;
@@ -422,17 +447,17 @@ int hrp_env_set_state(hrp_env *h, const hrp_state *s)
                 return -1;
             }
             x[d] = s->x[o]; timer[d] = s->timer[o];
-            y[d] = (float)s->y[o]; hd[d] = (float)s->heading[o]; sp[d] = (float)s->speed[o];
-            ts[d] = (float)s->target_speed[o]; de[d] = (float)s->delta[o];
-            ix[d] = (float)s->impact_x[o]; iy[d] = (float)s->impact_y[o];
+            y[d] = s->y[o]; hd[d] = s->heading[o]; sp[d] = s->speed[o];
+            ts[d] = s->target_speed[o]; de[d] = s->delta[o];
+            ix[d] = s->impact_x[o]; iy[d] = s->impact_y[o];
             fl[d] = (uint32_t)s->lane[o] | ((uint32_t)s->target_lane[o] << 8) |
                     ((uint32_t)(s->crashed[o] != 0) << 16) | ((uint32_t)(s->has_impact[o] != 0) << 17);
         }
         time[e] = s->time[e];
     }
-    if (push(P.x, x) || push(P.timer, timer) || push(P.time, time) || push(P.y, y) || push(P.heading, hd) ||
-        push(P.speed, sp) || push(P.tspeed, ts) || push(P.delta, de) || push(P.impx, ix) || push(P.impy, iy) ||
-        push(P.flags, fl))
+    if (push(P.x, x) || push(P.timer, timer) || push(P.time, time) || push_real(P.y, y, r64) ||
+        push_real(P.heading, hd, r64) || push_real(P.speed, sp, r64) || push_real(P.tspeed, ts, r64) ||
+        push_real(P.delta, de, r64) || push_real(P.impx, ix, r64) || push_real(P.impy, iy, r64) || push(P.flags, fl))
         return -2;
     if (s->episode) HRP_CUDA_OK(cudaMemcpy(P.episode, s->episode, E * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (s->obs_draw) HRP_CUDA_OK(cudaMemcpy(P.obs_draw, s->obs_draw, E * sizeof(uint32_t), cudaMemcpyHostToDevice));

@@ -13,26 +13,73 @@
 // repaired by odd-even transposition each frame) and every lane band has a 64-bit occupancy
 // mask in rank order, so "vehicle in front / behind on lane L" is two bit operations.
 //
-// Numerics: x and the IDM lane-change timer are fp64 (ordering and the 1.0 < timer test are
-// decided exactly as the fp64 reference decides them); everything else is fp32.
+// Numerics.  The kernels are templates over the working type R.  R = float is the product: x and the IDM
+// lane-change timer are fp64 (ordering and the 1.0 < timer test are decided exactly as the fp64 reference
+// decides them), everything else is fp32 with approximate division / rsqrt / exp2 / log2.  R = double is the
+// VALIDATION instantiation (hrp_env_create_ex, HRP_ENV_REAL64): the same code with fp64 state and IEEE fp64
+// arithmetic, slow, used by the parity tests to check the kernel's logic -- rank-ordered neighbour search, band
+// masks, list-order commits, collision bookkeeping -- bit-exactly against the fp64 oracle on every step, with no
+// rounding in the way (tests/test_env_gpu.py).
 #include <math.h>
 
 #include "hrp_internal.cuh"
 
 namespace {
 
-constexpr float kPi = 3.14159265358979323846f;
-constexpr float kLaneW = 4.0f;
-constexpr float kInvTwoSqrtAB = 0.12909944487358055f;  // 1 / (2 sqrt(3*5))
-constexpr float kTanBetaMax = 0.86602540378443865f;    // tan(pi/3) / 2
-constexpr float kDiag = 5.385164807134504f;            // sqrt(5^2 + 2^2)
+constexpr double kPiD = 3.14159265358979323846;
 
+// arithmetic of the working type
+template <typename R> struct Ops;
+template <> struct Ops<float> {
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ float rsqrt(float a) { return rsqrtf(a); }
+    static __device__ __forceinline__ float asin(float a) { return asinf(a); }
+    static __device__ __forceinline__ float tan(float a) { return tanf(a); }
+    // r^d for r >= 0 (<= 2 ulp in r; the result goes through exp2 / log2 anyway)
+    static __device__ __forceinline__ float powpos(float r, float d) { return r > 0.f ? exp2f(d * __log2f(r)) : 0.f; }
+    // sin and cos of a heading: traffic headings are a few tenths of a radian, where the Taylor polynomials
+    // (|error| < 3e-10 for |x| <= 0.5) are exact to fp32 rounding; anything larger takes the library path
+    static __device__ __forceinline__ void sincos(float x, float *s, float *c)
+    {
+        if (fabsf(x) <= 0.5f) {
+            float x2 = x * x;
+            float ps = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.f);
+            float pc = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.f);
+            *s = x * ps;
+            *c = pc;
+        } else {
+            sincosf(x, s, c);
+        }
+    }
+    // ContinuousAction.get_action: float32 lmap of the clipped np.float32 action (exact float32 operation order)
+    static __device__ __forceinline__ float lmap_action(float a, float lo, float span)
+    {
+        return __fadd_rn(lo, __fdiv_rn(__fmul_rn(__fsub_rn(a, -1.0f), span), 2.0f));
+    }
+};
+template <> struct Ops<double> {
+    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+    static __device__ __forceinline__ double rsqrt(double a) { return 1.0 / sqrt(a); }
+    static __device__ __forceinline__ double asin(double a) { return ::asin(a); }
+    static __device__ __forceinline__ double tan(double a) { return ::tan(a); }
+    static __device__ __forceinline__ double powpos(double r, double d) { return pow(r, d); }
+    static __device__ __forceinline__ void sincos(double x, double *s, double *c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ double lmap_action(double a, double lo, double span)
+    {
+        // the env's float32 arithmetic, then widened (the oracle does the same)
+        return (double)Ops<float>::lmap_action((float)a, (float)lo, (float)span);
+    }
+};
+
+template <typename R> struct __align__(16) Rec { R xr, v, ch, sh; };  // what a neighbour query reads of a vehicle: one vector load
+
+template <typename R>
 struct __align__(16) WarpS {
     double x[HRP_VS];    // absolute longitudinal position
     double key[HRP_VS];  // scratch: observation sort keys
-    float xr[HRP_VS];    // x - xref, fp32 working copy
-    float y[HRP_VS], v[HRP_VS], ch[HRP_VS], sh[HRP_VS], h[HRP_VS], ts[HRP_VS], delta[HRP_VS];
-    float impx[HRP_VS], impy[HRP_VS];
+    Rec<R> rec[HRP_VS];  // x - xref (working copy in R), speed, cos / sin of the heading
+    R y[HRP_VS], h[HRP_VS], ts[HRP_VS], delta[HRP_VS];
+    R impx[HRP_VS], impy[HRP_VS];
     int impkey[HRP_VS];
     float rowd[HRP_VS];  // scratch: per-row normalised distance of the embedding
     ull band[HRP_MAX_LANES];
@@ -43,34 +90,22 @@ struct __align__(16) WarpS {
     float obs[HRP_MAX_OBS_ROWS * HRP_MAX_FEATURES];
 };
 
+template <typename R>
 struct Veh {  // what the owning lane keeps in registers
     double x, timer;
-    float y, h, v, ts, delta, impx, impy, ch, sh;
-    float acc, tb;  // persistent action: acceleration and tan(beta)
+    R y, h, v, ts, delta, impx, impy, ch, sh;
+    R acc, tb;  // persistent action: acceleration and tan(beta)
     int lane, tlane;
     bool crashed, has_impact;
 };
 
-__device__ __forceinline__ float nzf(float x) { return fabsf(x) > 1e-2f ? x : (x >= 0.f ? 1e-2f : -1e-2f); }
-__device__ __forceinline__ float clipf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-__device__ __forceinline__ float wrap_to_pi(float x)
+template <typename R> __device__ __forceinline__ R nzf(R x) { return fabs(x) > R(1e-2) ? x : (x >= R(0) ? R(1e-2) : R(-1e-2)); }
+template <typename R> __device__ __forceinline__ R clipf(R x, R lo, R hi) { return fmin(fmax(x, lo), hi); }
+template <typename R> __device__ __forceinline__ R wrap_to_pi(R x)
 {
-    if (x >= -kPi && x < kPi) return x;
-    return x - 2.f * kPi * floorf((x + kPi) / (2.f * kPi));
-}
-// sin and cos of a heading: traffic headings are a few tenths of a radian, where the Taylor polynomials
-// (|error| < 3e-10 for |x| <= 0.5) are exact to fp32 rounding; anything larger takes the library path
-__device__ __forceinline__ void sincos_heading(float x, float *s, float *c)
-{
-    if (fabsf(x) <= 0.5f) {
-        float x2 = x * x;
-        float ps = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.f);
-        float pc = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.f);
-        *s = x * ps;
-        *c = pc;
-    } else {
-        sincosf(x, s, c);
-    }
+    const R pi = R(kPiD);
+    if (x >= -pi && x < pi) return x;
+    return x - R(2) * pi * floor((x + pi) / (R(2) * pi));
 }
 // first set bit above / last set bit below rank p of a 64-slot occupancy mask, on the two 32-bit halves (the
 // 64-bit shift / ffs / clz sequences the compiler emits for the one-line versions cost twice as many instructions)
@@ -88,74 +123,63 @@ __device__ __forceinline__ int slot_rear(ull mask, int p)
     const uint32_t mlo = p >= 32 ? lo : (p > 0 ? lo & ((1u << p) - 1u) : 0u);                      // bits 0 .. min(p, 32)-1
     return mhi ? 63 - __clz((int)mhi) : (mlo ? 31 - __clz((int)mlo) : -1);
 }
-__device__ __forceinline__ int closest_lane(float y, int lanes)
+template <typename R> __device__ __forceinline__ int closest_lane(R y, int lanes)
 {
     // argmin_i |y - 4 i| with the first minimum winning a tie (RoadNetwork.get_closest_lane_index):
     // ceil(y / 4 - 1/2), clamped.  y / 4 and the subtraction of 0.5 are exact in binary floating point
     // wherever the result can change the answer.
-    int i = (int)ceilf(y * 0.25f - 0.5f);
+    int i = (int)ceil(y * R(0.25) - R(0.5));
     return max(0, min(lanes - 1, i));
 }
 
 // IDMVehicle.desired_gap: e follows f
-__device__ __forceinline__ float desired_gap(const WarpS &S, int e, int f)
+template <typename R> __device__ __forceinline__ R desired_gap_rec(const Rec<R> &e, const Rec<R> &f)
 {
-    float ve = S.v[e], che = S.ch[e], she = S.sh[e];
-    float dvx = ve * che - S.v[f] * S.ch[f];
-    float dvy = ve * she - S.v[f] * S.sh[f];
-    float dv = dvx * che + dvy * she;
-    return 10.f + ve * 1.5f + ve * dv * kInvTwoSqrtAB;
+    R dvx = e.v * e.ch - f.v * f.ch;
+    R dvy = e.v * e.sh - f.v * f.sh;
+    R dv = dvx * e.ch + dvy * e.sh;
+    return R(10) + e.v * R(1.5) + e.v * dv * R(0.12909944487358055);  // 1 / (2 sqrt(3*5))
 }
 // COMFORT_ACC_MAX * (1 - (max(v,0)/|not_zero(v0)|)^delta); v0 already clipped to [0, 30]
-__device__ __forceinline__ float idm_free(float v, float v0, float delta)
+template <typename R> __device__ __forceinline__ R idm_free(R v, R v0, R delta)
 {
-    float r = __fdividef(fmaxf(v, 0.f), fabsf(nzf(v0)));  // <= 2 ulp; the result goes through exp2/log2 anyway
-    float p = r > 0.f ? exp2f(delta * __log2f(r)) : 0.f;
-    return 3.f * (1.f - p);
+    R r = Ops<R>::div(fmax(v, R(0)), fabs(nzf(v0)));
+    return R(3) * (R(1) - Ops<R>::powpos(r, delta));
 }
-// COMFORT_ACC_MAX * (desired_gap / not_zero(d))^2
-__device__ __forceinline__ float idm_interaction(const WarpS &S, int e, int f)
+// COMFORT_ACC_MAX * (desired_gap / not_zero(d))^2, e follows f
+template <typename R> __device__ __forceinline__ R idm_interaction_rec(const Rec<R> &e, const Rec<R> &f)
 {
-    float d = S.xr[f] - S.xr[e];
-    float g = __fdividef(desired_gap(S, e, f), nzf(d));
-    return 3.f * g * g;
-}
-
-// the same for the calling lane's own vehicle, whose state is in registers
-__device__ __forceinline__ float idm_interaction_own(const WarpS &S, float xr, float ve, float che, float she, int f)
-{
-    float dvx = ve * che - S.v[f] * S.ch[f];
-    float dvy = ve * she - S.v[f] * S.sh[f];
-    float gap = 10.f + ve * 1.5f + ve * (dvx * che + dvy * she) * kInvTwoSqrtAB;
-    float g = __fdividef(gap, nzf(S.xr[f] - xr));
-    return 3.f * g * g;
+    R g = Ops<R>::div(desired_gap_rec(e, f), nzf(f.xr - e.xr));
+    return R(3) * g * g;
 }
 
 // IDMVehicle.mobil for vehicle i and the candidate on `side` (0: lane-1, 1: lane+1).
 // Returns candidate lane + 1, or 0.  The free-road term of self_pred_a - self_a cancels.
-__device__ int mobil_item(const WarpS &S, const EnvDev &P, int i, int side)
+template <typename R> __device__ int mobil_item(const WarpS<R> &S, const EnvDev &P, int i, int side)
 {
     int li = S.lane[i];
     int c = side == 0 ? li - 1 : li + 1;
     if (c < 0 || c >= P.lanes) return 0;
     double xi = S.x[i];
-    if (!(fabsf(S.y[i] - kLaneW * c) <= 2.f * kLaneW && xi >= 0.0 && xi < 10005.0)) return 0;
-    if (fabsf(S.v[i]) < 1.f) return 0;
+    if (!(fabs(S.y[i] - R(4) * c) <= R(8) && xi >= 0.0 && xi < 10005.0)) return 0;
+    const Rec<R> me = S.rec[i];
+    if (fabs(me.v) < R(1)) return 0;
     int p = S.rank[i];
     ull mc = S.band[c];
     int sf = slot_front(mc, p), sr = slot_rear(mc, p);
     if (sr >= 0) {
         int nf = S.order[sr];
         bool ctrl = nf > 0 || P.ego_mode == 1;
-        float v0 = ctrl ? clipf(S.ts[nf], 0.f, 30.f) : 0.f;
-        float a = idm_free(S.v[nf], v0, S.delta[i]) - idm_interaction(S, nf, i);
-        if (a < -2.f) return 0;
+        R v0 = ctrl ? clipf(S.ts[nf], R(0), R(30)) : R(0);
+        const Rec<R> fo = S.rec[nf];
+        R a = idm_free(fo.v, v0, S.delta[i]) - idm_interaction_rec(fo, me);
+        if (a < R(-2)) return 0;
     }
-    float pred = sf >= 0 ? idm_interaction(S, i, S.order[sf]) : 0.f;
+    R pred = sf >= 0 ? idm_interaction_rec(me, S.rec[S.order[sf]]) : R(0);
     int so = slot_front(S.band[li], p);
-    float cur = so >= 0 ? idm_interaction(S, i, S.order[so]) : 0.f;
-    float jerk = cur - pred;
-    return jerk >= 0.2f ? c + 1 : 0;
+    R cur = so >= 0 ? idm_interaction_rec(me, S.rec[S.order[so]]) : R(0);
+    R jerk = cur - pred;
+    return jerk >= R(0.2) ? c + 1 : 0;
 }
 
 // RoadObject.handle_collisions for list-ordered pair (i < j): spherical pre-check, then the
@@ -164,60 +188,62 @@ __device__ int mobil_item(const WarpS &S, const EnvDev &P, int i, int side)
 // same |distance| unless one projected interval contains the other, so each of the 4 distinct
 // normals is evaluated once and both distance variants feed the minimum in the reference order.
 // Returns bit0 = intersecting, bit1 = will_intersect (+ translation).
-__device__ int collide_pair(const WarpS &S, int i, int j, float dt, float &tx, float &ty)
+template <typename R> __device__ int collide_pair(const WarpS<R> &S, int i, int j, R dt, R &tx, R &ty)
 {
-    float dx = S.xr[j] - S.xr[i], dy = S.y[j] - S.y[i];
-    float lim = kDiag + S.v[i] * dt;
-    if (lim < 0.f || dx * dx + dy * dy > lim * lim) return 0;
-    float uax = S.ch[i], uay = S.sh[i], ubx = S.ch[j], uby = S.sh[j];
-    float cax = S.xr[i], cay = S.y[i], cbx = S.xr[j], cby = S.y[j];
-    float rdx = (S.v[i] * uax - S.v[j] * ubx) * dt, rdy = (S.v[i] * uay - S.v[j] * uby) * dt;
+    const Rec<R> a = S.rec[i], b = S.rec[j];
+    const R cay = S.y[i], cby = S.y[j];
+    R dx = b.xr - a.xr, dy = cby - cay;
+    R lim = R(5.385164807134504) + a.v * dt;  // sqrt(5^2 + 2^2) + v dt
+    if (lim < R(0) || dx * dx + dy * dy > lim * lim) return 0;
+    R uax = a.ch, uay = a.sh, ubx = b.ch, uby = b.sh;
+    R cax = a.xr, cbx = b.xr;
+    R rdx = (a.v * uax - b.v * ubx) * dt, rdy = (a.v * uay - b.v * uby) * dt;
     {
         // cheap exit for the common near miss (vehicles side by side on adjacent lanes): if a's lateral
         // axis separates the rectangles now AND after the displacement, both flags end up false whatever
         // the other axes say, which is the reference's "no contact" result
-        float nx = -uay, ny = uax;
-        float pa = cax * nx + cay * ny, pb = cbx * nx + cby * ny;
-        float rb = 2.5f * fabsf(ubx * nx + uby * ny) + fabsf(-uby * nx + ubx * ny);
-        float gap = fabsf(pa - pb) - (1.f + rb);
-        if (gap > 0.f && gap - fabsf(nx * rdx + ny * rdy) > 0.f) return 0;
+        R nx = -uay, ny = uax;
+        R pa = cax * nx + cay * ny, pb = cbx * nx + cby * ny;
+        R rb = R(2.5) * fabs(ubx * nx + uby * ny) + fabs(-uby * nx + ubx * ny);
+        R gap = fabs(pa - pb) - (R(1) + rb);
+        if (gap > R(0) && gap - fabs(nx * rdx + ny * rdy) > R(0)) return 0;
     }
     bool inter = true, will = true;
-    float mind = INFINITY, ax = 0.f, ay = 0.f;
-    float dneg[2], nnx[2], nny[2], ddn[2];
+    R mind = R(INFINITY), ax = R(0), ay = R(0);
+    R dneg[2], nnx[2], nny[2], ddn[2];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         // reference edge order: -u_a, +w_a, (+u_a, -w_a), -u_b, +w_b, (+u_b, -w_b)
-        float nx, ny;
+        R nx, ny;
         if (k == 0) { nx = -uax; ny = -uay; }
         else if (k == 1) { nx = -uay; ny = uax; }
         else if (k == 2) { nx = -ubx; ny = -uby; }
         else { nx = -uby; ny = ubx; }
-        float pa = cax * nx + cay * ny, pb = cbx * nx + cby * ny;
-        float ra = 2.5f * fabsf(uax * nx + uay * ny) + fabsf(-uay * nx + uax * ny);
-        float rb = 2.5f * fabsf(ubx * nx + uby * ny) + fabsf(-uby * nx + ubx * ny);
-        float min_a = pa - ra, max_a = pa + ra, min_b = pb - rb, max_b = pb + rb;
-        float sd = min_a < min_b ? min_b - max_a : min_a - max_b;
-        if (sd > 0.f) inter = false;
-        float vp = nx * rdx + ny * rdy;
-        if (vp < 0.f) min_a += vp; else max_a += vp;
-        float d1 = min_b - max_a, d2 = min_a - max_b;
-        float dist = min_a < min_b ? d1 : d2;
-        if (dist > 0.f) will = false;
+        R pa = cax * nx + cay * ny, pb = cbx * nx + cby * ny;
+        R ra = R(2.5) * fabs(uax * nx + uay * ny) + fabs(-uay * nx + uax * ny);
+        R rb = R(2.5) * fabs(ubx * nx + uby * ny) + fabs(-uby * nx + ubx * ny);
+        R min_a = pa - ra, max_a = pa + ra, min_b = pb - rb, max_b = pb + rb;
+        R sd = min_a < min_b ? min_b - max_a : min_a - max_b;
+        if (sd > R(0)) inter = false;
+        R vp = nx * rdx + ny * rdy;
+        if (vp < R(0)) min_a += vp; else max_a += vp;
+        R d1 = min_b - max_a, d2 = min_a - max_b;
+        R dist = min_a < min_b ? d1 : d2;
+        if (dist > R(0)) will = false;
         if (!inter && !will) return 0;
-        float dd = (cax - cbx) * nx + (cay - cby) * ny;
-        if (fabsf(dist) < mind) {
-            mind = fabsf(dist);
-            if (dd > 0.f) { ax = nx; ay = ny; } else { ax = -nx; ay = -ny; }
+        R dd = (cax - cbx) * nx + (cay - cby) * ny;
+        if (fabs(dist) < mind) {
+            mind = fabs(dist);
+            if (dd > R(0)) { ax = nx; ay = ny; } else { ax = -nx; ay = -ny; }
         }
         dneg[k & 1] = max_a > max_b ? d2 : d1;  // the same edge seen through the opposite normal
         nnx[k & 1] = nx; nny[k & 1] = ny; ddn[k & 1] = dd;
         if (k & 1) {
 #pragma unroll
             for (int t = 0; t < 2; ++t)
-                if (fabsf(dneg[t]) < mind) {
-                    mind = fabsf(dneg[t]);
-                    if (ddn[t] < 0.f) { ax = -nnx[t]; ay = -nny[t]; } else { ax = nnx[t]; ay = nny[t]; }
+                if (fabs(dneg[t]) < mind) {
+                    mind = fabs(dneg[t]);
+                    if (ddn[t] < R(0)) { ax = -nnx[t]; ay = -nny[t]; } else { ax = nnx[t]; ay = nny[t]; }
                 }
         }
     }
@@ -227,7 +253,7 @@ __device__ int collide_pair(const WarpS &S, int i, int j, float dt, float &tx, f
 
 // ---------------------------------------------------------------------------------------
 // rank bookkeeping
-__device__ void rank_full(WarpS &S, int V, int lane)
+template <typename R> __device__ void rank_full(WarpS<R> &S, int V, int lane)
 {
     // rank = number of vehicles ordered before (x, list index); O(V) per vehicle, once per launch
 #pragma unroll
@@ -246,16 +272,17 @@ __device__ void rank_full(WarpS &S, int V, int lane)
     }
     __syncwarp();
 }
-__device__ void rank_repair(WarpS &S, int V, int lane)
+template <typename R> __device__ void rank_repair(WarpS<R> &S, int V, int lane)
 {
-    // fp32 pre-check on the ego-relative copies: an inversion (true gap <= 0) shows up as an fp32 gap below the
-    // margin (|xr| < 4096 m: two roundings <= 5e-4 m), so "every gap >= 4e-3" proves the order without fp64 loads
+    // pre-check on the ego-relative working copies: an inversion (true gap <= 0) shows up as a working-copy gap
+    // below the margin (fp32, |xr| < 4096 m: two roundings <= 5e-4 m), so "every gap >= 4e-3" proves the order
+    // without fp64 loads
     {
         bool sus = false;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             int s = lane + 32 * q;
-            if (s + 1 < V) sus |= S.xr[S.order[s + 1]] - S.xr[S.order[s]] < 4e-3f;
+            if (s + 1 < V) sus |= S.rec[S.order[s + 1]].xr - S.rec[S.order[s]].xr < R(4e-3);
         }
         if (!__any_sync(HRP_FULL, sus)) return;   // ranks are unchanged, nothing to rewrite
     }
@@ -264,7 +291,12 @@ __device__ void rank_repair(WarpS &S, int V, int lane)
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             int s = lane + 32 * q;
-            if (s + 1 < V) inv |= S.x[S.order[s]] > S.x[S.order[s + 1]];
+            if (s + 1 < V) {
+                // odd-even transposition keeps (x, list index) order: equal x never swaps back and forth
+                int a = S.order[s], b = S.order[s + 1];
+                double xa = S.x[a], xb = S.x[b];
+                inv |= xa > xb || (xa == xb && a > b);
+            }
         }
         if (!__any_sync(HRP_FULL, inv)) break;
 #pragma unroll
@@ -272,7 +304,8 @@ __device__ void rank_repair(WarpS &S, int V, int lane)
             int s = 2 * lane + par;
             if (s + 1 < V) {
                 int a = S.order[s], b = S.order[s + 1];
-                if (S.x[a] > S.x[b]) { S.order[s] = (unsigned char)b; S.order[s + 1] = (unsigned char)a; }
+                double xa = S.x[a], xb = S.x[b];
+                if (xa > xb || (xa == xb && a > b)) { S.order[s] = (unsigned char)b; S.order[s + 1] = (unsigned char)a; }
             }
             __syncwarp();
         }
@@ -287,52 +320,60 @@ __device__ void rank_repair(WarpS &S, int V, int lane)
 
 // ---------------------------------------------------------------------------------------
 // state movement HBM <-> registers/shared
-__device__ void publish(WarpS &S, const Veh &u, int k, double xref)
+template <typename R> __device__ __forceinline__ void publish(WarpS<R> &S, const Veh<R> &u, int k, double xref)
 {
-    S.x[k] = u.x; S.xr[k] = (float)(u.x - xref);
-    S.y[k] = u.y; S.v[k] = u.v; S.ch[k] = u.ch; S.sh[k] = u.sh; S.h[k] = u.h;
+    S.x[k] = u.x;
+    Rec<R> r;
+    r.xr = (R)(u.x - xref); r.v = u.v; r.ch = u.ch; r.sh = u.sh;
+    S.rec[k] = r;
+    S.y[k] = u.y; S.h[k] = u.h;
     S.ts[k] = u.ts; S.delta[k] = u.delta;
     S.lane[k] = (unsigned char)u.lane; S.tl_old[k] = S.tl_new[k] = (unsigned char)u.tlane;
     S.impkey[k] = -1; S.crash[k] = 0;
 }
-__device__ void load_env(const EnvDev &P, WarpS &S, Veh (&u)[2], int e, int lane, double &xref)
+template <typename R>
+__device__ void load_env(const EnvDev &P, WarpS<R> &S, Veh<R> (&u)[2], int e, int lane, double &xref)
 {
     size_t base = (size_t)e * HRP_VS;
     xref = P.x[base];  // ego x at the start of the step
+    const R *py = (const R *)P.y, *ph = (const R *)P.heading, *pv = (const R *)P.speed, *pts = (const R *)P.tspeed,
+            *pde = (const R *)P.delta, *pix = (const R *)P.impx, *piy = (const R *)P.impy;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         int k = lane + 32 * q;
         if (k < P.V) {
-            Veh &w = u[q];
+            Veh<R> &w = u[q];
             w.x = P.x[base + k]; w.timer = P.timer[base + k];
-            w.y = P.y[base + k]; w.h = P.heading[base + k]; w.v = P.speed[base + k];
-            w.ts = P.tspeed[base + k]; w.delta = P.delta[base + k];
-            w.impx = P.impx[base + k]; w.impy = P.impy[base + k];
+            w.y = py[base + k]; w.h = ph[base + k]; w.v = pv[base + k];
+            w.ts = pts[base + k]; w.delta = pde[base + k];
+            w.impx = pix[base + k]; w.impy = piy[base + k];
             uint32_t f = P.flags[base + k];
             w.lane = f & 0xff; w.tlane = (f >> 8) & 0xff;
             w.crashed = (f >> 16) & 1; w.has_impact = (f >> 17) & 1;
-            sincos_heading(w.h, &w.sh, &w.ch);
-            w.acc = 0.f; w.tb = 0.f;
+            Ops<R>::sincos(w.h, &w.sh, &w.ch);
+            w.acc = R(0); w.tb = R(0);
             publish(S, w, k, xref);
         } else {
-            u[q] = Veh{};  // empty slot: the frame code runs on it with selects, its results are never stored
-            u[q].ch = 1.f;
+            u[q] = Veh<R>{};  // empty slot: the frame code runs on it with selects, its results are never stored
+            u[q].ch = R(1);
         }
     }
     __syncwarp();
 }
-__device__ void store_env(const EnvDev &P, const Veh (&u)[2], int e, int lane)
+template <typename R> __device__ void store_env(const EnvDev &P, const Veh<R> (&u)[2], int e, int lane)
 {
     size_t base = (size_t)e * HRP_VS;
+    R *py = (R *)P.y, *ph = (R *)P.heading, *pv = (R *)P.speed, *pts = (R *)P.tspeed, *pde = (R *)P.delta,
+      *pix = (R *)P.impx, *piy = (R *)P.impy;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         int k = lane + 32 * q;
         if (k < P.V) {
-            const Veh &w = u[q];
+            const Veh<R> &w = u[q];
             P.x[base + k] = w.x; P.timer[base + k] = w.timer;
-            P.y[base + k] = w.y; P.heading[base + k] = w.h; P.speed[base + k] = w.v;
-            P.tspeed[base + k] = w.ts; P.delta[base + k] = w.delta;
-            P.impx[base + k] = w.impx; P.impy[base + k] = w.impy;
+            py[base + k] = w.y; ph[base + k] = w.h; pv[base + k] = w.v;
+            pts[base + k] = w.ts; pde[base + k] = w.delta;
+            pix[base + k] = w.impx; piy[base + k] = w.impy;
             P.flags[base + k] = (uint32_t)w.lane | ((uint32_t)w.tlane << 8) |
                                 ((uint32_t)w.crashed << 16) | ((uint32_t)w.has_impact << 17);
         }
@@ -342,12 +383,13 @@ __device__ void store_env(const EnvDev &P, const Veh (&u)[2], int e, int lane)
 // ---------------------------------------------------------------------------------------
 // HighwayEnv._create_vehicles / Vehicle.create_random with Philox draws.
 __device__ __forceinline__ float u01f(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
-__device__ int speed_to_index(float speed)
+template <typename R> __device__ int speed_to_index(R speed)
 {
-    float x = (speed - 20.f) / 10.f;
-    return (int)clipf(rintf(x * 2.f), 0.f, 2.f);
+    R x = (speed - R(20)) / R(10);
+    return (int)clipf(rint(x * R(2)), R(0), R(2));
 }
-__device__ void spawn_env(const EnvDev &P, WarpS &S, Veh (&u)[2], int e, int lane, uint32_t episode,
+template <typename R>
+__device__ void spawn_env(const EnvDev &P, WarpS<R> &S, Veh<R> (&u)[2], int e, int lane, uint32_t episode,
                           double &xref)
 {
     ull gid = P.env_id_base + (ull)e;
@@ -355,7 +397,7 @@ __device__ void spawn_env(const EnvDev &P, WarpS &S, Veh (&u)[2], int e, int lan
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         int k = lane + 32 * q;
-        Veh &w = u[q];
+        Veh<R> &w = u[q];
         if (k < P.V) {
             uint32_t r[4];
             hrp_philox((uint32_t)k, episode, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)P.seed,
@@ -372,12 +414,12 @@ __device__ void spawn_env(const EnvDev &P, WarpS &S, Veh (&u)[2], int e, int lan
             double offset = spacing * (12.0 + speed) * P.gap_factor;
             double inc = offset * (0.9 + (1.1 - 0.9) * (double)u01f(r[2]));
             val[q] = k == 0 ? 3.0 * offset + inc : inc;
-            w.y = kLaneW * ln; w.h = 0.f; w.v = (float)speed; w.ts = (float)speed;
+            w.y = R(4) * ln; w.h = R(0); w.v = (R)speed; w.ts = (R)speed;
             w.lane = ln; w.tlane = ln;
-            w.delta = k > 0 ? 3.5f + u01f(r[3]) : 4.0f;
-            w.impx = w.impy = 0.f; w.crashed = false; w.has_impact = false;
-            w.ch = 1.f; w.sh = 0.f; w.acc = 0.f; w.tb = 0.f;
-            if (k == 0 && P.ego_mode == 1) w.ts = 20.f + 5.f * speed_to_index(w.v);
+            w.delta = k > 0 ? (R)(3.5 + (4.5 - 3.5) * (double)u01f(r[3])) : R(4);
+            w.impx = w.impy = R(0); w.crashed = false; w.has_impact = false;
+            w.ch = R(1); w.sh = R(0); w.acc = R(0); w.tb = R(0);
+            if (k == 0 && P.ego_mode == 1) w.ts = R(20) + R(5) * speed_to_index(w.v);
         }
     }
     // x_k = x_{k-1} + inc_k: inclusive scan over list order (fp64)
@@ -396,7 +438,7 @@ __device__ void spawn_env(const EnvDev &P, WarpS &S, Veh (&u)[2], int e, int lan
     for (int q = 0; q < 2; ++q) {
         int k = lane + 32 * q;
         if (k < P.V) {
-            Veh &w = u[q];
+            Veh<R> &w = u[q];
             w.x = val[q];
             double t = (w.x + (double)w.y) * 3.14159265358979323846;
             w.timer = k > 0 ? t - floor(t) : 0.0;  // python: (x + y) * pi % 1.0, operands >= 0
@@ -408,21 +450,21 @@ __device__ void spawn_env(const EnvDev &P, WarpS &S, Veh (&u)[2], int e, int lan
 
 // ---------------------------------------------------------------------------------------
 // KinematicObservation.observe + embedding wrapper, warp-cooperative.
-__device__ double feature_value(const WarpS &S, int code, int k)
+template <typename R> __device__ double feature_value(const WarpS<R> &S, int code, int k)
 {
     switch (code) {
     case HRP_F_PRESENCE: return 1.0;
     case HRP_F_X: return S.x[k];
     case HRP_F_Y: return (double)S.y[k];
-    case HRP_F_VX: return (double)S.v[k] * (double)S.ch[k];
-    case HRP_F_VY: return (double)S.v[k] * (double)S.sh[k];
+    case HRP_F_VX: return (double)S.rec[k].v * (double)S.rec[k].ch;
+    case HRP_F_VY: return (double)S.rec[k].v * (double)S.rec[k].sh;
     case HRP_F_HEADING: return (double)S.h[k];
-    case HRP_F_COS_H: return (double)S.ch[k];
-    case HRP_F_SIN_H: return (double)S.sh[k];
+    case HRP_F_COS_H: return (double)S.rec[k].ch;
+    case HRP_F_SIN_H: return (double)S.rec[k].sh;
     }
     return 0.0;
 }
-__device__ void write_row(const EnvDev &P, WarpS &S, int row, int k)
+template <typename R> __device__ void write_row(const EnvDev &P, WarpS<R> &S, int row, int k)
 {
     S.rowveh[row] = k;
     for (int f = 0; f < P.F; ++f) {
@@ -437,7 +479,10 @@ __device__ void write_row(const EnvDev &P, WarpS &S, int row, int k)
     }
 }
 
-// the embedding epilogue on an [N, F] table in shared memory -> out[N, Fout] in global memory
+// the embedding epilogue on an [N, F] table in shared memory -> out[N, Fout] in global memory.  float32 with the
+// reference's operation order (numpy float32 arithmetic): explicit round-to-nearest intrinsics, IEEE division and
+// square root, and the full-range sinf / cosf / sincosf of the CUDA math library (this file is NOT compiled with
+// --use_fast_math: the angles reach 2 pi, outside the range where the SFU approximations hold their error bound).
 __device__ void embed_store(int kind, int edim, int use_euclid, int ego_idx, float max_dist,
                             const float *__restrict__ table, const float *tab, float *rowd, int N,
                             int F, int Fout, int lane, float *__restrict__ out,
@@ -490,7 +535,8 @@ __device__ void embed_store(int kind, int edim, int use_euclid, int ego_idx, flo
     }
 }
 
-__device__ void observe_env(const EnvDev &P, WarpS &S, int e, int lane, float *__restrict__ obs,
+template <typename R>
+__device__ void observe_env(const EnvDev &P, WarpS<R> &S, int e, int lane, float *__restrict__ obs,
                             const int32_t *__restrict__ perm_in, int32_t *__restrict__ row_vehicle,
                             uint32_t draw)
 {
@@ -499,7 +545,7 @@ __device__ void observe_env(const EnvDev &P, WarpS &S, int e, int lane, float *_
     for (int i = lane; i < N; i += 32) S.rowveh[i] = -1;
     // Road.close_objects_to: list order, ||p - p_ego|| < 200 and -10 < dx unless see_behind
     double ex = S.x[0];
-    float ey = S.y[0];
+    R ey = S.y[0];
     bool close[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -575,17 +621,19 @@ __device__ void observe_env(const EnvDev &P, WarpS &S, int e, int lane, float *_
 
 // ---------------------------------------------------------------------------------------
 // One simulation frame: Road.act() then Road.step(dt)
-__device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane, double xref)
+template <typename R>
+__device__ void simulate_frame(const EnvDev &P, WarpS<R> &S, Veh<R> (&u)[2], int lane, double xref)
 {
     const int V = P.V;
-    const float dt = P.dt;
+    const R dt = (R)P.dt64;
     const bool ego_ctrl = P.ego_mode == 1;
+    const R kPi = R(kPiD);
 
     // ---- band occupancy masks in rank order: |y - 4L| <= 3 (on_lane with margin 1)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         int s = lane + 32 * q;
-        float yy = 0.f;
+        R yy = R(0);
         bool inx = false;
         if (s < V) {
             int veh = S.order[s];
@@ -594,7 +642,7 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
             inx = xx >= -5.0 && xx < 10005.0;
         }
         for (int L = 0; L < P.lanes; ++L) {
-            unsigned b = __ballot_sync(HRP_FULL, inx && fabsf(yy - kLaneW * L) <= 3.f);
+            unsigned b = __ballot_sync(HRP_FULL, inx && fabs(yy - R(4) * L) <= R(3));
             if (lane == 0) reinterpret_cast<unsigned *>(&S.band[L])[q] = b;
         }
     }
@@ -605,7 +653,7 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         int k = lane + 32 * q;
-        Veh &w = u[q];
+        Veh<R> &w = u[q];
         bool idm = k > 0 && k < V && !w.crashed;
         mid[q] = idm && w.lane != w.tlane;
         fire[q] = idm && w.lane == w.tlane && 1.0 < w.timer;
@@ -641,7 +689,7 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
         int k = __ffsll((long long)mm) - 1;
         mm &= mm - 1;
         int T = S.tl_new[k];
-        float xk = S.xr[k];
+        const Rec<R> rk = S.rec[k];
         bool hit = false;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -649,8 +697,10 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
             if (j < V && j != k && (j > 0 || ego_ctrl) && S.lane[j] != T) {
                 int tj = j < k ? S.tl_new[j] : S.tl_old[j];
                 if (tj == T) {
-                    float d = S.xr[j] - xk;
-                    if (d > 0.f && d < desired_gap(S, k, j)) hit = true;
+                    const Rec<R> rj = S.rec[j];
+                    // the reference decides "ahead" on the fp64 positions: x_j - x_k > 0
+                    R d = rj.xr - rk.xr;
+                    if (S.x[j] - S.x[k] > 0.0 && d < desired_gap_rec(rk, rj)) hit = true;
                 }
             }
         }
@@ -668,32 +718,34 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const int k = lane + 32 * q;
-        Veh &w = u[q];
+        Veh<R> &w = u[q];
         const bool valid = k < V;
         const bool act = valid && !w.crashed && (k > 0 || ego_ctrl);  // ContinuousAction ego keeps its action dict
         // ControlledVehicle.steering_control(target_lane) -> tan(beta) without leaving the tangent
-        const float lat = w.y - kLaneW * w.tlane;
-        const float lsc = -(1.f / 0.6f) * lat;
-        const float rv = __fdividef(1.f, nzf(w.v));
+        const R lat = w.y - R(4) * w.tlane;
+        const R lsc = -(R(1) / R(0.6)) * lat;
+        const R rv = Ops<R>::div(R(1), nzf(w.v));
         // clip(asin(clip(c, -1, 1)), -pi/4, pi/4) == asin(clip(c, -sin(pi/4), sin(pi/4))): asin is monotone
-        const float hc = asinf(clipf(lsc * rv, -0.70710678118654752f, 0.70710678118654752f));
-        const float href = clipf(hc, -kPi / 4.f, kPi / 4.f);
-        const float hrc = 5.f * wrap_to_pi(href - w.h);
-        const float ss = clipf(2.5f * rv * hrc, -1.f, 1.f);  // sin(slip)
-        const float tslip = ss * rsqrtf(fmaxf(1.f - ss * ss, 0.f));  // tan(slip); +-inf at |ss| == 1
-        const float tb_new = clipf(tslip, -kTanBetaMax, kTanBetaMax);  // tan(beta) = clip(2 tan slip, +-tan(pi/3)) / 2
+        const R hc = Ops<R>::asin(clipf(lsc * rv, R(-0.70710678118654752), R(0.70710678118654752)));
+        const R href = clipf(hc, -kPi / R(4), kPi / R(4));
+        const R hrc = R(5) * wrap_to_pi(href - w.h);
+        const R ss = clipf(R(2.5) * rv * hrc, R(-1), R(1));  // sin(slip)
+        const R tslip = ss * Ops<R>::rsqrt(fmax(R(1) - ss * ss, R(0)));  // tan(slip); +-inf at |ss| == 1
+        // tan(beta) = clip(2 tan slip, +-tan(pi/3)) / 2
+        const R tb_new = clipf(tslip, R(-0.86602540378443865), R(0.86602540378443865));
         // IDMVehicle.acceleration against the front vehicle of the own lane and of the target lane
         const int p = valid ? (int)S.rank[k] : 0;
-        const float a0 = idm_free(w.v, clipf(w.ts, 0.f, 30.f), w.delta);
-        const float xr_own = (float)(w.x - xref);
+        const R a0 = idm_free(w.v, clipf(w.ts, R(0), R(30)), w.delta);
+        Rec<R> me;
+        me.xr = (R)(w.x - xref); me.v = w.v; me.ch = w.ch; me.sh = w.sh;
         const int sf = slot_front(S.band[w.lane], p), st = slot_front(S.band[w.tlane], p);
-        const float i1 = idm_interaction_own(S, xr_own, w.v, w.ch, w.sh, S.order[max(sf, 0)]);
-        const float i2 = idm_interaction_own(S, xr_own, w.v, w.ch, w.sh, S.order[max(st, 0)]);
-        float acc = a0 - (sf >= 0 ? i1 : 0.f);
-        const float acc_t = a0 - (st >= 0 ? i2 : 0.f);
-        acc = w.lane != w.tlane ? fminf(acc, acc_t) : acc;
-        const float acc_idm = clipf(acc, -6.f, 6.f);
-        const float acc_mdp = (1.f / 0.6f) * (w.ts - w.v);  // MDPVehicle: speed_control
+        const R i1 = idm_interaction_rec(me, S.rec[S.order[max(sf, 0)]]);
+        const R i2 = idm_interaction_rec(me, S.rec[S.order[max(st, 0)]]);
+        R acc = a0 - (sf >= 0 ? i1 : R(0));
+        const R acc_t = a0 - (st >= 0 ? i2 : R(0));
+        acc = w.lane != w.tlane ? fmin(acc, acc_t) : acc;
+        const R acc_idm = clipf(acc, R(-6), R(6));
+        const R acc_mdp = (R(1) / R(0.6)) * (w.ts - w.v);  // MDPVehicle: speed_control
         w.tb = act ? tb_new : w.tb;
         w.acc = act ? (k > 0 ? acc_idm : acc_mdp) : w.acc;
     }
@@ -703,27 +755,30 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const int k = lane + 32 * q;
-        Veh &w = u[q];
+        Veh<R> &w = u[q];
         w.timer += k > 0 ? P.dt64 : 0.0;
-        w.tb = w.crashed ? 0.f : w.tb;
-        w.acc = w.crashed ? -1.0f * w.v : w.acc;
-        w.acc = w.v > 40.f ? fminf(w.acc, 40.f - w.v) : (w.v < -40.f ? fmaxf(w.acc, -40.f - w.v) : w.acc);
-        const float cb = rsqrtf(1.f + w.tb * w.tb), sb = w.tb * cb;
-        const float c = w.ch * cb - w.sh * sb, s = w.sh * cb + w.ch * sb;
+        w.tb = w.crashed ? R(0) : w.tb;
+        w.acc = w.crashed ? R(-1) * w.v : w.acc;
+        w.acc = w.v > R(40) ? fmin(w.acc, R(40) - w.v) : (w.v < R(-40) ? fmax(w.acc, R(-40) - w.v) : w.acc);
+        const R cb = Ops<R>::rsqrt(R(1) + w.tb * w.tb), sb = w.tb * cb;
+        const R c = w.ch * cb - w.sh * sb, s = w.sh * cb + w.ch * sb;
         w.x += (double)(w.v * c * dt);
         w.y += w.v * s * dt;
         w.x += w.has_impact ? (double)w.impx : 0.0;   // pending impact of the previous frame's collision
-        w.y += w.has_impact ? w.impy : 0.f;
+        w.y += w.has_impact ? w.impy : R(0);
         w.crashed = w.crashed || w.has_impact;
         w.has_impact = false;
-        w.impx = w.impy = 0.f;
-        w.h += w.v * sb * 0.4f * dt;   // / (LENGTH / 2); the product form saves the IEEE division
+        w.impx = w.impy = R(0);
+        w.h += w.v * sb * R(0.4) * dt;   // / (LENGTH / 2); the product form saves the IEEE division
         w.v += w.acc * dt;
         w.lane = closest_lane(w.y, P.lanes);
-        sincos_heading(w.h, &w.sh, &w.ch);
+        Ops<R>::sincos(w.h, &w.sh, &w.ch);
         if (k < V) {
-            S.x[k] = w.x; S.xr[k] = (float)(w.x - xref);
-            S.y[k] = w.y; S.v[k] = w.v; S.ch[k] = w.ch; S.sh[k] = w.sh;
+            S.x[k] = w.x;
+            Rec<R> r;
+            r.xr = (R)(w.x - xref); r.v = w.v; r.ch = w.ch; r.sh = w.sh;
+            S.rec[k] = r;
+            S.y[k] = w.y;
             S.lane[k] = (unsigned char)w.lane;
             S.tl_old[k] = S.tl_new[k] = (unsigned char)w.tlane;
         }
@@ -733,11 +788,11 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
 
     // ---- collisions: pairs within the pre-check radius are neighbours in rank order
     int a[2];
-    float xa[2];
+    R xa[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         a[q] = lane + 32 * q < V ? (int)S.order[lane + 32 * q] : -1;
-        xa[q] = S.xr[max(a[q], 0)];
+        xa[q] = S.rec[max(a[q], 0)].xr;
     }
     for (int off = 1; off < V; ++off) {
         int b[2];
@@ -749,14 +804,14 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
             b[q] = 0;
             if (cand[q]) {
                 b[q] = S.order[s2];
-                cand[q] = S.xr[b[q]] - xa[q] <= 8.8f;  // >= sqrt(29) + max speed * dt
+                cand[q] = S.rec[b[q]].xr - xa[q] <= R(8.8);  // >= sqrt(29) + max speed * dt
             }
         }
         if (!__any_sync(HRP_FULL, cand[0] || cand[1])) break;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             int ev = 0, ei = 0, ej = 0;
-            float tx = 0.f, ty = 0.f;
+            R tx = R(0), ty = R(0);
             if (cand[q]) {
                 ei = min(a[q], b[q]); ej = max(a[q], b[q]);
                 ev = collide_pair(S, ei, ej, dt, tx, ty);
@@ -767,12 +822,12 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
                 evm &= evm - 1;
                 int bv = __shfl_sync(HRP_FULL, ev, src);
                 int bi = __shfl_sync(HRP_FULL, ei, src), bj = __shfl_sync(HRP_FULL, ej, src);
-                float btx = __shfl_sync(HRP_FULL, tx, src), bty = __shfl_sync(HRP_FULL, ty, src);
+                R btx = __shfl_sync(HRP_FULL, tx, src), bty = __shfl_sync(HRP_FULL, ty, src);
                 if (lane == 0) {
                     if (bv & 2) {
                         int ki = 64 + bj, kj = bi;  // pairs (i, *) come after every pair (*, i)
-                        if (ki > S.impkey[bi]) { S.impkey[bi] = ki; S.impx[bi] = 0.5f * btx; S.impy[bi] = 0.5f * bty; }
-                        if (kj > S.impkey[bj]) { S.impkey[bj] = kj; S.impx[bj] = -0.5f * btx; S.impy[bj] = -0.5f * bty; }
+                        if (ki > S.impkey[bi]) { S.impkey[bi] = ki; S.impx[bi] = R(0.5) * btx; S.impy[bi] = R(0.5) * bty; }
+                        if (kj > S.impkey[bj]) { S.impkey[bj] = kj; S.impx[bj] = R(-0.5) * btx; S.impy[bj] = R(-0.5) * bty; }
                     }
                     if (bv & 1) { S.crash[bi] = 1; S.crash[bj] = 1; }
                 }
@@ -784,7 +839,7 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
     for (int q = 0; q < 2; ++q) {
         int k = lane + 32 * q;
         if (k >= V) continue;
-        Veh &w = u[q];
+        Veh<R> &w = u[q];
         if (S.crash[k]) { w.crashed = true; S.crash[k] = 0; }
         if (S.impkey[k] >= 0) {
             w.has_impact = true; w.impx = S.impx[k]; w.impy = S.impy[k];
@@ -795,47 +850,50 @@ __device__ void simulate_frame(const EnvDev &P, WarpS &S, Veh (&u)[2], int lane,
 }
 
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * HRP_WARPS_PER_CTA, HRP_STEP_CTAS_PER_SM)
-hrp_step_kernel(const EnvDev P, const float *__restrict__ actions, float *__restrict__ obs,
-                float *__restrict__ reward, uint8_t *__restrict__ term, uint8_t *__restrict__ trunc,
-                const int32_t *__restrict__ perm, int32_t *__restrict__ row_vehicle)
+template <typename R, int WARPS>
+__device__ __forceinline__ void step_body(const EnvDev &P, const float *__restrict__ actions, float *__restrict__ obs,
+                                          float *__restrict__ reward, uint8_t *__restrict__ term,
+                                          uint8_t *__restrict__ trunc, const int32_t *__restrict__ perm,
+                                          int32_t *__restrict__ row_vehicle)
 {
-    __shared__ WarpS smem[HRP_WARPS_PER_CTA];
+    __shared__ WarpS<R> smem[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * HRP_WARPS_PER_CTA + warp;
+    const int e = blockIdx.x * WARPS + warp;
+    // Launched with programmatic stream serialisation.  The successor in the stream (the policy's first GEMM, or the
+    // next step) may be scheduled as CTAs of this grid retire; it waits for this grid to complete before it reads
+    // anything.  This kernel reads the simulator state, which its predecessor may have written (a step after a step,
+    // a step after a reset), so it waits for the predecessor before the first load: only the index arithmetic above
+    // overlaps the predecessor's tail.
+    hrp_pdl_release();
+    hrp_pdl_wait();
     if (e >= P.E) return;
-    WarpS &S = smem[warp];
-    Veh u[2];
+    WarpS<R> &S = smem[warp];
+    Veh<R> u[2];
     double xref;
     load_env(P, S, u, e, lane, xref);
     rank_full(S, P.V, lane);
 
-    // Launched with programmatic stream serialisation: everything above needs the simulator state only, so it may
-    // overlap the tail of the policy kernel that is still producing the actions.  No hrp_pdl_release() in this
-    // kernel: a following step would read the state before this one has stored it.
-    hrp_pdl_wait();
     // ActionType.act on the first frame
     float a0 = actions[2 * e], a1 = actions[2 * e + 1];
     if (lane == 0) {
         if (P.ego_mode == 0) {
             // ContinuousAction.get_action: float32 lmap of the clipped np.float32 action
-            a0 = clipf(a0, -1.f, 1.f); a1 = clipf(a1, -1.f, 1.f);
-            u[0].acc = __fadd_rn(-5.0f, __fdiv_rn(__fmul_rn(__fsub_rn(a0, -1.0f), 10.0f), 2.0f));
-            float steer = __fadd_rn(-0.78539816339744831f,
-                                    __fdiv_rn(__fmul_rn(__fsub_rn(a1, -1.0f), 1.5707963267948966f), 2.0f));
-            u[0].tb = 0.5f * tanf(steer);
+            a0 = fminf(fmaxf(a0, -1.f), 1.f); a1 = fminf(fmaxf(a1, -1.f), 1.f);
+            u[0].acc = Ops<R>::lmap_action((R)a0, R(-5), R(10));
+            R steer = Ops<R>::lmap_action((R)a1, (R)(-0.78539816339744831f), (R)1.5707963267948966f);
+            u[0].tb = R(0.5) * Ops<R>::tan(steer);
         } else {
             // MDPVehicle.act(action) / ControlledVehicle.act(action)
             int act = (int)a0;
-            Veh &w = u[0];
+            Veh<R> &w = u[0];
             if (act == 3 || act == 4) {
                 int idx = speed_to_index(w.v) + (act == 3 ? 1 : -1);
                 idx = max(0, min(2, idx));
-                w.ts = 20.f + 5.f * idx;
+                w.ts = R(20) + R(5) * idx;
                 S.ts[0] = w.ts;
             } else if (act == 0 || act == 2) {
                 int t = max(0, min(P.lanes - 1, w.tlane + (act == 2 ? 1 : -1)));
-                if (fabsf(w.y - kLaneW * t) <= 2.f * kLaneW && w.x >= 0.0 && w.x < 10005.0) w.tlane = t;
+                if (fabs(w.y - R(4) * t) <= R(8) && w.x >= 0.0 && w.x < 10005.0) w.tlane = t;
                 S.tl_old[0] = S.tl_new[0] = (unsigned char)w.tlane;
             }
         }
@@ -848,21 +906,21 @@ hrp_step_kernel(const EnvDev P, const float *__restrict__ actions, float *__rest
     int done = 0;
     double tnow = 0.0;
     if (lane == 0) {
-        const Veh &w = u[0];
+        const Veh<R> &w = u[0];
         int rl = P.ego_mode == 1 ? w.tlane : w.lane;
-        float fs = w.v * w.ch;
-        float scaled = (fs - P.rs_lo) / (P.rs_hi - P.rs_lo);
-        bool on_road = fabsf(w.y - kLaneW * w.lane) <= 2.f && w.x >= -5.0 && w.x < 10005.0;
-        float r = P.collision_reward * (w.crashed ? 1.f : 0.f) +
-                  P.right_lane_reward * ((float)rl / (float)max(P.lanes - 1, 1)) +
-                  P.high_speed_reward * clipf(scaled, 0.f, 1.f);
+        R fs = w.v * w.ch;
+        R scaled = (fs - (R)P.rs_lo) / ((R)P.rs_hi - (R)P.rs_lo);
+        bool on_road = fabs(w.y - R(4) * w.lane) <= R(2) && w.x >= -5.0 && w.x < 10005.0;
+        R r = (R)P.collision_reward * (w.crashed ? R(1) : R(0)) +
+              (R)P.right_lane_reward * ((R)rl / (R)max(P.lanes - 1, 1)) +
+              (R)P.high_speed_reward * clipf(scaled, R(0), R(1));
         if (P.normalize_reward)
-            r = (r - P.collision_reward) / ((P.high_speed_reward + P.right_lane_reward) - P.collision_reward);
-        r *= on_road ? 1.f : 0.f;
+            r = (r - (R)P.collision_reward) / (((R)P.high_speed_reward + (R)P.right_lane_reward) - (R)P.collision_reward);
+        r *= on_road ? R(1) : R(0);
         tnow = P.time[e] + P.dtime;
         bool te = w.crashed || (P.offroad_terminal && !on_road);
         bool tr = tnow >= P.duration;
-        reward[e] = r; term[e] = te; trunc[e] = tr;
+        reward[e] = (float)r; term[e] = te; trunc[e] = tr;
         done = (te || tr) ? 1 : 0;
     }
     done = __shfl_sync(HRP_FULL, done, 0);
@@ -882,16 +940,33 @@ hrp_step_kernel(const EnvDev P, const float *__restrict__ actions, float *__rest
     store_env(P, u, e, lane);
 }
 
-__global__ void __launch_bounds__(32 * HRP_WARPS_PER_CTA)
+__global__ void __launch_bounds__(32 * HRP_WARPS_PER_CTA, HRP_STEP_CTAS_PER_SM)
+hrp_step_kernel(const EnvDev P, const float *__restrict__ actions, float *__restrict__ obs,
+                float *__restrict__ reward, uint8_t *__restrict__ term, uint8_t *__restrict__ trunc,
+                const int32_t *__restrict__ perm, int32_t *__restrict__ row_vehicle)
+{
+    step_body<float, HRP_WARPS_PER_CTA>(P, actions, obs, reward, term, trunc, perm, row_vehicle);
+}
+// validation instantiation: fp64 state and arithmetic (two envs per CTA: the per-warp block is twice as large)
+__global__ void __launch_bounds__(32 * HRP_WARPS_PER_CTA_F64)
+hrp_step_kernel_f64(const EnvDev P, const float *__restrict__ actions, float *__restrict__ obs,
+                    float *__restrict__ reward, uint8_t *__restrict__ term, uint8_t *__restrict__ trunc,
+                    const int32_t *__restrict__ perm, int32_t *__restrict__ row_vehicle)
+{
+    step_body<double, HRP_WARPS_PER_CTA_F64>(P, actions, obs, reward, term, trunc, perm, row_vehicle);
+}
+
+template <typename R, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
 hrp_observe_kernel(const EnvDev P, float *__restrict__ obs, const int32_t *__restrict__ perm,
                    int32_t *__restrict__ row_vehicle)
 {
-    __shared__ WarpS smem[HRP_WARPS_PER_CTA];
+    __shared__ WarpS<R> smem[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * HRP_WARPS_PER_CTA + warp;
+    const int e = blockIdx.x * WARPS + warp;
     if (e >= P.E) return;
-    WarpS &S = smem[warp];
-    Veh u[2];
+    WarpS<R> &S = smem[warp];
+    Veh<R> u[2];
     double xref;
     load_env(P, S, u, e, lane, xref);
     uint32_t draw = P.obs_draw[e];
@@ -899,16 +974,17 @@ hrp_observe_kernel(const EnvDev P, float *__restrict__ obs, const int32_t *__res
     if (lane == 0) P.obs_draw[e] = draw + 1;
 }
 
-__global__ void __launch_bounds__(32 * HRP_WARPS_PER_CTA)
+template <typename R, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
 hrp_reset_kernel(const EnvDev P, const uint8_t *__restrict__ mask, float *__restrict__ obs)
 {
-    __shared__ WarpS smem[HRP_WARPS_PER_CTA];
+    __shared__ WarpS<R> smem[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * HRP_WARPS_PER_CTA + warp;
+    const int e = blockIdx.x * WARPS + warp;
     if (e >= P.E) return;
     if (mask && !mask[e]) return;
-    WarpS &S = smem[warp];
-    Veh u[2];
+    WarpS<R> &S = smem[warp];
+    Veh<R> u[2];
     double xref;
     spawn_env(P, S, u, e, lane, 0u, xref);
     uint32_t draw = P.obs_draw[e];
@@ -939,6 +1015,12 @@ hrp_embed_kernel(int kind, int edim, int use_euclid, int ego_idx, float max_dist
 int hrp_launch_step(const EnvDev &P, const float *actions, float *obs, float *reward, uint8_t *term,
                     uint8_t *trunc, const int32_t *perm, int32_t *row_vehicle, cudaStream_t s)
 {
+    if (P.real64) {
+        int grid = (P.E + HRP_WARPS_PER_CTA_F64 - 1) / HRP_WARPS_PER_CTA_F64;
+        HRP_CUDA_OK(hrp_launch_pdl(hrp_step_kernel_f64, dim3(grid), dim3(32 * HRP_WARPS_PER_CTA_F64), 0, s, P, actions, obs,
+                                   reward, term, trunc, perm, row_vehicle));
+        return 0;
+    }
     int grid = (P.E + HRP_WARPS_PER_CTA - 1) / HRP_WARPS_PER_CTA;
     HRP_CUDA_OK(hrp_launch_pdl(hrp_step_kernel, dim3(grid), dim3(32 * HRP_WARPS_PER_CTA), 0, s, P, actions, obs, reward, term,
                                trunc, perm, row_vehicle));
@@ -947,15 +1029,25 @@ int hrp_launch_step(const EnvDev &P, const float *actions, float *obs, float *re
 int hrp_launch_observe(const EnvDev &P, float *obs, const int32_t *perm, int32_t *row_vehicle,
                        cudaStream_t s)
 {
-    int grid = (P.E + HRP_WARPS_PER_CTA - 1) / HRP_WARPS_PER_CTA;
-    hrp_observe_kernel<<<grid, 32 * HRP_WARPS_PER_CTA, 0, s>>>(P, obs, perm, row_vehicle);
+    if (P.real64) {
+        int grid = (P.E + HRP_WARPS_PER_CTA_F64 - 1) / HRP_WARPS_PER_CTA_F64;
+        hrp_observe_kernel<double, HRP_WARPS_PER_CTA_F64><<<grid, 32 * HRP_WARPS_PER_CTA_F64, 0, s>>>(P, obs, perm, row_vehicle);
+    } else {
+        int grid = (P.E + HRP_WARPS_PER_CTA - 1) / HRP_WARPS_PER_CTA;
+        hrp_observe_kernel<float, HRP_WARPS_PER_CTA><<<grid, 32 * HRP_WARPS_PER_CTA, 0, s>>>(P, obs, perm, row_vehicle);
+    }
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }
 int hrp_launch_reset(const EnvDev &P, const uint8_t *mask, float *obs, cudaStream_t s)
 {
-    int grid = (P.E + HRP_WARPS_PER_CTA - 1) / HRP_WARPS_PER_CTA;
-    hrp_reset_kernel<<<grid, 32 * HRP_WARPS_PER_CTA, 0, s>>>(P, mask, obs);
+    if (P.real64) {
+        int grid = (P.E + HRP_WARPS_PER_CTA_F64 - 1) / HRP_WARPS_PER_CTA_F64;
+        hrp_reset_kernel<double, HRP_WARPS_PER_CTA_F64><<<grid, 32 * HRP_WARPS_PER_CTA_F64, 0, s>>>(P, mask, obs);
+    } else {
+        int grid = (P.E + HRP_WARPS_PER_CTA - 1) / HRP_WARPS_PER_CTA;
+        hrp_reset_kernel<float, HRP_WARPS_PER_CTA><<<grid, 32 * HRP_WARPS_PER_CTA, 0, s>>>(P, mask, obs);
+    }
     HRP_CUDA_OK(cudaGetLastError());
     return 0;
 }

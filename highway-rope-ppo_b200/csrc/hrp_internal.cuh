@@ -8,6 +8,7 @@
 #define HRP_VS 64            // vehicle slots per env in every SoA array (two per lane)
 #define HRP_WARPS_PER_CTA 4  // envs per CTA (one warp each)
 #define HRP_STEP_CTAS_PER_SM 7  // 28 envs per SM: 4096 envs fill 148 SMs in one wave (<= 72 registers)
+#define HRP_WARPS_PER_CTA_F64 2  // the fp64 validation instantiation: its per-warp shared-memory block is twice as large
 #define HRP_FULL 0xffffffffu
 
 typedef unsigned long long ull;
@@ -16,11 +17,11 @@ typedef unsigned long long ull;
 struct EnvDev {
     int E, V, lanes, frames;
     int ego_mode, autoreset, normalize_reward, offroad_terminal;
-    float dt;
+    int real64;      // 0: product arithmetic (fp32 + fp64 x / timer); 1: fp64 validation instantiation (fp64 state arrays)
     double dt64;     // 1/simulation_frequency (IDM timer is advanced in fp64)
     double dtime;    // 1/policy_frequency
     double duration;
-    float collision_reward, right_lane_reward, high_speed_reward, rs_lo, rs_hi;
+    double collision_reward, right_lane_reward, high_speed_reward, rs_lo, rs_hi;
     // Kinematics observation
     int N, F, Fout;
     int feat[HRP_MAX_FEATURES];
@@ -37,7 +38,7 @@ struct EnvDev {
     ull env_id_base, seed;
     // SoA simulator state in HBM: [E][HRP_VS] per vehicle field, [E] per env field
     double *x, *timer, *time;
-    float *y, *heading, *speed, *tspeed, *delta, *impx, *impy;
+    void *y, *heading, *speed, *tspeed, *delta, *impx, *impy;   // float arrays, double arrays when real64
     uint32_t *flags;  // lane | target_lane<<8 | crashed<<16 | has_impact<<17
     uint32_t *episode, *obs_draw;
 };

@@ -135,7 +135,8 @@ class HighwayVecEnv:
     """
 
     def __init__(self, cfg: Dict[str, Any], num_envs: int, device: Any = "cuda", embed: Optional[EmbedSpec] = None,
-                 autoreset: bool = True, env_id_base: int = 0, seed: int = 0):
+                 autoreset: bool = True, env_id_base: int = 0, seed: int = 0, real64: bool = False):
+        # real64: the fp64 VALIDATION instantiation of the kernels (HRP_ENV_REAL64; parity tests only, slow)
         lib = _lib.load()
         _lib.require_device()
         self.device = torch.device(device)
@@ -151,8 +152,10 @@ class HighwayVecEnv:
         table = self.embed.table
         tptr = None if table is None else table.ctypes.data
         h = C.c_void_p()
-        _lib.check(lib.hrp_env_create(C.byref(self.cfg), tptr, 0 if table is None else table.size, self.num_envs,
-                                      int(env_id_base), self.dev_index, C.byref(h)), "hrp_env_create")
+        self.real64 = bool(real64)
+        _lib.check(lib.hrp_env_create_ex(C.byref(self.cfg), tptr, 0 if table is None else table.size, self.num_envs,
+                                         int(env_id_base), self.dev_index, 1 if self.real64 else 0, C.byref(h)),
+                   "hrp_env_create_ex")
         self._h = h
         self._lib = lib
         self.V = int(lib.hrp_env_num_vehicles(h))

@@ -106,6 +106,13 @@ int hrp_device_count(void);
  *      a shard owns envs [env_id_base, env_id_base+num_envs). */
 int hrp_env_create(const hrp_cfg *cfg, const float *embed_table_host, int64_t embed_table_len,
                    int32_t num_envs, uint64_t env_id_base, int32_t device, hrp_env **out);
+/* the same with flags.  HRP_ENV_REAL64 selects the VALIDATION instantiation of the simulator kernels: fp64 state
+ * arrays and IEEE fp64 arithmetic throughout (the product keeps x and the lane-change timer in fp64 and everything
+ * else in fp32).  Same code path, same entry points, several times slower; the parity tests use it to compare the
+ * kernel's logic bit-exactly with the fp64 oracle, and the fp32 kernel with the fp64 kernel. */
+#define HRP_ENV_REAL64 1u
+int hrp_env_create_ex(const hrp_cfg *cfg, const float *embed_table_host, int64_t embed_table_len,
+                      int32_t num_envs, uint64_t env_id_base, int32_t device, uint32_t flags, hrp_env **out);
 int hrp_env_destroy(hrp_env *env);
 int hrp_env_obs_dim(const hrp_env *env, int32_t *rows, int32_t *cols);
 int hrp_env_num_vehicles(const hrp_env *env);

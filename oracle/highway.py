@@ -87,6 +87,12 @@ def lib():
                                     C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]
         L.hw_last_min_margin.restype = C.c_double
         L.hw_last_min_margin.argtypes = [C.c_void_p]
+        L.hw_record_margin.argtypes = [C.c_void_p, C.c_double]
+        L.hw_marginal_keys.restype = C.c_int32
+        L.hw_marginal_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.hw_force_decisions.restype = C.c_int32
+        L.hw_force_decisions.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.hw_slow_vehicles.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -204,6 +210,47 @@ class OracleEnv:
 
     def min_margin(self) -> float:
         return float(lib().hw_last_min_margin(self._h))
+
+    # -- either-branch parity aid (highway_oracle.h) ------------------------------------------------
+    def record_margin(self, below: float) -> None:
+        """List the decisions of the following steps / observations decided by less than ``below``."""
+        lib().hw_record_margin(self._h, float(below))
+
+    def marginal(self, with_margins: bool = False):
+        """Keys of the decisions listed since the last ``step`` began (``decode_key`` names them)."""
+        keys = np.zeros(1024, dtype=np.uint64)
+        marg = np.zeros(1024, dtype=np.float64)
+        n = min(int(lib().hw_marginal_keys(self._h, keys.ctypes.data, marg.ctypes.data, 1024)), 1024)
+        out = [int(k) for k in keys[:n]]
+        return (out, [float(m) for m in marg[:n]]) if with_margins else out
+
+    def force(self, keys=()) -> None:
+        """Decide the listed keys the other way from now on (empty: back to the fp64 outcome)."""
+        k = np.asarray(list(keys), dtype=np.uint64)
+        if lib().hw_force_decisions(self._h, k.ctypes.data if len(k) else None, len(k)) != 0:
+            raise ValueError("oracle: too many forced decisions")
+
+    def slow_vehicles(self) -> np.ndarray:
+        out = np.zeros(HW_MAX_VEHICLES, dtype=np.uint8)
+        lib().hw_slow_vehicles(self._h, out.ctypes.data)
+        return out[: self.V].astype(bool)
+
+
+DECISION_KINDS = ("?", "closest_lane", "on_band", "on_road", "reachable", "x_order", "not_zero_sign", "mobil_safe",
+                  "mobil_gain", "abort_ahead", "abort_gap", "speed_below_1", "speed_index", "speed_limit", "precheck",
+                  "sat_now", "sat_will", "sat_axis", "obs_close", "obs_behind", "obs_order")
+
+
+def key_fields(key: int):
+    """(kind, frame, a, b, c) of a decision key."""
+    return (key >> 32) & 0xff, (key >> 24) & 0xff, (key >> 16) & 0xff, (key >> 8) & 0xff, key & 0xff
+
+
+def decode_key(key: int) -> str:
+    kind, frame, a, b, c = (key >> 32) & 0xff, (key >> 24) & 0xff, (key >> 16) & 0xff, (key >> 8) & 0xff, key & 0xff
+    fr = {250: "pre", 251: "end", 252: "obs"}.get(frame, str(frame))
+    name = DECISION_KINDS[kind] if kind < len(DECISION_KINDS) else str(kind)
+    return f"{name}[frame {fr}: {a},{b},{c}]"
 
 
 def shuffle_perm(seed: int, env_id: int, draw: int, n: int) -> np.ndarray:

@@ -43,6 +43,13 @@ static const double LANE_CHANGE_MIN_ACC_GAIN = 0.2;
 static const double LANE_CHANGE_MAX_BRAKING_IMPOSED = 2.0;
 static const double LANE_CHANGE_DELAY = 1.0;
 
+/* decision kinds (first component of a key) */
+enum {
+    HW_D_LANE = 1, HW_D_ON_BAND, HW_D_ON_ROAD, HW_D_REACH, HW_D_ORDER, HW_D_NZ_SIGN, HW_D_MOBIL_SAFE, HW_D_MOBIL_GAIN,
+    HW_D_ABORT_AHEAD, HW_D_ABORT_GAP, HW_D_SPEED1, HW_D_SPEED_INDEX, HW_D_VMAX, HW_D_PRECHECK, HW_D_SAT_NOW,
+    HW_D_SAT_WILL, HW_D_SAT_AXIS, HW_D_OBS_CLOSE, HW_D_OBS_BEHIND, HW_D_OBS_ORDER
+};
+
 typedef struct {
     double x, y, heading, speed;
     double target_speed, delta, timer;
@@ -62,13 +69,57 @@ struct hw_env {
     uint32_t episode;
     uint32_t obs_draw;
     double min_margin;
+    /* test aid: keyed decisions (see dec()) */
+    int frame;                 /* simulation frame of the running policy step, HW_FRAME_* outside the frame loop */
+    double record_below;       /* decisions decided by less than this are listed in marg[] */
+    uint64_t marg[HW_MAX_MARGINAL];
+    double marg_val[HW_MAX_MARGINAL];
+    int nmarg;
+    uint64_t forced[HW_MAX_FORCED];
+    int nforced;
+    uint8_t slow[HW_MAX_VEHICLES]; /* controlled vehicle acted below 0.5 m/s during the last step */
 };
 
-/* ---- decision-margin bookkeeping (test aid only) ------------------------- */
-static inline void mg(hw_env *e, double m)
+/* ---- decision bookkeeping (test aid only) --------------------------------
+ * Every discrete decision of a step -- a comparison whose outcome selects a branch, an argmin, a
+ * sort order -- goes through dec(): `margin` is the signed distance of the decided quantity from
+ * its threshold and `res` the outcome the fp64 arithmetic gives.  A decision is named by a key
+ * (kind, frame, a, b, c) that does not depend on control flow, so that the SAME logical decision
+ * evaluated several times (e.g. "vehicle j is on the band of lane L in frame f", asked once per
+ * neighbour query) is one key.  dec() records the smallest |margin| of the step, lists the keys
+ * decided by less than record_below, and returns the outcome INVERTED for keys in forced[]: the
+ * either-branch parity check of tests/test_env_gpu.py re-runs a step with marginal decisions
+ * forced the other way and requires the fp32 kernel to equal one of the outcomes. */
+enum { HW_FRAME_PRE = 250, HW_FRAME_END = 251, HW_FRAME_OBS = 252 };
+static inline uint64_t dkey(const hw_env *e, int kind, int a, int b, int c)
 {
-    m = fabs(m);
-    if (m < e->min_margin) e->min_margin = m;
+    return ((uint64_t)(kind & 0xff) << 32) | ((uint64_t)(e->frame & 0xff) << 24) | ((uint64_t)(a & 0xff) << 16) |
+           ((uint64_t)(b & 0xff) << 8) | (uint64_t)(c & 0xff);
+}
+static int dec(hw_env *e, int kind, int a, int b, int c, double margin, int res)
+{
+    margin = fabs(margin);
+    if (margin < e->min_margin) e->min_margin = margin;
+    if (margin < e->record_below || e->nforced) {
+        uint64_t key = dkey(e, kind, a, b, c);
+        if (margin < e->record_below) {
+            int q = 0;
+            while (q < e->nmarg && e->marg[q] != key) ++q;
+            if (q == e->nmarg && e->nmarg < HW_MAX_MARGINAL) { e->marg[q] = key; e->marg_val[q] = margin; e->nmarg++; }
+        }
+        for (int q = 0; q < e->nforced; ++q)
+            if (e->forced[q] == key) return !res;
+    }
+    return res;
+}
+/* strict order of two vehicles along the road, one key per unordered pair */
+static int x_before(hw_env *e, int a, int b)
+{
+    int lo = a < b ? a : b, hi = a < b ? b : a;
+    int lt = e->v[lo].x < e->v[hi].x, gt = e->v[lo].x > e->v[hi].x; /* equal: neither is strictly before */
+    int c = dec(e, HW_D_ORDER, lo, hi, 0, e->v[lo].x - e->v[hi].x, lt);
+    if (c != lt) gt = !c; /* forced: strictly the other way */
+    return a < b ? c : gt;
 }
 
 /* ---- utils.py ------------------------------------------------------------ */
@@ -112,48 +163,49 @@ void hw_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32
 static inline double u01(uint32_t r) { return (double)(r >> 8) * (1.0 / 16777216.0); }
 
 /* ---- road geometry: 4 straight lanes, lane i centred on y = 4 i (A.3) ---- */
-static int closest_lane(hw_env *e, double x, double y, double heading)
+static int closest_lane(hw_env *e, int who, double x, double y, double heading)
 {
     /* RoadNetwork.get_closest_lane_index with distance_with_heading */
     double best = 0, second = INFINITY;
-    int arg = -1;
+    int arg = -1, arg2 = -1;
     double ang = fabs(wrap_to_pi(heading - 0.0));
     for (int i = 0; i < e->cfg.lanes_count; ++i) {
         double r = y - LANE_WIDTH * i;
         double d = fabs(r) + fmax(x - ROAD_LENGTH, 0) + fmax(0 - x, 0) + 1.0 * ang;
-        if (arg < 0 || d < best) { second = (arg < 0) ? INFINITY : best; best = d; arg = i; }
-        else if (d < second) second = d;
+        if (arg < 0 || d < best) { second = (arg < 0) ? INFINITY : best; arg2 = arg; best = d; arg = i; }
+        else if (d < second) { second = d; arg2 = i; }
     }
-    if (e->cfg.lanes_count > 1) mg(e, second - best);
+    /* forced: the runner-up lane */
+    if (e->cfg.lanes_count > 1 && dec(e, HW_D_LANE, who, 0, 0, second - best, 0)) return arg2;
     return arg;
 }
-static int on_lane(hw_env *e, double x, double y, int lane, double margin)
+static int on_lane(hw_env *e, int who, double x, double y, int lane, double margin)
 {
     double lat = y - LANE_WIDTH * lane;
-    mg(e, fabs(lat) - (LANE_WIDTH / 2 + margin));
-    return fabs(lat) <= LANE_WIDTH / 2 + margin && -VEH_LENGTH <= x && x < ROAD_LENGTH + VEH_LENGTH;
+    int in = dec(e, margin > 0 ? HW_D_ON_BAND : HW_D_ON_ROAD, who, lane, 0, fabs(lat) - (LANE_WIDTH / 2 + margin),
+                 fabs(lat) <= LANE_WIDTH / 2 + margin);
+    return in && -VEH_LENGTH <= x && x < ROAD_LENGTH + VEH_LENGTH;
 }
-static int is_reachable_from(hw_env *e, double x, double y, int lane)
+static int is_reachable_from(hw_env *e, int who, double x, double y, int lane)
 {
     double lat = y - LANE_WIDTH * lane;
-    mg(e, fabs(lat) - 2 * LANE_WIDTH);
-    return fabs(lat) <= 2 * LANE_WIDTH && 0 <= x && x < ROAD_LENGTH + VEH_LENGTH;
+    int in = dec(e, HW_D_REACH, who, lane, 0, fabs(lat) - 2 * LANE_WIDTH, fabs(lat) <= 2 * LANE_WIDTH);
+    return in && 0 <= x && x < ROAD_LENGTH + VEH_LENGTH;
 }
 
 /* ---- Road.neighbour_vehicles (A.6) --------------------------------------- */
 static void neighbours(hw_env *e, int self, int lane, int *front, int *rear)
 {
-    double s = e->v[self].x;
-    double s_front = 0, s_rear = 0;
+    /* upstream: s <= s_v and (s_front is None or s_v <= s_front) -> front; s_v < s and (s_rear is None or
+     * s_v > s_rear) -> rear.  Stated through x_before() so that every pairwise order is one keyed decision. */
     int vf = -1, vr = -1;
     for (int j = 0; j < e->V; ++j) {
         if (j == self) continue;
         const veh_t *o = &e->v[j];
-        if (!on_lane(e, o->x, o->y, lane, 1.0)) continue;
-        double sv = o->x;
-        mg(e, sv - s);
-        if (s <= sv && (vf < 0 || sv <= s_front)) { s_front = sv; vf = j; }
-        if (sv < s && (vr < 0 || sv > s_rear)) { s_rear = sv; vr = j; }
+        if (!on_lane(e, j, o->x, o->y, lane, 1.0)) continue;
+        int j_behind = x_before(e, j, self);                           /* s_v < s */
+        if (!j_behind && (vf < 0 || !x_before(e, vf, j))) vf = j;       /* s <= s_v and s_v <= s_front */
+        if (j_behind && (vr < 0 || x_before(e, vr, j))) vr = j;         /* s_v < s and s_v > s_rear */
     }
     *front = vf; *rear = vr;
 }
@@ -185,16 +237,19 @@ static double idm_acceleration(const veh_t *self, const veh_t *ego, const veh_t 
 /* ---- ControlledVehicle.steering_control / speed_control (A.5) ------------ */
 static double steering_control(hw_env *e, const veh_t *v, int target_lane)
 {
-    mg(e, fabs(v->speed) - 1e-2); mg(e, v->speed); /* not_zero(speed): eps switch and sign */
+    int who = (int)(v - e->v);
+    /* not_zero(speed): the eps switch is continuous, the sign at |speed| < eps is a decision */
+    double nzs = not_zero(v->speed);
+    if (fabs(v->speed) <= 1e-2 && dec(e, HW_D_NZ_SIGN, who, 0, 0, v->speed, 0)) nzs = -nzs;
     /* test aid: below 0.5 m/s the two divisions by the speed amplify a 1e-6 rounding of y by > 1e3
-     * (the controller is ill-conditioned as v -> 0): such steps are reported as marginal */
-    if (fabs(v->speed) < 0.5) mg(e, 0.0);
+     * (the controller is ill-conditioned as v -> 0): the vehicle is flagged, the tests widen its tolerances */
+    if (fabs(v->speed) < 0.5) e->slow[who] = 1;
     double lat = v->y - LANE_WIDTH * target_lane;
     double lateral_speed_command = -(1.0 / TAU_LATERAL) * lat;
-    double heading_command = asin(clipd(lateral_speed_command / not_zero(v->speed), -1, 1));
+    double heading_command = asin(clipd(lateral_speed_command / nzs, -1, 1));
     double heading_ref = 0.0 + clipd(heading_command, -PI / 4, PI / 4);
     double heading_rate_command = (1.0 / TAU_HEADING) * wrap_to_pi(heading_ref - v->heading);
-    double slip = asin(clipd(VEH_LENGTH / 2 / not_zero(v->speed) * heading_rate_command, -1, 1));
+    double slip = asin(clipd(VEH_LENGTH / 2 / nzs * heading_rate_command, -1, 1));
     double steer = atan(2 * tan(slip));
     return clipd(steer, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
 }
@@ -213,8 +268,9 @@ static int mobil(hw_env *e, int self, int cand)
     const veh_t *new_foll = nf >= 0 ? &e->v[nf] : NULL;
     double new_following_a = idm_acceleration(me, new_foll, new_prec);
     double new_following_pred_a = idm_acceleration(me, new_foll, me);
-    mg(e, new_following_pred_a + LANE_CHANGE_MAX_BRAKING_IMPOSED);
-    if (new_following_pred_a < -LANE_CHANGE_MAX_BRAKING_IMPOSED) return 0;
+    if (dec(e, HW_D_MOBIL_SAFE, self, cand, 0, new_following_pred_a + LANE_CHANGE_MAX_BRAKING_IMPOSED,
+            new_following_pred_a < -LANE_CHANGE_MAX_BRAKING_IMPOSED))
+        return 0;
     neighbours(e, self, me->lane, &op, &of);
     const veh_t *old_prec = op >= 0 ? &e->v[op] : NULL;
     const veh_t *old_foll = of >= 0 ? &e->v[of] : NULL;
@@ -225,8 +281,7 @@ static int mobil(hw_env *e, int self, int cand)
     double old_following_pred_a = idm_acceleration(me, old_foll, old_prec);
     double jerk = self_pred_a - self_a +
                   POLITENESS * (new_following_pred_a - new_following_a + old_following_pred_a - old_following_a);
-    mg(e, jerk - LANE_CHANGE_MIN_ACC_GAIN);
-    if (jerk < LANE_CHANGE_MIN_ACC_GAIN) return 0;
+    if (dec(e, HW_D_MOBIL_GAIN, self, cand, 0, jerk - LANE_CHANGE_MIN_ACC_GAIN, jerk < LANE_CHANGE_MIN_ACC_GAIN)) return 0;
     return 1;
 }
 
@@ -241,8 +296,11 @@ static void change_lane_policy(hw_env *e, int self)
                 o->target_lane == me->target_lane) {
                 double d = o->x - me->x;
                 double d_star = desired_gap(me, o);
-                mg(e, d); mg(e, d - d_star);
-                if (0 < d && d < d_star) { me->target_lane = me->lane; break; }
+                if (dec(e, HW_D_ABORT_AHEAD, self, j, 0, d, 0 < d) &&
+                    dec(e, HW_D_ABORT_GAP, self, j, 0, d - d_star, d < d_star)) {
+                    me->target_lane = me->lane;
+                    break;
+                }
             }
         }
         return;
@@ -255,9 +313,8 @@ static void change_lane_policy(hw_env *e, int self)
     if (me->lane > 0) cands[nc++] = me->lane - 1;
     if (me->lane < e->cfg.lanes_count - 1) cands[nc++] = me->lane + 1;
     for (int k = 0; k < nc; ++k) {
-        if (!is_reachable_from(e, me->x, me->y, cands[k])) continue;
-        mg(e, fabs(me->speed) - 1);
-        if (fabs(me->speed) < 1) continue;
+        if (!is_reachable_from(e, self, me->x, me->y, cands[k])) continue;
+        if (dec(e, HW_D_SPEED1, self, 0, 0, fabs(me->speed) - 1, fabs(me->speed) < 1)) continue;
         if (mobil(e, self, cands[k])) me->target_lane = cands[k];
     }
 }
@@ -284,10 +341,14 @@ static void idm_act(hw_env *e, int self)
 }
 
 /* ---- MDPVehicle (DiscreteMetaAction ego; secondary mode) ------ */
-static int speed_to_index(double speed)
+static int speed_to_index(hw_env *e, int who, double speed)
 {
     double x = (speed - 20.0) / (30.0 - 20.0);
     double r = nearbyint(x * 2.0); /* np.round: half to even (default FE_TONEAREST) */
+    if (e) { /* forced: the other neighbouring integer */
+        double f = x * 2.0 - floor(x * 2.0);
+        if (dec(e, HW_D_SPEED_INDEX, who, 0, 0, f - 0.5, 0)) r = (r > x * 2.0) ? r - 1 : r + 1;
+    }
     return (int)clipd(r, 0, 2);
 }
 static void controlled_act(hw_env *e, int self, int action)
@@ -295,12 +356,12 @@ static void controlled_act(hw_env *e, int self, int action)
     /* actions {0:LANE_LEFT,1:IDLE,2:LANE_RIGHT,3:FASTER,4:SLOWER}; -1 == None */
     veh_t *me = &e->v[self];
     if (action == 3 || action == 4) {
-        int idx = speed_to_index(me->speed) + (action == 3 ? 1 : -1);
+        int idx = speed_to_index(e, self, me->speed) + (action == 3 ? 1 : -1);
         idx = (int)clipd(idx, 0, 2);
         me->target_speed = 20.0 + 5.0 * idx; /* np.linspace(20, 30, 3) */
     } else if (action == 2 || action == 0) {
         int t = (int)clipd(me->target_lane + (action == 2 ? 1 : -1), 0, e->cfg.lanes_count - 1);
-        if (is_reachable_from(e, me->x, me->y, t)) me->target_lane = t;
+        if (is_reachable_from(e, self, me->x, me->y, t)) me->target_lane = t;
     }
     double steer = steering_control(e, me, me->target_lane);
     me->act_steer = clipd(steer, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
@@ -313,9 +374,10 @@ static void vehicle_step(hw_env *e, int idx, double dt)
     veh_t *v = &e->v[idx];
     if (v->is_idm) v->timer += dt;
     if (v->crashed) { v->act_steer = 0; v->act_acc = -1.0 * v->speed; }
-    mg(e, v->speed - MAX_SPEED); mg(e, v->speed - MIN_SPEED);
-    if (v->speed > MAX_SPEED) v->act_acc = fmin(v->act_acc, 1.0 * (MAX_SPEED - v->speed));
-    else if (v->speed < MIN_SPEED) v->act_acc = fmax(v->act_acc, 1.0 * (MIN_SPEED - v->speed));
+    if (dec(e, HW_D_VMAX, idx, 0, 0, v->speed - MAX_SPEED, v->speed > MAX_SPEED))
+        v->act_acc = fmin(v->act_acc, 1.0 * (MAX_SPEED - v->speed));
+    else if (dec(e, HW_D_VMAX, idx, 1, 0, v->speed - MIN_SPEED, v->speed < MIN_SPEED))
+        v->act_acc = fmax(v->act_acc, 1.0 * (MIN_SPEED - v->speed));
     double beta = atan(1.0 / 2 * tan(v->act_steer));
     double vx = v->speed * cos(v->heading + beta);
     double vy = v->speed * sin(v->heading + beta);
@@ -327,7 +389,7 @@ static void vehicle_step(hw_env *e, int idx, double dt)
     }
     v->heading += v->speed * sin(beta) / (VEH_LENGTH / 2) * dt;
     v->speed += v->act_acc * dt;
-    v->lane = closest_lane(e, v->x, v->y, v->heading);
+    v->lane = closest_lane(e, idx, v->x, v->y, v->heading);
 }
 
 /* ---- utils.are_polygons_intersecting + RoadObject.handle_collisions (A.7) - */
@@ -362,7 +424,7 @@ static void handle_collisions(hw_env *e, int ia, int ib, double dt)
     double diag = sqrt(VEH_LENGTH * VEH_LENGTH + VEH_WIDTH * VEH_WIDTH);
     double lim = (diag + diag) / 2 + A->speed * dt;
     double dist = sqrt(dx * dx + dy * dy);
-    if (dist > lim) return;
+    if (dec(e, HW_D_PRECHECK, ia, ib, 0, dist - lim, dist > lim)) return;
     double a[5][2], b[5][2];
     polygon(A, a); polygon(B, b);
     double da[2] = {A->speed * cos(A->heading) * dt, A->speed * sin(A->heading) * dt};
@@ -381,13 +443,12 @@ static void handle_collisions(hw_env *e, int ia, int ib, double dt)
             project(a, n, &min_a, &max_a);
             project(b, n, &min_b, &max_b);
             double sd = interval_distance(min_a, max_a, min_b, max_b);
-            mg(e, sd);
-            if (sd > 0) intersecting = 0;
+            int edge = 2 * poly + (k & 1); /* edges k and k + 2 of a rectangle are opposite normals of ONE axis: one key */
+            if (dec(e, HW_D_SAT_NOW, ia, ib, edge, sd, sd > 0)) intersecting = 0;
             double vp = n[0] * (da[0] - db[0]) + n[1] * (da[1] - db[1]);
             if (vp < 0) min_a += vp; else max_a += vp;
             double distance = interval_distance(min_a, max_a, min_b, max_b);
-            mg(e, distance);
-            if (distance > 0) will_intersect = 0;
+            if (dec(e, HW_D_SAT_WILL, ia, ib, edge, distance, distance > 0)) will_intersect = 0;
             if (!intersecting && !will_intersect) break;
             {
                 double cx = 0, cy = 0;
@@ -395,18 +456,21 @@ static void handle_collisions(hw_env *e, int ia, int ib, double dt)
                 double dd = (cx / 4) * n[0] + (cy / 4) * n[1];
                 double sx = dd > 0 ? n[0] : -n[0], sy = dd > 0 ? n[1] : -n[1];
                 seen_d[nseen] = fabs(distance); seen_ax[nseen][0] = sx; seen_ax[nseen][1] = sy; ++nseen;
-                if (fabs(distance) < min_distance) {
+                /* the axis choice matters only through the impact vector: the margin is recorded when
+                 * the two axes differ (n and -n of one rectangle give the same vector) */
+                int differs = fabs(sx - axis[0]) + fabs(sy - axis[1]) > 1e-9;
+                int wins = fabs(distance) < min_distance;
+                if (differs && isfinite(min_distance))
+                    wins = dec(e, HW_D_SAT_AXIS, ia, ib, edge, fabs(distance) - min_distance, wins);
+                if (wins) {
                     min_distance = fabs(distance);
                     axis[0] = sx; axis[1] = sy;
                 }
             }
         }
     }
+    (void)seen_d; (void)seen_ax;
     if (will_intersect) {
-        /* test aid: how close another edge came to winning the min-|distance| choice of the
-         * translation axis (a different axis means a different impact vector) */
-        for (int q = 0; q < nseen; ++q)
-            if (fabs(seen_ax[q][0] - axis[0]) + fabs(seen_ax[q][1] - axis[1]) > 1e-6) mg(e, seen_d[q] - min_distance);
         double tx = min_distance * axis[0], ty = min_distance * axis[1];
         A->impact_x = tx / 2; A->impact_y = ty / 2; A->has_impact = 1;
         B->impact_x = -tx / 2; B->impact_y = -ty / 2; B->has_impact = 1;
@@ -418,18 +482,22 @@ static void handle_collisions(hw_env *e, int ia, int ib, double dt)
 static int ego_on_road(hw_env *e)
 {
     const veh_t *ego = &e->v[0];
-    return on_lane(e, ego->x, ego->y, ego->lane, 0.0);
+    return on_lane(e, 0, ego->x, ego->y, ego->lane, 0.0);
 }
 
 void hw_step(hw_env *e, const float *action, double *reward, int32_t *terminated, int32_t *truncated)
 {
     const hw_cfg *c = &e->cfg;
     e->min_margin = INFINITY;
+    e->nmarg = 0;
+    memset(e->slow, 0, sizeof(e->slow));
+    e->frame = HW_FRAME_PRE;
     e->time += 1.0 / c->policy_frequency;
     int frames = c->simulation_frequency / c->policy_frequency;
     double dt = 1.0 / c->simulation_frequency;
     veh_t *ego = &e->v[0];
     for (int frame = 0; frame < frames; ++frame) {
+        e->frame = frame;
         if (e->steps % frames == 0) {
             if (c->ego_mode == 0) {
                 /* ContinuousAction.get_action: float32 arithmetic on the np.float32 action */
@@ -457,6 +525,7 @@ void hw_step(hw_env *e, const float *action, double *reward, int32_t *terminated
             for (int j = i + 1; j < e->V; ++j) handle_collisions(e, i, j, dt);
         e->steps += 1;
     }
+    e->frame = HW_FRAME_END;
     /* HighwayEnv._rewards / _reward (A.9) */
     int lane = ego->is_controlled ? ego->target_lane : ego->lane;
     double forward_speed = ego->speed * cos(ego->heading);
@@ -491,10 +560,17 @@ static double feature_value(const veh_t *v, int code)
     }
     return 0.0;
 }
+/* sort key |x_p - x_ego| of p strictly greater than that of q (p listed before q: p < q) */
+static int obs_after(hw_env *e, int p, int q)
+{
+    double kp = fabs(e->v[p].x - e->v[0].x), kq = fabs(e->v[q].x - e->v[0].x);
+    return dec(e, HW_D_OBS_ORDER, p, q, 0, kp - kq, kp > kq);
+}
 void hw_observe(const hw_env *ce, float *obs, const int32_t *perm, int32_t *row_vehicle)
 {
-    hw_env *e = (hw_env *)ce; /* margins only */
+    hw_env *e = (hw_env *)ce; /* decision bookkeeping only */
     const hw_cfg *c = &e->cfg;
+    e->frame = HW_FRAME_OBS;
     int N = c->obs_vehicles, F = c->obs_nfeat;
     const veh_t *ego = &e->v[0];
     int cand[HW_MAX_VEHICLES], nc = 0;
@@ -502,23 +578,19 @@ void hw_observe(const hw_env *ce, float *obs, const int32_t *perm, int32_t *row_
         const veh_t *o = &e->v[j];
         double dx = o->x - ego->x, dy = o->y - ego->y;
         double dist = sqrt(dx * dx + dy * dy);
-        mg(e, dist - PERCEPTION_DISTANCE);
-        if (!(dist < PERCEPTION_DISTANCE)) continue;
+        if (!dec(e, HW_D_OBS_CLOSE, j, 0, 0, dist - PERCEPTION_DISTANCE, dist < PERCEPTION_DISTANCE)) continue;
         if (!c->obs_see_behind) {
-            mg(e, dx + 2 * VEH_LENGTH);
-            if (!(-2 * VEH_LENGTH < dx)) continue;
+            if (!dec(e, HW_D_OBS_BEHIND, j, 0, 0, dx + 2 * VEH_LENGTH, -2 * VEH_LENGTH < dx)) continue;
         }
         cand[nc++] = j;
     }
     if (c->obs_sorted) { /* Python sorted(): stable, key |lane_distance_to| */
-        for (int a = 1; a < nc; ++a) {
+        for (int a = 1; a < nc; ++a) { /* insertion sort: stable; one keyed decision per compared pair */
             int cur = cand[a];
-            double key = fabs(e->v[cur].x - ego->x);
             int b = a - 1;
-            while (b >= 0 && fabs(e->v[cand[b]].x - ego->x) > key) { cand[b + 1] = cand[b]; --b; }
+            while (b >= 0 && obs_after(e, cand[b], cur)) { cand[b + 1] = cand[b]; --b; }
             cand[b + 1] = cur;
         }
-        for (int a = 1; a < nc; ++a) mg(e, fabs(e->v[cand[a]].x - ego->x) - fabs(e->v[cand[a - 1]].x - ego->x));
     }
     if (nc > N - 1) nc = N - 1;
     double table[HW_MAX_VEHICLES][HW_MAX_FEATURES];
@@ -602,7 +674,7 @@ void hw_reset(hw_env *e, uint64_t seed, uint64_t env_id, uint32_t episode)
         v->is_controlled = k > 0 || c->ego_mode == 1;
         v->delta = k > 0 ? 3.5 + (4.5 - 3.5) * u01(r[3]) : 4.0;
         v->timer = k > 0 ? pymod((v->x + v->y) * PI, LANE_CHANGE_DELAY) : 0.0;
-        if (k == 0 && c->ego_mode == 1) v->target_speed = 20.0 + 5.0 * speed_to_index(speed);
+        if (k == 0 && c->ego_mode == 1) v->target_speed = 20.0 + 5.0 * speed_to_index(NULL, 0, speed);
     }
 }
 
@@ -620,6 +692,21 @@ hw_env *hw_create(const hw_cfg *cfg)
 void hw_destroy(hw_env *e) { free(e); }
 int hw_num_vehicles(const hw_env *e) { return e->V; }
 double hw_last_min_margin(const hw_env *e) { return e->min_margin; }
+void hw_record_margin(hw_env *e, double below) { e->record_below = below; }
+int32_t hw_marginal_keys(const hw_env *e, uint64_t *keys, double *margins, int32_t max)
+{
+    int n = e->nmarg < max ? e->nmarg : max;
+    for (int q = 0; q < n; ++q) { keys[q] = e->marg[q]; if (margins) margins[q] = e->marg_val[q]; }
+    return e->nmarg;
+}
+int32_t hw_force_decisions(hw_env *e, const uint64_t *keys, int32_t n)
+{
+    if (n < 0 || n > HW_MAX_FORCED) return -1;
+    for (int q = 0; q < n; ++q) e->forced[q] = keys[q];
+    e->nforced = n;
+    return 0;
+}
+void hw_slow_vehicles(const hw_env *e, uint8_t *out) { memcpy(out, e->slow, (size_t)e->V); }
 
 void hw_get_state(const hw_env *e, hw_state *s)
 {

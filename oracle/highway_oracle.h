@@ -14,7 +14,9 @@
  * PARITY UNPINNED: the reference's own tests never touch the simulator, and
  * upstream highway-env could not be run in this build, so the simulator half
  * of the oracle is checked only for self-consistency (known-answer vectors
- * derived by hand from the published formulas, see tests/test_oracle_env.py).
+ * derived by hand from the published formulas, see tests/test_oracle_cpu.py).
+ * profiles/r02_highway_env_probe.txt records that the GPU box has no
+ * highway_env / gymnasium either.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.
@@ -29,6 +31,8 @@ extern "C" {
 
 #define HW_MAX_VEHICLES 128
 #define HW_MAX_FEATURES 8
+#define HW_MAX_MARGINAL 1024 /* marginal decisions listed per step */
+#define HW_MAX_FORCED 16   /* decisions that can be forced the other way at once */
 
 /* feature codes for the Kinematics observation (highway-env to_dict keys) */
 enum {
@@ -121,6 +125,17 @@ void hw_batch_step(hw_env **envs, int32_t n, const float *actions, float *obs,
 /* smallest margin by which any discrete decision taken during the last hw_step()
  * was decided (lane argmin, timer, MOBIL thresholds, SAT separations ...) */
 double hw_last_min_margin(const hw_env *env);
+
+/* ---- either-branch parity aid.  Every discrete decision has a control-flow independent key
+ * (kind << 32 | frame << 24 | a << 16 | b << 8 | c).  hw_record_margin: decisions of the following
+ * steps / observations that are decided by less than `below` are listed (hw_marginal_keys returns
+ * how many there were; the list restarts with every hw_step).  hw_force_decisions: the listed keys
+ * are decided the OTHER way from now on (n = 0 clears).  hw_slow_vehicles: controlled vehicles that
+ * acted below 0.5 m/s in the last step (ill-conditioned steering: tolerances are widened). */
+void    hw_record_margin(hw_env *env, double below);
+int32_t hw_marginal_keys(const hw_env *env, uint64_t *keys, double *margins, int32_t max);
+int32_t hw_force_decisions(hw_env *env, const uint64_t *keys, int32_t n);
+void    hw_slow_vehicles(const hw_env *env, uint8_t *out);
 
 #ifdef __cplusplus
 }

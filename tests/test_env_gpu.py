@@ -1,18 +1,30 @@
 """GPU parity of the simulator kernels (hrp_env_step / observe / reset through the C-ABI) against the
-CPU oracle (oracle/highway_oracle.c), by STATE INJECTION: every step the oracle's fp64 state is
-injected into the GPU handle, both sides step once on the same action, and the results are compared.
+CPU oracle (oracle/highway_oracle.c).  Three kinds of comparison, none of which waives an env-step:
 
-Tolerances (stated here, used below).  The kernel integrates in fp32 with x and the lane-change
-timer in fp64; the oracle is fp64 throughout.
-  * discrete results -- lane and target-lane indices, crashed / pending-impact flags, terminated /
-    truncated, and the vehicle index shown in every observation row -- must be EXACT whenever the
-    oracle reports that no discrete decision of that step was taken within MARGIN of its threshold
-    (hw_last_min_margin); steps closer than that -- and steps where a controlled vehicle crawls below 0.5 m/s,
-    where the controller's divisions by the speed amplify rounding by > 1e3 -- are counted and must stay a minority;
-  * x, y: 1e-3 m;  speed: 2e-4 m/s;  heading: 1e-4 rad;  reward: 2e-5;  observation entries: 2e-5
-    (normalised units);  IDM timer: 1e-9.
+1. STATE INJECTION, fp32 product kernel, either-branch rule.  Every step the oracle's fp64 state is injected
+   into the GPU handle, both sides step once on the same action and everything is compared: lane and
+   target-lane indices, crashed / pending-impact flags, terminated / truncated and the vehicle index shown in
+   every observation row EXACTLY; x, y: 1e-3 m; speed: 2e-4 m/s; heading: 1e-4 rad; reward: 2e-5; observation
+   entries: 2e-5 (normalised units); IDM timer: 1e-9.  The kernel integrates in fp32 (x and the lane-change
+   timer in fp64), so a decision the oracle takes within MARGIN = 1e-3 of its threshold may legitimately fall
+   the other way.  Such a step is NOT skipped: the oracle is re-run from the same state with its marginal
+   decisions forced the other way (keyed decisions, highway_oracle.h), breadth first over combinations, and the
+   kernel must equal ONE of the outcomes in full.  Counts are reported as agree / flipped / neither and any
+   `neither` fails the test.  Vehicles that act below 0.5 m/s (the steering controller divides by the speed
+   twice, and IDM vehicles reversing in a jam have an unstable lateral loop: rounding is amplified by > 1e3 in
+   one step) get their continuous tolerances widened by 1e3, vehicles within 60 m of one by 30 (oracle/parity.py);
+   nothing discrete is relaxed for them.
+2. STATE INJECTION and FREE RUNNING, fp64 validation instantiation of the same kernels (HRP_ENV_REAL64): with
+   no rounding in the way the discrete state must be bit-exact on 100 % of the steps, no margin rule at all, and
+   the continuous state within 1e-7 (positions and impacts 2e-6: separating-axis ties between nearly parallel
+   rectangles, oracle/parity.py); free running means ONE injection followed by 45 steps of both sides with
+   in-kernel respawn, which exercises what per-step injection hides (pending impacts crossing a step boundary,
+   episode / draw counters, accumulated state).
+3. FREE-RUNNING WINDOWS of the fp32 kernel: inject once, run 5 / 15 / 40 steps on both sides, compare every step
+   until the first step on which the oracle reports a decision closer than the accumulated drift allows.
 """
 import copy
+from collections import Counter
 
 import numpy as np
 import pytest
@@ -22,9 +34,8 @@ from oracle import highway as oh
 
 pytestmark = pytest.mark.gpu
 
-MARGIN = 1e-3
-TOL = dict(x=1e-3, y=1e-3, speed=2e-4, heading=1e-4, impact_x=1e-3, impact_y=1e-3, timer=1e-9, target_speed=1e-5)
-DISCRETE = ("lane", "target_lane", "crashed", "has_impact")
+from oracle.parity import DISCRETE, MARGIN, SLOW_FACTOR, TOL, TOL64, Got as _Got, either_branch as _either_branch, \
+    mismatch as _mismatch
 
 
 def _vec(cfg, E, **kw):
@@ -63,10 +74,11 @@ def test_philox_matches_oracle():
         assert np.array_equal(out, oh.philox4x32_10(ctr, key))
 
 
+@pytest.mark.parametrize("real64", [False, True])
 @pytest.mark.parametrize("seed,base", [(0, 0), (42, 0), (2**40 + 7, 1000)])
-def test_reset_matches_oracle(highway_config, seed, base):
+def test_reset_matches_oracle(highway_config, seed, base, real64):
     E = 96
-    env = _vec(highway_config, E, env_id_base=base)
+    env = _vec(highway_config, E, env_id_base=base, real64=real64)
     env.reset(seed)
     st = env.get_state()
     o = oh.OracleEnv(highway_config)
@@ -78,24 +90,28 @@ def test_reset_matches_oracle(highway_config, seed, base):
         np.testing.assert_allclose(st["x"][e], ref["x"], atol=1e-9)
         np.testing.assert_allclose(st["timer"][e], ref["timer"], atol=1e-8)
         for k in ("y", "speed", "target_speed", "delta", "heading"):
-            np.testing.assert_allclose(st[k][e], ref[k], rtol=2e-7, atol=1e-7, err_msg=k)
+            np.testing.assert_allclose(st[k][e], ref[k], rtol=1e-12 if real64 else 2e-7, atol=1e-7, err_msg=k)
         assert st["time"][e] == 0.0 and st["episode"][e] == 0
     env.close()
 
 
-def _injected_parity(cfg, E, steps, seed, action_fn, sorted_obs=True, obs_tol=2e-5):
-    """Returns (#env-steps compared exactly, #env-steps skipped as marginal, max abs errors)."""
+def _injected_parity(cfg, E, steps, seed, action_fn, sorted_obs=True, obs_tol=2e-5, real64=False):
+    """State-injection parity.  Returns a dict: agree / flipped / neither env-step counts, the kinds of the decisions
+    that had to be flipped, the worst continuous errors of the agreeing steps and the first few failures."""
     N = cfg["observation"]["vehicles_count"]
-    env = _vec(cfg, E, autoreset=False)
+    env = _vec(cfg, E, autoreset=False, real64=real64)
     oracles = [oh.OracleEnv(cfg) for _ in range(E)]
     for e, o in enumerate(oracles):
         o.reset(seed, env_id=e, episode=0)
     rng = np.random.default_rng(seed)
     rows = torch.zeros((E, N), dtype=torch.int32, device="cuda:0")
-    compared = skipped = 0
-    worst = {k: 0.0 for k in list(TOL) + ["reward", "obs"]}
+    tol, rew_tol = (TOL64, 1e-6) if real64 else (TOL, 2e-5)
+    obs_tol = 1e-6 if real64 else obs_tol
+    stats = {"agree": 0, "flipped": 0, "neither": 0, "kinds": Counter(), "worst": {}, "failures": []}
     for t in range(steps):
-        st = _stack_states(oracles)
+        sts = [o.get_state() for o in oracles]
+        st = {k: np.stack([s[k] for s in sts]) for k in oh.STATE_F64 + oh.STATE_I32}
+        st["time"] = np.array([s["time"] for s in sts])
         env.set_state(st)
         actions = action_fn(rng, E, t).astype(np.float32)
         perm = None
@@ -104,35 +120,37 @@ def _injected_parity(cfg, E, steps, seed, action_fn, sorted_obs=True, obs_tol=2e
         obs, rew, term, trunc = env.step(torch.from_numpy(actions).cuda(),
                                          perm=None if perm is None else torch.from_numpy(perm).cuda(),
                                          row_vehicle=rows)
-        got = env.get_state()
+        state = env.get_state()
         obs, rew, term, trunc, rv = (x.cpu().numpy() for x in (obs, rew, term, trunc, rows))
         for e, o in enumerate(oracles):
+            got = _Got(state, e, obs, rew, term, trunc, rv)
+            pe = None if perm is None else perm[e]
             r, te, tr = o.step(actions[e])
-            margin = o.min_margin()
-            ref = o.get_state()
-            want_obs, want_rows = o.observe(perm=None if perm is None else perm[e], with_rows=True)
-            margin = min(margin, o.min_margin())
-            if margin < MARGIN:
-                skipped += 1
+            want_obs, want_rows = o.observe(perm=pe, with_rows=True)
+            why = _mismatch(got, o, r, te, tr, want_obs, want_rows, tol, obs_tol, rew_tol, stats["worst"])
+            if why is None:
+                stats["agree"] += 1
             else:
-                compared += 1
-                for k in DISCRETE:
-                    assert np.array_equal(got[k][e], ref[k]), (k, t, e, got[k][e], ref[k])
-                assert bool(term[e]) == te and bool(trunc[e]) == tr, (t, e)
-                assert np.array_equal(rv[e], want_rows), (t, e, rv[e], want_rows)
-                for k, tol in TOL.items():
-                    err = float(np.max(np.abs(got[k][e] - ref[k])))
-                    worst[k] = max(worst[k], err)
-                    assert err <= tol, (k, t, e, err)
-                worst["reward"] = max(worst["reward"], abs(float(rew[e]) - r))
-                assert abs(float(rew[e]) - r) <= 2e-5, (t, e, rew[e], r)
-                err = float(np.max(np.abs(obs[e] - want_obs)))
-                worst["obs"] = max(worst["obs"], err)
-                assert err <= obs_tol, (t, e, err)
+                forced = None if real64 else _either_branch(o, sts[e], actions[e], pe, got, tol, obs_tol, rew_tol, why=why)
+                if forced:
+                    stats["flipped"] += 1
+                    stats["kinds"].update(oh.decode_key(k).split("[")[0] for k in forced)
+                else:
+                    stats["neither"] += 1
+                    if len(stats["failures"]) < 5:
+                        stats["failures"].append((t, e, why))
             if te or tr:  # reference loop: reset right after done
                 o.reset(seed, env_id=e, episode=1 + t)
     env.close()
-    return compared, skipped, worst
+    return stats
+
+
+def _report(name, s):
+    n = s["agree"] + s["flipped"] + s["neither"]
+    print(f"{name}: {n} env-steps: agree {s['agree']}, flipped {s['flipped']} {dict(s['kinds'])}, neither {s['neither']}; "
+          f"max abs err {({k: float(f'{v:.3g}') for k, v in s['worst'].items()})}")
+    assert s["neither"] == 0, s["failures"]
+    return n
 
 
 def _random_actions(rng, E, t):
@@ -147,59 +165,185 @@ def _gentle_actions(rng, E, t):
 
 def test_step_parity_random_actions(highway_config):
     """>= 1000 injected-state env-steps with uniformly random actions (crashes, off-road, respawns)."""
-    compared, skipped, worst = _injected_parity(highway_config, E=48, steps=25, seed=1, action_fn=_random_actions)
-    print("random actions: compared", compared, "marginal", skipped, "max abs err", worst)
-    assert compared >= 1000 and skipped <= 0.3 * (compared + skipped)
+    s = _injected_parity(highway_config, E=48, steps=25, seed=1, action_fn=_random_actions)
+    assert _report("random actions", s) >= 1000 and s["flipped"] <= 0.3 * s["agree"]
 
 
 def test_step_parity_gentle_actions(highway_config):
     """Long episodes (40 steps, truncation) where IDM / MOBIL traffic interaction is the bulk of the work."""
-    compared, skipped, worst = _injected_parity(highway_config, E=32, steps=42, seed=2, action_fn=_gentle_actions)
-    print("gentle actions: compared", compared, "marginal", skipped, "max abs err", worst)
-    assert compared >= 1000 and skipped <= 0.3 * (compared + skipped)
+    s = _injected_parity(highway_config, E=32, steps=42, seed=2, action_fn=_gentle_actions)
+    assert _report("gentle actions", s) >= 1000 and s["flipped"] <= 0.3 * s["agree"]
 
 
 def test_step_parity_shuffled_30_rows_7_features(highway_config):
     """BASELINE config 3 shape: N = 30 observed vehicles, all 7 features, shuffled with an injected permutation."""
     cfg = _cfg(highway_config, observation=dict(vehicles_count=30, order="shuffled",
                                                features=["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"]))
-    compared, skipped, worst = _injected_parity(cfg, E=16, steps=20, seed=3, action_fn=_random_actions,
-                                                sorted_obs=False)
-    print("shuffled N=30 F=7: compared", compared, "marginal", skipped, "max abs err", worst)
-    assert compared >= 250 and skipped <= 0.3 * (compared + skipped)
+    s = _injected_parity(cfg, E=16, steps=20, seed=3, action_fn=_random_actions, sorted_obs=False)
+    assert _report("shuffled N=30 F=7", s) >= 320
 
 
 def test_step_parity_dense_small_road(highway_config):
     """Edge sizes: 2 lanes, 12 vehicles at density 3 (frequent contacts), 5 observed rows, see_behind."""
     cfg = _cfg(highway_config, lanes_count=2, vehicles_count=12, vehicles_density=3,
                observation=dict(vehicles_count=5, see_behind=True))
-    compared, skipped, worst = _injected_parity(cfg, E=32, steps=30, seed=4, action_fn=_random_actions)
-    print("dense 2-lane: compared", compared, "marginal", skipped, "max abs err", worst)
-    assert compared >= 600 and skipped <= 0.4 * (compared + skipped)
+    s = _injected_parity(cfg, E=32, steps=30, seed=4, action_fn=_random_actions)
+    assert _report("dense 2-lane", s) >= 960
+
+
+def _meta_actions(rng, E, t):
+    a = np.zeros((E, 2))
+    a[:, 0] = rng.integers(0, 5, E)
+    return a
+
+
+def _meta_cfg(highway_config):
+    cfg = _cfg(highway_config)
+    cfg["action"] = {"type": "DiscreteMetaAction"}
+    return cfg
 
 
 def test_step_parity_meta_action_ego(highway_config):
     """DiscreteMetaAction / MDPVehicle ego (north_star; unreachable through the reference runner)."""
-    cfg = _cfg(highway_config)
-    cfg["action"] = {"type": "DiscreteMetaAction"}
-
-    def act(rng, E, t):
-        a = np.zeros((E, 2))
-        a[:, 0] = rng.integers(0, 5, E)
-        return a
-
-    compared, skipped, worst = _injected_parity(cfg, E=24, steps=40, seed=5, action_fn=act)
-    print("meta-action ego: compared", compared, "marginal", skipped, "max abs err", worst)
-    # LANE_LEFT/RIGHT reachability tests |y - 4 lane| <= 8 sit exactly on the threshold for a centred ego
-    assert compared >= 600 and skipped <= 0.4 * (compared + skipped)
+    s = _injected_parity(_meta_cfg(highway_config), E=24, steps=40, seed=5, action_fn=_meta_actions)
+    assert _report("meta-action ego", s) >= 960
 
 
 def test_single_vehicle_and_max_vehicles(highway_config):
     """Edge sizes: an empty road (ego only: every observation row but the first is padding) and V = 64."""
-    for vc, n in ((0, 15), (63, 15)):
+    for vc in (0, 63):
         cfg = _cfg(highway_config, vehicles_count=vc)
-        compared, skipped, _ = _injected_parity(cfg, E=8, steps=12, seed=6 + vc, action_fn=_gentle_actions)
-        assert compared >= 80
+        s = _injected_parity(cfg, E=8, steps=12, seed=6 + vc, action_fn=_gentle_actions)
+        assert _report(f"vehicles_count {vc}", s) == 96
+
+
+# ---- fp64 validation instantiation: bit-exact discrete state on every step, no margin rule -------------------------
+@pytest.mark.parametrize("name", ["random", "gentle", "dense", "meta", "shuffled30"])
+def test_fp64_kernel_is_exact_on_every_step(highway_config, name):
+    cfg, fn, sorted_obs, E, steps = {
+        "random": (highway_config, _random_actions, True, 32, 25),
+        "gentle": (highway_config, _gentle_actions, True, 24, 42),
+        "dense": (_cfg(highway_config, lanes_count=2, vehicles_count=12, vehicles_density=3,
+                       observation=dict(vehicles_count=5, see_behind=True)), _random_actions, True, 32, 30),
+        "meta": (_meta_cfg(highway_config), _meta_actions, True, 24, 40),
+        "shuffled30": (_cfg(highway_config, observation=dict(vehicles_count=30, order="shuffled",
+                                                             features=["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"])),
+                       _random_actions, False, 16, 20),
+    }[name]
+    s = _injected_parity(cfg, E=E, steps=steps, seed=11, action_fn=fn, sorted_obs=sorted_obs, real64=True)
+    n = _report(f"fp64 kernel, {name}", s)
+    assert s["flipped"] == 0 and s["agree"] == n == E * steps
+
+
+def _free_run(cfg, E, steps, seed, action_fn, real64, window=None):
+    """ONE injection (the oracle's spawn), then `steps` steps of both sides without re-injection, in-kernel respawn
+    on, the oracle respawning the same episodes.  fp64 kernel: everything is compared on every step.  fp32 kernel:
+    an env is compared until the first step on which the oracle took a decision by less than the drift bound."""
+    N = cfg["observation"]["vehicles_count"]
+    env = _vec(cfg, E, autoreset=True, real64=real64, seed=seed)
+    env.reset(seed)
+    oracles = [oh.OracleEnv(cfg) for _ in range(E)]
+    episode = [0] * E
+    for e, o in enumerate(oracles):
+        o.reset(seed, env_id=e, episode=0)
+    st = _stack_states(oracles)
+    full = dict(st)
+    state0 = env.get_state()
+    full["episode"], full["obs_draw"] = state0["episode"], state0["obs_draw"]
+    env.set_state(full)
+    rng = np.random.default_rng(seed)
+    rows = torch.zeros((E, N), dtype=torch.int32, device="cuda:0")
+    live = np.ones(E, dtype=bool)
+    closest = np.full(E, np.inf)
+    compared, lengths, worst = 0, [], {}
+    for t in range(steps):
+        actions = action_fn(rng, E, t).astype(np.float32)
+        obs, rew, term, trunc = env.step(torch.from_numpy(actions).cuda(), row_vehicle=rows)
+        state = env.get_state()
+        obs, rew, term, trunc, rv = (x.cpu().numpy() for x in (obs, rew, term, trunc, rows))
+        for e, o in enumerate(oracles):
+            if not live[e]:
+                continue
+            r, te, tr = o.step(actions[e])
+            margin = o.min_margin()
+            if te or tr:  # the kernel respawned inside the step: the state and the observation are the new episode's
+                episode[e] += 1
+                o.reset(seed, env_id=e, episode=episode[e])
+            want_obs, want_rows = o.observe(with_rows=True)
+            margin = min(margin, o.min_margin())
+            got = _Got(state, e, obs, rew, term, trunc, rv)
+            if real64:
+                why = _mismatch(got, o, r, te, tr, want_obs, want_rows, TOL64, 1e-6, 1e-6, worst)
+                assert why is None, (t, e, why)
+                assert state["episode"][e] == episode[e]
+            else:
+                # tolerances and the decision margin grow with the steps since the injection.  A window ends at the
+                # first difference, and a difference is only legitimate if the oracle has taken a decision inside the
+                # drift-scaled margin at this or an earlier step of the window (the two sides may then have branched).
+                drift = 1.0 + t
+                closest[e] = min(closest[e], margin / drift)
+                why = _mismatch(got, o, r, te, tr, want_obs, want_rows, {k: v * drift for k, v in TOL.items()},
+                                2e-5 * drift, 2e-5 * drift, worst)
+                if why is not None:
+                    assert closest[e] < MARGIN, (t, e, why, closest[e])
+                    live[e] = False
+                    lengths.append(t)
+                    continue
+            compared += 1
+    lengths += [steps] * int(live.sum())
+    env.close()
+    return compared, lengths, worst
+
+
+def test_fp64_kernel_free_running_45_steps(highway_config):
+    """Inject once, then 45 free-running steps with in-kernel respawn: bit-exact discrete state throughout."""
+    compared, _, worst = _free_run(highway_config, E=24, steps=45, seed=21, action_fn=_gentle_actions, real64=True)
+    print("fp64 free run, gentle:", compared, "env-steps, max abs err", worst)
+    assert compared == 24 * 45
+    compared, _, worst = _free_run(highway_config, E=24, steps=30, seed=22, action_fn=_random_actions, real64=True)
+    print("fp64 free run, random:", compared, "env-steps, max abs err", worst)
+    assert compared == 24 * 30
+    cfg = _meta_cfg(highway_config)
+    compared, _, worst = _free_run(cfg, E=16, steps=45, seed=23, action_fn=_meta_actions, real64=True)
+    print("fp64 free run, meta-action:", compared, "env-steps, max abs err", worst)
+    assert compared == 16 * 45
+
+
+@pytest.mark.parametrize("window", [5, 15, 40])
+def test_fp32_kernel_free_running_windows(highway_config, window):
+    """Inject once, run `window` steps on both sides, compare every step until the first marginal decision."""
+    compared, lengths, worst = _free_run(highway_config, E=48, steps=window, seed=30 + window,
+                                         action_fn=_gentle_actions, real64=False)
+    print(f"fp32 free run, window {window}: {compared} env-steps compared, mean compared length "
+          f"{np.mean(lengths):.1f}, full windows {sum(l == window for l in lengths)}/48, max abs err", worst)
+    assert np.mean(lengths) >= 0.6 * window
+
+
+def test_fp32_kernel_matches_fp64_kernel(highway_config):
+    """The product kernel against the validation instantiation on identical injected states (no oracle involved):
+    discrete state equal wherever the fp64 kernel's neighbours in state space agree, continuous state within TOL."""
+    E, seed = 64, 77
+    a, b = _vec(highway_config, E, autoreset=False), _vec(highway_config, E, autoreset=False, real64=True)
+    a.reset(seed)
+    b.reset(seed)
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    same = total = 0
+    for t in range(20):
+        b.set_state(a.get_state())   # fp32-representable states: both start from identical values
+        act = torch.rand((E, 2), generator=g, device="cuda:0") * 2 - 1
+        act[:, 1] *= 0.1
+        a.step(act)
+        b.step(act)
+        sa, sb = a.get_state(), b.get_state()
+        for e in range(E):
+            total += 1
+            if all(np.array_equal(sa[k][e], sb[k][e]) for k in DISCRETE):
+                same += 1
+                for k, tol in TOL.items():
+                    assert np.max(np.abs(sa[k][e] - sb[k][e])) <= tol * (SLOW_FACTOR if np.any(np.abs(sb["speed"][e]) < 0.6) else 1), (k, t, e)
+    print(f"fp32 vs fp64 kernel: discrete state identical on {same}/{total} env-steps")
+    assert same >= 0.8 * total
+    a.close(); b.close()
 
 
 def test_shuffle_draw_matches_oracle_permutation(highway_config):

@@ -402,3 +402,105 @@ def test_sim_observation_normalisation_and_clip(highway_config):
     np.testing.assert_allclose(obs[1], [0.2, -0.04, 3.0 / 30.0, 0.0], atol=1e-7)           # nearest first (sorted)
     np.testing.assert_allclose(obs[2], [1.0, 0.04, -3.0 / 30.0, 0.0], atol=1e-7)           # 150 m ahead: clipped
     assert np.all(obs[3:] == 0.0)
+
+
+# ---------------------------------------------------------------- keyed decisions / either-branch aid
+def _mobil_scene(o):
+    """Vehicle 1 (lane 1, timer fired) behind a slow vehicle 2: lane 0 is free, lane 2 holds a follower 3."""
+    o.reset(5)
+    st = o.get_state()
+    st["x"][:] = [0.0, 200.0, 235.0, 1000.0]
+    st["y"][:] = [12.0, 4.0, 4.0, 8.0]
+    st["lane"][:] = st["target_lane"][:] = [3, 1, 1, 2]
+    st["speed"][:] = [0.0, 25.0, 18.0, 30.0]
+    st["target_speed"][:] = [0.0, 30.0, 18.0, 30.0]
+    st["delta"][:] = 4.0
+    st["timer"][:] = [0.0, 1.0 + 1e-9, 0.0, 0.0]
+    st["heading"][:] = 0.0
+    st["crashed"][:] = 0
+    st["has_impact"][:] = 0
+    return st
+
+
+def test_decision_keys_list_and_force(highway_config):
+    """hw_record_margin lists the decisions of a step that fall below the bound, hw_force_decisions takes the
+    listed decision the other way and nothing else; clearing the forced set restores the fp64 outcome."""
+    cfg = copy.deepcopy(highway_config)
+    cfg["vehicles_count"] = 3
+    o = oh.OracleEnv(cfg)
+    st = _mobil_scene(o)
+    o.set_state(st)
+    o.step([0.0, 0.0])
+    base = o.get_state()
+    assert base["target_lane"][1] == 2          # both neighbours acceptable: the later candidate (lane 2) wins
+    assert o.marginal() == []                   # nothing recorded while the bound is 0
+    # a bound of 1e9 lists every decision of the step; the MOBIL gain test of vehicle 1 towards lane 2 is one of them
+    o.record_margin(1e9)
+    o.set_state(st)
+    o.step([0.0, 0.0])
+    keys = o.marginal()
+    names = [oh.decode_key(k) for k in keys]
+    gain = [k for k, n in zip(keys, names) if n.startswith("mobil_gain[frame 0: 1,2,")]
+    assert len(gain) == 1 and len(set(keys)) == len(keys)
+    o.record_margin(0.0)
+    o.force(gain)
+    o.set_state(st)
+    o.step([0.0, 0.0])
+    forced = o.get_state()
+    assert forced["target_lane"][1] == 0        # lane 2 refused: the earlier candidate (lane 0) stands
+    others = [2, 3]
+    assert np.array_equal(forced["target_lane"][others], base["target_lane"][others])
+    o.force(())
+    o.set_state(st)
+    o.step([0.0, 0.0])
+    again = o.get_state()
+    for k in oh.STATE_F64 + oh.STATE_I32:
+        assert np.array_equal(again[k], base[k]), k
+
+
+def test_decision_keys_are_control_flow_independent(highway_config):
+    """The same logical decision asked several times in a frame (vehicle j on the band of lane L) is ONE key, and
+    forcing it flips every evaluation: the band test of the slow vehicle 2 on its own lane hides it from vehicle 1."""
+    cfg = copy.deepcopy(highway_config)
+    cfg["vehicles_count"] = 3
+    o = oh.OracleEnv(cfg)
+    st = _mobil_scene(o)
+    st["timer"][1] = 0.0                        # no lane change: only the car-following term matters
+    o.set_state(st)
+    o.step([0.0, 0.0])
+    braking = o.get_state()["speed"][1]
+    o.record_margin(1e9)
+    o.set_state(st)
+    o.step([0.0, 0.0])
+    keys = [k for k in o.marginal() if oh.decode_key(k).startswith("on_band[frame 0: 2,1,")]
+    o.record_margin(0.0)
+    assert len(keys) == 1
+    o.force(keys)
+    o.set_state(st)
+    o.step([0.0, 0.0])
+    o.force(())
+    assert o.get_state()["speed"][1] > braking + 0.05   # frame 0 ran without a vehicle in front
+
+
+def test_observation_order_decision(highway_config):
+    """Sorted observation: forcing the order decision of two candidates swaps exactly their rows."""
+    cfg = copy.deepcopy(highway_config)
+    cfg["vehicles_count"] = 3
+    o = oh.OracleEnv(cfg)
+    o.reset(5)
+    st = o.get_state()
+    st["x"][:] = [300.0, 320.0, 320.0005, 350.0]
+    st["y"][:] = [4.0, 8.0, 0.0, 4.0]
+    st["lane"][:] = st["target_lane"][:] = [1, 2, 0, 1]
+    o.set_state(st)
+    o.record_margin(1e-3)
+    o.step([0.0, 0.0])
+    _, rows = o.observe(with_rows=True)
+    keys = [k for k in o.marginal() if oh.decode_key(k).startswith("obs_order")]
+    if keys:   # the two vehicles stayed within 1e-3 m of each other (same speed model): swap them
+        o.force(keys)
+        _, swapped = o.observe(with_rows=True)
+        o.force(())
+        a, b = list(rows[1:3]), list(swapped[1:3])
+        assert sorted(a) == sorted(b) == [1, 2] and a != b
+    o.record_margin(0.0)

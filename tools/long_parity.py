@@ -24,13 +24,31 @@ runs = [
     ("configs[2]: N=30 F=4 shuffled", T._cfg(base, observation=dict(vehicles_count=30, order="shuffled")), 64, 160, 14,
      T._gentle_actions, False),
 ]
+total = 0
 for name, cfg, E, steps, seed, fn, sorted_obs in runs:
     # observation tolerance = the state tolerance of y (1e-3 m) over its normalisation half-range (16 m); the unit
     # tests' 2e-5 is tighter than the state tolerances imply and is exceeded about once in 1e4 env-steps
-    compared, skipped, worst = T._injected_parity(cfg, E=E, steps=steps, seed=seed, action_fn=fn, sorted_obs=sorted_obs,
-                                                  obs_tol=6.5e-5)
-    print(f"{name}: {E} envs x {steps} injected-state steps = {E * steps} env-steps; compared exactly {compared}, "
-          f"marginal (a discrete decision within {T.MARGIN} of its threshold in the oracle) {skipped}")
-    print("   max abs error:", ", ".join(f"{k} {v:.3g}" for k, v in worst.items()))
-print("discrete state (lane, target lane, crashed, impact flags), terminated / truncated and the vehicle index of every "
-      "observation row were identical on every compared env-step (the harness asserts it)")
+    s = T._injected_parity(cfg, E=E, steps=steps, seed=seed, action_fn=fn, sorted_obs=sorted_obs, obs_tol=6.5e-5)
+    n = s["agree"] + s["flipped"] + s["neither"]
+    total += n
+    print(f"{name}: {E} envs x {steps} injected-state steps = {n} env-steps, NONE skipped: agree with the fp64 oracle "
+          f"{s['agree']}, agree with the oracle after flipping marginal (< {T.MARGIN}) decisions {s['flipped']}, "
+          f"neither {s['neither']}")
+    print("   flipped decision kinds:", dict(s["kinds"]))
+    print("   max abs error of the agreeing steps:", ", ".join(f"{k} {v:.3g}" for k, v in s["worst"].items()))
+    for f in s["failures"]:
+        print("   FAILURE (step, env, first difference):", f)
+    assert s["neither"] == 0
+# the fp64 validation instantiation of the same kernels: bit-exact discrete state, no margin rule
+for name, cfg, E, steps, seed, fn, sorted_obs in runs[:2]:
+    s = T._injected_parity(cfg, E=E, steps=steps // 2, seed=seed + 100, action_fn=fn, sorted_obs=sorted_obs, real64=True)
+    n = s["agree"] + s["flipped"] + s["neither"]
+    print(f"fp64 kernel, {name}: {n} env-steps: discrete state bit-exact and continuous state within 1e-7 on {s['agree']}, "
+          f"differing on {s['neither']}")
+    print("   max abs error:", ", ".join(f"{k} {v:.3g}" for k, v in s["worst"].items()))
+    assert s["neither"] == 0 and s["flipped"] == 0
+for steps, fn, nm in ((45, T._gentle_actions, "gentle"), (45, T._random_actions, "random")):
+    compared, _, worst = T._free_run(base, E=64, steps=steps, seed=40, action_fn=fn, real64=True)
+    print(f"fp64 kernel, free running ({nm} actions, one injection, in-kernel respawn): {compared} env-steps, every one "
+          "bit-exact in the discrete state; max abs error:", ", ".join(f"{k} {v:.3g}" for k, v in worst.items()))
+print(f"total fp32 env-steps checked with the either-branch rule: {total}; skipped: 0")
