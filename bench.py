@@ -38,7 +38,6 @@ if ROOT not in sys.path:
 
 METRIC = "policy env-steps/s (4096 envs/GPU)"
 UNIT = "env-steps/s"
-OVERRIDE = {"observation": {"order": "shuffled"}}
 KERNELS_PER_ACT = 4   # 3 x tcgen05 GEMM (trunk 2, actor | critic hidden layers as one) + heads_act (dot products, Philox sampling, log-prob)
 KERNELS_PER_ENV_STEP = 1
 
@@ -146,6 +145,18 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def offline_ncu(kernel):
+    """Per-env counters of `kernel` from the ncu summary committed under profiles/ (tools/ncu_summary.py writes
+    profiles/ncu_counters.json from an `ncu --set full` capture); None when there is none."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_counters.json")) as f:
+            c = json.load(f)[kernel]
+        return {"dram_bytes_per_env": float(c["dram_bytes"]) / c["envs"],
+                "warp_instructions_per_env": float(c["warp_instructions"]) / c["envs"], "source": c["source"]}
+    except Exception:
+        return None
 
 
 def algorithmic_bytes_per_env_step(V=51, N=15, Fout=4):
@@ -353,11 +364,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    E, S, A, H = args.envs, 60, 2, args.hidden
+    E, A, H = args.envs, 2, args.hidden
     set_random_seeds(42)
-    env = make_vec_env(Condition.SHUFFLED_ROPE, HIGHWAY_CONFIG, 4, OVERRIDE, num_envs=E, device=dev, seed=42,
-                       env_id_base=rank * E)
-    agent = PPOAgent(S, A, lr=3e-4, hidden_dim=H, batch_size=4096, epochs=8, device=dev)
+    cond_name, d_embed, over = condition_of(args)
+    env = make_vec_env(Condition[cond_name], HIGHWAY_CONFIG, d_embed, over, num_envs=E, device=dev, seed=42,
+                       env_id_base=rank * E, strict_d_embed=False)
+    N, Fout = env.N, env.F_out
+    S = N * Fout
+    agent = PPOAgent(S, A, lr=3e-4, hidden_dim=H, batch_size=args.minibatch, epochs=args.epochs, device=dev)
+    agent.actor_critic.row_base = rank * E   # exploration noise keyed by the global env id
     obs = env.reset(42).view(E, S)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {"action": torch.empty((E, A), device=dev), "pre_tanh": torch.empty((E, A), device=dev),
@@ -370,6 +385,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         policy_env_step()
     K = args.steps
+    calls0 = (agent.launches, env.launches)   # hrp_ppo_act_sample / hrp_env_step calls enqueued so far
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     sampler = ClockSampler(local)
     barrier()
@@ -384,6 +400,9 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.result()
+    # kernels of this library launched inside the timed region: counted calls x kernels per call (a policy call is
+    # 3 tcgen05 GEMM launches + heads_act, an env step is one fused kernel; profiles/r02_launches_bench.csv)
+    gpu_launches = (agent.launches - calls0[0]) * KERNELS_PER_ACT + (env.launches - calls0[1]) * KERNELS_PER_ENV_STEP
     total_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
     # the split of a step into policy and env kernel time, from a second pass with an event between the two phases
     # (that event serialises them, so act_ms + env_ms is slightly more than a step of the timed pass)
@@ -429,29 +448,31 @@ def run_ours(args):
 
     # roofline of the dominant kernel (the fused env step), from the flushed per-step events
     peak, peak_src = measured_peak()
-    bytes_per_launch = algorithmic_bytes_per_env_step() * E
+    bytes_per_launch = algorithmic_bytes_per_env_step(51, N, Fout) * E
     env_kernel_s = env_ms * 1e-3 / K
     achieved = bytes_per_launch / env_kernel_s / 1e9
+    off = offline_ncu("hrp_step_kernel")   # counters of an ncu capture committed under profiles/ (not measured in this run)
     roofline = {"bound": "hbm", "kernel": "hrp_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one 4096-env launch, ncu --set full
-                # (profiles/r01_step_kernel_v3_ncu_full.csv): the 64-slot state arena is read once, writes stay in L2
-                "traffic": int(12_756_000 * E / 4096), "peak_source": peak_src,
+                "traffic": None if off is None else int(off["dram_bytes_per_env"] * E),
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_us": env_kernel_s * 1e6,
                 "share_of_step": env_ms / (env_ms + act_ms),
-                # the binding resource: warp-instruction issue slots.  1.018e8 warp instructions per 4096-env launch
-                # (ncu smsp__inst_executed.sum, profiles/r01_step_kernel_*), 4 schedulers x 148 SMs x sm clock
-                "issue": {"warp_instructions_per_launch": 1.018e8 * E / 4096,
-                          "achieved_ginst_s": 1.018e8 * E / 4096 / env_kernel_s / 1e9,
-                          "peak_ginst_s": 4 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6 / 1e9,
-                          "frac": 1.018e8 * E / 4096 / env_kernel_s / (4 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6)},
                 "note": "instruction-issue-bound kernel (15 fused substeps per launch), not HBM-bound; see DESIGN.md 3.1"}
+    if off is not None:
+        # the binding resource: warp-instruction issue slots (4 schedulers x 148 SMs x sm clock)
+        wi = off["warp_instructions_per_env"] * E
+        peak_issue = 4 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6
+        roofline["traffic_source"] = roofline_src = off["source"]
+        roofline["issue"] = {"warp_instructions_per_launch": wi, "source": roofline_src + " (offline ncu capture, scaled by envs)",
+                             "achieved_ginst_s": wi / env_kernel_s / 1e9, "peak_ginst_s": peak_issue / 1e9,
+                             "frac": wi / env_kernel_s / peak_issue}
 
     # e2e: the same step through the host-buffer API (pinned host obs -> policy -> host actions -> env -> host obs)
     e2e = None
     if not args.no_e2e:
         Ke = min(K, 200)
-        obs_h = torch.zeros((E, 15, 4), dtype=torch.float32).pin_memory()
+        obs_h = torch.zeros((E, N, Fout), dtype=torch.float32).pin_memory()
         act_h = torch.zeros((E, 2), dtype=torch.float32).pin_memory()
         rew_h = torch.zeros(E, dtype=torch.float32).pin_memory().numpy()
         te_h = torch.zeros(E, dtype=torch.uint8).pin_memory().numpy()
@@ -484,27 +505,73 @@ def run_ours(args):
                "h2d_bytes_per_step": E * S * 4, "d2h_bytes_per_step": E * 2 * 4 + E * S * 4 + E * 4 + 2 * E,
                "steps": Ke, "api": "PPOAgent.act on a pinned-host observation + VecEnv.step_host (hrp_env_step_host_on): the device action feeds the step, the host receives action, observation, reward and flags"}
 
-    # PPO iteration (rollout of T steps + update: 8 epochs of 4096-sample minibatches, gradient all-reduce if N > 1)
+    # PPO iteration (rollout of T steps + update: epochs x minibatches, gradient exchange if N > 1)
     ppo = None
     if not args.no_ppo:
+        from highway_rope_ppo_b200.training.routine import collect_rollout
+
         T = args.rollout
         o = env.reset(42)
         _, o = rollout_and_update(env, agent, T, obs=o)  # warm-up
         barrier()
-        e0.record()
         iters = 2
-        for _ in range(iters):
-            m, o = rollout_and_update(env, agent, T, obs=o)
-        e1.record()
+        evp = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(iters)]
+        for it in range(iters):   # rollout_and_update, with an event between its two halves
+            evp[it][0].record()
+            r = collect_rollout(env, agent, T, o)
+            o = r["states"][T].clone()
+            _, _, last_v = agent.actor_critic.forward(o)
+            evp[it][1].record()
+            m = agent.update(last_value=last_v.view(-1))
+            evp[it][2].record()
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        t = torch.tensor([sum(e[0].elapsed_time(e[2]) for e in evp), sum(e[1].elapsed_time(e[2]) for e in evp)],
+                         dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ppo = {"value": world * E * T * iters / (float(t.cpu()) * 1e-3), "unit": "samples/s", "rollout_T": T,
-               "epochs": 8, "minibatch": 4096, "last_loss": m["loss"],
+        tot_ms, upd_ms = (float(x) for x in t.cpu())
+        n_local = E * T
+        bs = min(args.minibatch, n_local)
+        opt_steps = args.epochs * ((n_local + bs - 1) // bs)
+        # useful fp32 FLOPs of one optimizer step on one rank: forward, input gradients, weight gradients of the three
+        # hidden GEMMs (the N = 2 / 1 heads are not GEMMs here); 3xTF32 executes three tensor-core passes per product
+        fwd = 2.0 * bs * (S * H + H * H + H * 2 * H)
+        dgrad = 2.0 * bs * (2 * H * H + H * H)
+        wgrad = 2.0 * bs * (S * H + H * H + 2 * H * H)
+        flops_step = fwd + dgrad + wgrad
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                tens_peak, tens_src = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        except Exception:
+            tens_peak, tens_src = 2250.0, "fallback (nominal dense bf16 2.25 PFLOP/s)"
+        step_us = upd_ms * 1e3 / (iters * opt_steps)
+        ach = flops_step / (step_us * 1e-6) / 1e12
+        ppo = {"value": world * E * T * iters / (tot_ms * 1e-3), "unit": "samples/s", "rollout_T": T,
+               "epochs": args.epochs, "minibatch": bs, "last_loss": m["loss"],
+               "update_ms": upd_ms / iters, "rollout_ms": (tot_ms - upd_ms) / iters, "optimizer_step_us": step_us,
                "cuda_graphs": agent._graph_state is not None, "backend": dist.get_backend() if world > 1 else None,
                "gradient_exchange": ("peer-memory kernel (hrp_clip_adam_step_p2p)" if agent._comm is not None else "nccl all_reduce") if world > 1 else None,
-               "definition": "T policy+env steps then PPOAgent.update (GAE, 8 epochs, clip+Adam), amortised"}
+               "definition": "T policy+env steps then PPOAgent.update (GAE, epochs x minibatches, clip+Adam), amortised",
+               "roofline_ppo": {"bound": "tensor", "kernel": "one optimizer step (forward + backward GEMMs, loss, clip + Adam)",
+                                "achieved": ach, "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak,
+                                "peak_source": tens_src, "useful_flops_per_step": flops_step,
+                                "note": "useful fp32 FLOPs / measured time of a whole optimizer step; kind::tf32 runs at half "
+                                        "the bf16 rate and 3xTF32 issues three passes per product, so 1/6 of this peak is "
+                                        "the ceiling of the arithmetic mode"}}
+        if world > 1:
+            # every rank must hold bit-identical parameters after the sharded updates (same reduced gradient, same Adam)
+            flat = agent.actor_critic.flat
+            digest = torch.stack([flat.double().sum(), (flat.double() * torch.arange(1, flat.numel() + 1, device=dev,
+                                                                                    dtype=torch.float64)).sum()])
+            lo, hi = digest.clone(), digest.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            ref = flat.clone()
+            dist.broadcast(ref, src=0)
+            same = torch.tensor([1 if torch.equal(ref, flat) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            ppo["ranks_bit_identical"] = bool(int(same.item()) == 1 and torch.equal(lo, hi))
+            assert ppo["ranks_bit_identical"], "parameters differ between ranks after the sharded PPO updates"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -512,12 +579,21 @@ def run_ours(args):
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{r['envs']} envs x {r['steps']} policy steps ({r['seconds']:.1f} s), oracle C restatement of "
                          "highway-env 1.10.1 (OpenMP over envs) + torch CPU policy forward"}
+        if not args.no_ppo:
+            upd = cpu_ppo_update(args, 2 * args.minibatch)
+            cpu["ppo_samples_per_s"] = {
+                "value": cpu_ppo_samples_per_s(args, r["value"], upd), "unit": "samples/s", "kind": "port", "cores": upd["cores"],
+                "update_s_per_sample": upd["s_per_sample"],
+                "sample": f"update: {upd['samples']} stored samples, {upd['optimizer_steps']} optimizer steps of "
+                          f"{min(args.minibatch, upd['samples'])} ({upd['seconds']:.2f} s), torch fp32 autograd restatement of "
+                          f"ppo/agent.py:196-252 pinned to the reference agent's fixtures (S={upd['state_dim']}, "
+                          f"H={upd['hidden_dim']}); rollout: the CPU env-steps/s above"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (x, lane-change timer f64)", "data": "synthetic", "config": workload_config(args),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": K * (KERNELS_PER_ACT + KERNELS_PER_ENV_STEP),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "value_back_to_back_l2_warm": warm_value, "env_only_steps_per_s": env_only,
                 "policy_ms_per_step": act_ms / K, "env_ms_per_step": env_ms / K, "ppo_samples_per_s": ppo,

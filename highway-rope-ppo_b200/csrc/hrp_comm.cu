@@ -200,7 +200,9 @@ int hrp_clip_adam_step_p2p(hrp_comm *c, float *params, float *exp_avg, float *ex
         hrp_set_error("hrp_clip_adam_step_p2p: bad arguments (hrp_comm_connect first)");
         return -1;
     }
-    static int max_ctas = 0;
+    static int max_ctas_dev[HRP_MAX_DEVICES] = {0};
+    if (c->device < 0 || c->device >= HRP_MAX_DEVICES) { hrp_set_error("device index %d not supported", c->device); return -1; }
+    int &max_ctas = max_ctas_dev[c->device];
     if (max_ctas == 0) {
         int sms = 0, per_sm = 0;
         HRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));

@@ -10,6 +10,7 @@
 #define HRP_STEP_CTAS_PER_SM 7  // 28 envs per SM: 4096 envs fill 148 SMs in one wave (<= 72 registers)
 #define HRP_WARPS_PER_CTA_F64 2  // the fp64 validation instantiation: its per-warp shared-memory block is twice as large
 #define HRP_FULL 0xffffffffu
+#define HRP_MAX_DEVICES 64  // per-device caches of launch configuration
 
 typedef unsigned long long ull;
 

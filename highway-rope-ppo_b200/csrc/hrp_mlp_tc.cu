@@ -637,11 +637,15 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
     constexpr int OPERANDS = STAGES * PARTS * (A_TILE_BYTES + BN * BK * 4);
     constexpr int EPILOGUE = BM * (BN + 4) * 4;
     constexpr int SMEM = (OPERANDS > EPILOGUE ? OPERANDS : EPILOGUE) + 1024;
-    static bool configured = false;
+    // the attribute is per device (a process may drive several GPUs)
+    static bool configured[HRP_MAX_DEVICES] = {false};
     auto kern = tc_gemm_kernel<AMODE, BMODE, NSPLIT, BN, ASYNC>;
-    if (!configured) {
+    int dev = 0;
+    HRP_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= HRP_MAX_DEVICES) { hrp_set_error("device index %d not supported", dev); return -1; }
+    if (!configured[dev]) {
         HRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        configured = true;
+        configured[dev] = true;
     }
     HRP_CUDA_OK(hrp_launch_pdl(kern, grid, dim3(TC_LAUNCH_THREADS), (size_t)SMEM, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc,
                                bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2));

@@ -302,16 +302,16 @@ heads_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const f
 
 // heads + ActorCritic.get_action (agent.py:56-74) in one pass for the rollout: one warp per row forms mean[A] and
 // value from the two hidden activations (all loads of the row in flight together), then lane a < A samples
-// z_a = mean_a + std_a * n_a with n ~ N(0,1) from Philox4x32-10(counter = (row, draw), key = seed) through
+// z_a = mean_a + std_a * n_a with n ~ N(0,1) from Philox4x32-10(counter = (global row, draw), key = seed) through
 // Box-Muller (or takes n from noise[], or n = 0 when deterministic) and writes tanh(z_a), z_a; the log-prob terms of
 // the A lanes are added by shuffles.
 __global__ void __launch_bounds__(256)
 heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const float *__restrict__ wa2,
                  const float *__restrict__ ba2, const float *__restrict__ wc2, const float *__restrict__ bc2,
                  const float *__restrict__ log_std, const float *__restrict__ noise, int mode /*0 det, 1 noise[], 2 philox*/,
-                 unsigned long long seed, unsigned long long draw, int ld, long long B, int H, int A,
-                 float *__restrict__ action, float *__restrict__ pre_tanh, float *__restrict__ log_prob,
-                 float *__restrict__ value)
+                 unsigned long long seed, unsigned long long draw, unsigned long long row_base, int ld, long long B,
+                 int H, int A, float *__restrict__ action, float *__restrict__ pre_tanh,
+                 float *__restrict__ log_prob, float *__restrict__ value)
 {
     hrp_pdl_release();
     hrp_pdl_wait();
@@ -340,7 +340,10 @@ heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, con
     float nrm = 0.f;
     if (mode == 2) {
         uint32_t r[4];
-        hrp_philox((uint32_t)b, (uint32_t)((unsigned long long)b >> 32), (uint32_t)draw, (uint32_t)(draw >> 32),
+        // the counter is the GLOBAL row (row_base = first global env id of this shard): the shards of a sharded
+        // rollout draw different noise, and together exactly what one process over all envs would draw
+        const unsigned long long gb = row_base + (unsigned long long)b;
+        hrp_philox((uint32_t)gb, (uint32_t)(gb >> 32), (uint32_t)draw, (uint32_t)(draw >> 32),
                    (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5A5A5A5Au, r);
         const uint32_t r1 = a < 2 ? r[0] : r[2], r2 = a < 2 ? r[1] : r[3];
         float u1 = ((float)(r1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
@@ -779,15 +782,15 @@ static int forward_impl(hrp_ppo *h, const float *params, const float *x, long lo
 }
 
 static int act_impl(hrp_ppo *h, const float *params, const float *states, const float *noise, int mode,
-                    unsigned long long seed, unsigned long long draw, long long batch, float *action, float *pre_tanh,
-                    float *log_prob, float *value, cudaStream_t s)
+                    unsigned long long seed, unsigned long long draw, unsigned long long row_base, long long batch,
+                    float *action, float *pre_tanh, float *log_prob, float *value, cudaStream_t s)
 {
     const Layout &L = h->L;
     if (int rc = forward_impl(h, params, states, batch, nullptr, nullptr, s)) return rc;
     HRP_CUDA_OK(hrp_launch_pdl(heads_act_kernel, dim3((unsigned)((batch + 7) / 8)), dim3(256), 0, s, (const float *)h->ac,
                                (const float *)(h->ac + L.H), params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2,
-                               params + L.log_std, noise, mode, seed, draw, 2 * L.H, (long long)batch, L.H, L.A, action,
-                               pre_tanh, log_prob, value));
+                               params + L.log_std, noise, mode, seed, draw, row_base, 2 * L.H, (long long)batch, L.H, L.A,
+                               action, pre_tanh, log_prob, value));
     return 0;
 }
 
@@ -887,16 +890,17 @@ int hrp_ppo_act(hrp_ppo *h, const float *params, const float *states, const floa
 {
     if (!h || !params || !states || !action || !pre_tanh || !value) { hrp_set_error("hrp_ppo_act: null argument"); return -1; }
     if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
-    return act_impl(h, params, states, noise, noise ? 1 : 0, 0ull, 0ull, batch, action, pre_tanh, log_prob, value,
+    return act_impl(h, params, states, noise, noise ? 1 : 0, 0ull, 0ull, 0ull, batch, action, pre_tanh, log_prob, value,
                     (cudaStream_t)stream);
 }
 
-int hrp_ppo_act_sample(hrp_ppo *h, const float *params, const float *states, uint64_t seed, uint64_t draw, int64_t batch,
-                       float *action, float *pre_tanh, float *log_prob, float *value, void *stream)
+int hrp_ppo_act_sample(hrp_ppo *h, const float *params, const float *states, uint64_t seed, uint64_t draw,
+                       uint64_t row_base, int64_t batch, float *action, float *pre_tanh, float *log_prob, float *value,
+                       void *stream)
 {
     if (!h || !params || !states || !action || !pre_tanh || !value) { hrp_set_error("hrp_ppo_act_sample: null argument"); return -1; }
     if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
-    return act_impl(h, params, states, nullptr, 2, seed, draw, batch, action, pre_tanh, log_prob, value,
+    return act_impl(h, params, states, nullptr, 2, seed, draw, row_base, batch, action, pre_tanh, log_prob, value,
                     (cudaStream_t)stream);
 }
 
@@ -1023,10 +1027,14 @@ int hrp_clip_adam_step(float *params, const float *grad, float *exp_avg, float *
         return -1;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    static int max_ctas = 0;
+    // per device: a process may drive several GPUs (ExperimentRunner with a device pool)
+    static int max_ctas_dev[HRP_MAX_DEVICES] = {0};
+    int dev = 0;
+    HRP_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= HRP_MAX_DEVICES) { hrp_set_error("device index %d not supported", dev); return -1; }
+    int &max_ctas = max_ctas_dev[dev];
     if (max_ctas == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        HRP_CUDA_OK(cudaGetDevice(&dev));
+        int sms = 0, per_sm = 0;
         HRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         HRP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_adam_kernel, ADAM_THREADS, 0));
         max_ctas = sms * per_sm < ADAM_MAX_CTAS ? sms * per_sm : ADAM_MAX_CTAS;

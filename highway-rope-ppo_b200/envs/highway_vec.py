@@ -153,6 +153,7 @@ class HighwayVecEnv:
         tptr = None if table is None else table.ctypes.data
         h = C.c_void_p()
         self.real64 = bool(real64)
+        self.env_id_base = int(env_id_base)
         _lib.check(lib.hrp_env_create_ex(C.byref(self.cfg), tptr, 0 if table is None else table.size, self.num_envs,
                                          int(env_id_base), self.dev_index, 1 if self.real64 else 0, C.byref(h)),
                    "hrp_env_create_ex")

@@ -93,9 +93,14 @@ class ActorCritic:
             off += n
         self._h = C.c_void_p()
         self.max_batch = 0
+        self.workspace_generation = 0   # bumped whenever the native workspace is re-created (CUDA-graph cache key)
         self._ensure_workspace(max_batch)
         self._noise_seed = int(torch.randint(0, 2**62, (1,)).item())
         self._draw = 0
+        # global index of row 0 of the batches this instance acts on (a shard's first global env id): the
+        # exploration noise is keyed by (seed, global row, draw), so shards draw different noise and a sharded
+        # rollout reproduces the single-process one
+        self.row_base = 0
 
     def _ensure_workspace(self, batch: int) -> None:
         if batch <= self.max_batch:
@@ -107,6 +112,7 @@ class ActorCritic:
         _lib.check(self._lib.hrp_ppo_create(self.state_dim, self.action_dim, self.hidden_dim, int(batch),
                                             self.device.index, C.byref(self._h)), "hrp_ppo_create")
         self.max_batch = int(batch)
+        self.workspace_generation += 1
 
     def __del__(self):  # pragma: no cover
         try:
@@ -198,7 +204,7 @@ class ActorCritic:
             # construction, so set_random_seeds() still fixes the rollout; one draw counter per call)
             self._draw += 1
             _lib.check(self._lib.hrp_ppo_act_sample(self._h, self.flat.data_ptr(), states.data_ptr(), self._noise_seed,
-                                                    self._draw, B, out["action"].data_ptr(),
+                                                    self._draw, int(self.row_base), B, out["action"].data_ptr(),
                                                     out["pre_tanh"].data_ptr(), out["log_prob"].data_ptr(),
                                                     out["value"].data_ptr(), self._stream()), "hrp_ppo_act_sample")
             return out
@@ -534,7 +540,8 @@ class PPOAgent:
         that the captured pointers stay valid.  The first epoch of a new configuration runs eagerly (it also
         warms every kernel variant before anything is captured)."""
         ac = self.actor_critic
-        key = (n, bs, world, ac._h.value, float(self.eps_clip), float(self.value_coef), float(self.entropy_coef),
+        # the workspace generation, not its address: a re-created workspace may reuse the freed one's address
+        key = (n, bs, world, ac.workspace_generation, float(self.eps_clip), float(self.value_coef), float(self.entropy_coef),
                float(self.max_grad_norm), self.optimizer.lr, self.optimizer.betas, self.optimizer.eps)
         st = self._graph_state
         if st is None or st["key"] != key:

@@ -157,6 +157,8 @@ def collect_rollout(vec_env, agent, T: int, obs: Optional[torch.Tensor] = None,
     the reference's reset-after-done loop (``routine.py:125-147``).
     """
     E, S, A = vec_env.num_envs, vec_env.N * vec_env.F_out, agent.actor_critic.action_dim
+    # exploration noise is keyed by the GLOBAL env id: a shard's rows start at its first global env
+    agent.actor_critic.row_base = int(getattr(vec_env, "env_id_base", 0))
     r = agent.memory.begin_rollout(T, E, S, A)
     states = r["states"]
     if obs is None:

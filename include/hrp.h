@@ -192,12 +192,14 @@ int hrp_ppo_forward(hrp_ppo *h, const float *params_dev, const float *states_dev
 int hrp_ppo_act(hrp_ppo *h, const float *params_dev, const float *states_dev, const float *noise_dev,
                 int64_t batch, float *action_dev, float *pre_tanh_dev, float *log_prob_dev,
                 float *value_dev, void *stream);
-/* the same with the standard normals drawn inside the kernel: Philox4x32-10 keyed by seed, counter = (row,
- * draw), Box-Muller.  The reference samples with torch's generator (Normal.sample, agent.py:64); the stream
- * differs, the distribution does not. */
+/* the same with the standard normals drawn inside the kernel: Philox4x32-10 keyed by seed, counter =
+ * (row_base + row, draw), Box-Muller.  row_base is the global index of this batch's first row (the shard's first
+ * global env id): a rollout sharded over ranks draws exactly the noise one process over all envs would draw.  The
+ * reference samples with torch's generator (Normal.sample, agent.py:64); the stream differs, the distribution does
+ * not. */
 int hrp_ppo_act_sample(hrp_ppo *h, const float *params_dev, const float *states_dev, uint64_t seed, uint64_t draw,
-                       int64_t batch, float *action_dev, float *pre_tanh_dev, float *log_prob_dev,
-                       float *value_dev, void *stream);
+                       uint64_t row_base, int64_t batch, float *action_dev, float *pre_tanh_dev,
+                       float *log_prob_dev, float *value_dev, void *stream);
 /* PPOMemory.compute_advantages (agent.py:126-138) over [T,E] (time-major), reverse scan.
  * last_value_dev[E]; done as uint8.  Outputs advantages[T,E] (float32), returns[T,E]. */
 int hrp_gae(const float *reward_dev, const float *value_dev, const uint8_t *done_dev,

@@ -103,11 +103,13 @@ def _priority(key, vehicles):
     return (0 if (vehicles and who & vehicles) else 1, -frame if frame < 250 else -999)
 
 
-def either_branch(o, st0, action, perm, got, tol, obs_tol, rew_tol, max_nodes=400, max_depth=10, why=None):
+def either_branch(o, st0, action, perm, got, tol, obs_tol, rew_tol, max_nodes=3000, max_depth=12, why=None):
     """Re-run the oracle step from ``st0`` with marginal decisions forced the other way; returns the forced keys
     under which the kernel's results equal the oracle's in full, or None.  Best-first search over sets of forced
     decisions: the node whose outcome differs least from the kernel's is expanded first (a flip that repairs one of
-    several differing vehicles leads on), its children ordered by `_priority`."""
+    several differing vehicles leads on), its children ordered by `_priority`.  A flip that leaves the oracle's
+    outcome bit-identical to its parent's (e.g. the contact test of two vehicles that have crashed already) is
+    not extended, one that takes the outcome further from the kernel's is not extended either."""
     import heapq
 
     o.record_margin(MARGIN)
@@ -118,13 +120,15 @@ def either_branch(o, st0, action, perm, got, tol, obs_tol, rew_tol, max_nodes=40
         o.force(forced)
         r, te, tr = o.step(action)
         want_obs, want_rows = o.observe(perm=perm, with_rows=True)
-        return compare(got, o, r, te, tr, want_obs, want_rows, tol, obs_tol, rew_tol), o.marginal()
+        st = o.get_state()
+        sig = hash(tuple(st[k].tobytes() for k in ("x", "y", "speed", "heading") + DISCRETE) + (want_rows.tobytes(),))
+        return compare(got, o, r, te, tr, want_obs, want_rows, tol, obs_tol, rew_tol), o.marginal(), sig
 
-    c, keys = run(())
+    c, keys, sig = run(())
     if c is not None:
-        heapq.heappush(heap, (c["score"], 0, tick, (), c, keys))
+        heapq.heappush(heap, (c["score"], 0, tick, (), c, keys, sig))
     while heap and nodes < max_nodes and found is None:
-        _, depth, _, forced, c, keys = heapq.heappop(heap)
+        _, depth, _, forced, c, keys, sig = heapq.heappop(heap)
         if depth >= max_depth:
             continue
         for k in sorted((k for k in keys if k not in forced), key=lambda k: _priority(k, c["vehicles"])):
@@ -133,13 +137,13 @@ def either_branch(o, st0, action, perm, got, tol, obs_tol, rew_tol, max_nodes=40
                 continue
             seen.add(nxt)
             nodes += 1
-            c2, keys2 = run(nxt)
+            c2, keys2, sig2 = run(nxt)
             if c2 is None:
                 found = nxt
                 break
-            if c2["score"] <= c["score"]:   # flips that take the outcome further away are not extended
+            if sig2 != sig and c2["score"] <= c["score"]:
                 tick += 1
-                heapq.heappush(heap, (c2["score"], depth + 1, tick, nxt, c2, keys2))
+                heapq.heappush(heap, (c2["score"], depth + 1, tick, nxt, c2, keys2, sig2))
             if nodes >= max_nodes:
                 break
     # leave the oracle on its own (unforced) outcome

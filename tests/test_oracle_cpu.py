@@ -504,3 +504,63 @@ def test_observation_order_decision(highway_config):
         a, b = list(rows[1:3]), list(swapped[1:3])
         assert sorted(a) == sorted(b) == [1, 2] and a != b
     o.record_margin(0.0)
+
+
+# ---------------------------------------------------------------- PPO at the swept / benchmarked widths
+def compact_of(vec, sizes):
+    """tools/gen_golden.py:compact -- per-tensor norms, 8 seeded projections, every 257th entry."""
+    v = np.asarray(vec, dtype=np.float64)
+    rng = np.random.default_rng(1234)
+    proj = np.array([float(rng.standard_normal(v.size) @ v) for _ in range(8)])
+    norms, off = [], 0
+    for n in sizes:
+        norms.append(float(np.sqrt((v[off:off + n] ** 2).sum())))
+        off += int(n)
+    return {"norms": np.array(norms), "proj": proj, "samples": np.asarray(vec, dtype=np.float32)[::257].copy()}
+
+
+def check_compact(vec, g, tag, atol, sizes):
+    """`vec` against the compact form stored under `tag`: samples and per-tensor norms within atol (absolute,
+    in units of the vector), projections within atol * sqrt(len)."""
+    c = compact_of(vec, sizes)
+    np.testing.assert_allclose(c["samples"], g[f"{tag}_samples"], atol=atol, rtol=0)
+    lim = atol * np.sqrt(np.maximum(np.asarray(sizes, dtype=np.float64), 1.0)) + 1e-5 * np.abs(g[f"{tag}_norms"])
+    assert np.all(np.abs(c["norms"] - g[f"{tag}_norms"]) <= lim), (tag, c["norms"], g[f"{tag}_norms"])
+    np.testing.assert_allclose(c["proj"], g[f"{tag}_proj"], atol=4 * atol * np.sqrt(len(vec)), rtol=1e-5)
+
+
+WIDE = sorted(os.path.basename(p)[len("ppo_wide_"):-4] for p in glob.glob(os.path.join(GOLDEN, "ppo_wide_*.npz")))
+
+
+def reference_init(S, A, H, seed):
+    """The reference's ActorCritic construction order (ppo/agent.py:22-42) under torch.manual_seed(seed)."""
+    import torch.nn as nn
+
+    torch.manual_seed(seed)
+    shared = nn.Sequential(nn.Linear(S, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU())
+    actor = nn.Sequential(nn.Linear(H, H), nn.ReLU(), nn.Linear(H, A))
+    critic = nn.Sequential(nn.Linear(H, H), nn.ReLU(), nn.Linear(H, 1))
+    parts = [torch.zeros(A)]
+    for seq in (shared, actor, critic):
+        parts += [p.detach().reshape(-1) for p in seq.parameters()]
+    return torch.cat(parts)
+
+
+@pytest.mark.parametrize("name", WIDE)
+def test_ppo_oracle_matches_reference_at_swept_widths(name):
+    """hidden_dim 128 / 256 / 384 (main.py:52) and 512 (BASELINE configs[3]), state_dim up to 600 (configs[2])."""
+    g = golden(f"ppo_wide_{name}.npz")
+    S, A, H, B, seed = (int(v) for v in g["dims"])
+    sizes = g["sizes"]
+    flat = reference_init(S, A, H, seed)
+    assert np.array_equal(compact_of(flat.numpy(), sizes)["samples"], g["params0_samples"])
+    assert abs(float(flat.double().sum()) - float(g["params0_sum"])) < 1e-9
+    t = lambda k: torch.from_numpy(g[k])
+    mean, log_std, value = ppo_ref.forward(flat, t("states"), S, A, H)
+    np.testing.assert_allclose(mean.numpy(), g["mean"], atol=2e-6)
+    np.testing.assert_allclose(value.numpy(), g["value"], atol=2e-6)
+    r = ppo_ref.loss_and_grad(flat, t("states"), t("pre_tanh"), t("old_logp"), t("adv"), t("ret"), S, A, H)
+    assert abs(r["loss"] - float(g["loss"])) < 1e-5 and abs(r["clip_fraction"] - float(g["clip_fraction"])) < 1e-7
+    check_compact(r["grad"].numpy(), g, "grads", 2e-6 * max(1.0, float(g["grad_absmax"])), sizes)
+    p1, m, v, total = ppo_ref.clip_adam(flat, r["grad"], torch.zeros_like(flat), torch.zeros_like(flat), 1)
+    assert abs(total - float(g["total_norm"])) < 1e-4 * max(1.0, total)

@@ -253,6 +253,30 @@ def test_in_kernel_sampling_is_standard_normal_and_self_consistent():
     assert torch.equal(b.act(x)["pre_tanh"], out1["pre_tanh"])
 
 
+def test_sharded_sampling_equals_single_process_sampling():
+    """The exploration noise is keyed by (seed, GLOBAL row, draw): two shards acting on rows [0, B/2) and [B/2, B)
+    with their row_base draw exactly what one process draws for rows [0, B), and NOT the same noise as each other."""
+    torch.manual_seed(5)
+    whole = _agent(60, 2, 64, 4096)
+    x = torch.randn(4096, 60, device="cuda:0") * 0.3
+    want = {k: v.clone() for k, v in whole.act(x).items()}
+    parts = []
+    for r in range(2):
+        torch.manual_seed(5)                       # every rank seeds identically (set_random_seeds)
+        shard = _agent(60, 2, 64, 2048)
+        shard.actor_critic.row_base = 2048 * r
+        parts.append({k: v.clone() for k, v in shard.act(x[2048 * r:2048 * (r + 1)]).items()})
+    for k in ("pre_tanh", "action", "log_prob"):
+        assert torch.equal(torch.cat([parts[0][k], parts[1][k]]), want[k]), k
+    mean, std, _ = whole.actor_critic.forward(x)
+    n = (want["pre_tanh"] - mean) / std
+    assert abs(float((n[:2048] * n[2048:]).mean())) < 0.05      # the two shards' noise is independent
+    # a graph captured against one workspace must not survive its re-creation
+    g0 = whole.actor_critic.workspace_generation
+    whole.actor_critic._ensure_workspace(8192)
+    assert whole.actor_critic.workspace_generation == g0 + 1
+
+
 def test_loads_a_checkpoint_written_by_the_reference_agent():
     """tests/golden/checkpoint_ref_s12_h16.pth was written by the reference's PPOAgent.save (agent.py:310-318) after
     one update; dims are inferred the way visualize.py:53-58 does.  Outputs must match the reference network's, the
@@ -337,3 +361,89 @@ def test_peer_memory_adam_step_with_one_rank_equals_the_plain_step():
     assert lib.hrp_comm_create(9, 0, n, 0, C.byref(comm), handle) == -1      # more ranks than one box holds
     assert lib.hrp_clip_adam_step_p2p(None, pa.data_ptr(), ma.data_ptr(), va.data_ptr(), sa.data_ptr(), 3e-4, 0.9, 0.999,
                                       1e-8, 0.5, scr_a.data_ptr(), st) == -1
+
+
+# ---- the swept and benchmarked widths (main.py:50-58: hidden_dim 128 / 256 / 384, batch 32 / 64; BASELINE configs[2..3]:
+# ---- hidden_dim 512, state_dim 240 / 360 / 600), pinned to fixtures the reference's own agent produced
+def _compact_of(vec, sizes):
+    v = np.asarray(vec, dtype=np.float64)
+    rng = np.random.default_rng(1234)
+    proj = np.array([float(rng.standard_normal(v.size) @ v) for _ in range(8)])
+    norms, off = [], 0
+    for n in sizes:
+        norms.append(float(np.sqrt((v[off:off + n] ** 2).sum())))
+        off += int(n)
+    return {"norms": np.array(norms), "proj": proj, "samples": np.asarray(vec, dtype=np.float32)[::257].copy()}
+
+
+def _check_compact(vec, g, tag, atol, sizes):
+    c = _compact_of(vec, sizes)
+    np.testing.assert_allclose(c["samples"], g[f"{tag}_samples"], atol=atol, rtol=0)
+    lim = atol * np.sqrt(np.maximum(np.asarray(sizes, dtype=np.float64), 1.0)) + 1e-4 * np.abs(g[f"{tag}_norms"])
+    assert np.all(np.abs(c["norms"] - g[f"{tag}_norms"]) <= lim), (tag, c["norms"], g[f"{tag}_norms"])
+    np.testing.assert_allclose(c["proj"], g[f"{tag}_proj"], atol=4 * atol * np.sqrt(len(vec)), rtol=1e-4)
+
+
+import glob  # noqa: E402
+import os  # noqa: E402
+
+from conftest import GOLDEN  # noqa: E402
+
+_WIDE = sorted(os.path.basename(p)[len("ppo_wide_"):-4] for p in glob.glob(os.path.join(GOLDEN, "ppo_wide_*.npz")))
+
+
+@pytest.mark.parametrize("name", _WIDE)
+def test_swept_widths_match_reference(name):
+    g = golden(f"ppo_wide_{name}.npz")
+    S, A, H, B, seed = (int(v) for v in g["dims"])
+    sizes = g["sizes"]
+    torch.manual_seed(seed)
+    agent = _agent(S, A, H, B)
+    ac = agent.actor_critic
+    flat0 = ac.flat.cpu().numpy()
+    assert np.array_equal(flat0[::257], g["params0_samples"])            # same initialisation stream as the reference
+    assert abs(float(flat0.astype(np.float64).sum()) - float(g["params0_sum"])) < 1e-9
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    mean, std, value = ac.forward(cu("states"))
+    np.testing.assert_allclose(mean.cpu().numpy(), g["mean"], atol=2e-5)
+    np.testing.assert_allclose(value.cpu().numpy(), g["value"], atol=2e-5)
+    logp, _, _ = ac.evaluate(cu("states"), None, cu("pre_tanh"))
+    np.testing.assert_allclose(logp.cpu().numpy(), g["logp"], atol=5e-5, rtol=1e-5)
+    flat = {"states": cu("states"), "pre_tanh": cu("pre_tanh"), "log_prob": cu("old_logp"), "adv": cu("adv"),
+            "ret": cu("ret")}
+    agent._metrics.zero_()
+    agent._minibatch_step(flat, None, B, 1)
+    m = agent._metrics.cpu().numpy()
+    assert abs(m[0] - float(g["loss"])) < 2e-5 and abs(m[1] - float(g["actor_loss"])) < 2e-5
+    assert abs(m[2] - float(g["critic_loss"])) < 2e-5 * max(1.0, float(g["critic_loss"]))
+    assert abs(m[4] - float(g["clip_fraction"])) < 1e-6
+    _check_compact(agent.grad.cpu().numpy(), g, "grads", 1e-4 * float(g["grad_absmax"]) + 2e-6, sizes)
+    # Adam's first step: lr * g_clipped / (|g_clipped| + eps), ~ +-lr wherever |g| >> eps
+    step1 = ac.flat.cpu().numpy() - flat0
+    want = g["step1_samples"]
+    solid = np.abs(want) > 0.9 * 3e-4
+    assert solid.mean() > 0.3
+    np.testing.assert_allclose(step1[::257][solid], want[solid], atol=3e-6)
+
+
+def test_full_update_at_hidden_512_matches_reference():
+    """PPOAgent.update at BASELINE configs[3]'s hidden_dim (512 stored transitions, bs 64, 2 epochs = 16 optimizer steps)."""
+    g = golden("ppo_wideupdate_s60_h512_n512.npz")
+    S, A, H, n, bs, epochs, np_seed, seed = (int(v) for v in g["dims"])
+    torch.manual_seed(seed)
+    agent = _agent(S, A, H, bs, epochs=epochs)
+    flat0 = agent.actor_critic.flat.cpu().numpy()
+    assert np.array_equal(flat0[::257], g["params0_samples"])
+    for t in range(n):
+        agent.memory.store(g["states"][t], g["action"][t], g["pre_tanh"][t], float(g["reward"][t]), None,
+                           float(g["logp"][t]), bool(g["done"][t]), np.float32(g["value"][t]))
+    np.random.seed(np_seed)
+    metrics = agent.update(last_value=float(g["last_value"]))
+    want = dict(zip((str(k) for k in g["metric_names"]), g["metric_values"]))
+    for k in ("loss", "policy_loss", "value_loss", "entropy", "explained_variance"):
+        assert abs(metrics[k] - want[k]) <= 2e-3 * max(1.0, abs(want[k])), (k, metrics[k], want[k])
+    motion = agent.actor_critic.flat.cpu().numpy() - flat0
+    moved = float(np.abs(g["motion_samples"]).max())
+    err = float(np.abs(motion[::257] - g["motion_samples"]).max())
+    print("H=512 update: max parameter motion", moved, "max error of the sampled entries", err)
+    assert err <= 0.02 * moved + 1e-6

@@ -1,7 +1,11 @@
-"""GPU-box debugging aid: rerun an injected-state parity loop and print the worst offenders with context."""
+"""Dump one env-step of the state-injection parity run for offline analysis: the injected state, the action, the
+kernel's (fp32 and fp64 instantiation) and the oracle's outcome.
+
+    python tools/debug_parity.py <seed> <E> <gentle|random> <t> <env> [<t> <env> ...]  ->  gpurun_out/debug_case_*.npz
+"""
 import copy
-import sys
 import os
+import sys
 
 import numpy as np
 import torch
@@ -9,68 +13,38 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from oracle import highway as oh
-from highway_rope_ppo_b200.config.base_config import HIGHWAY_CONFIG
-from highway_rope_ppo_b200.envs.highway_vec import HighwayVecEnv
+import test_env_gpu as T  # noqa: E402
+from highway_rope_ppo_b200.config.base_config import HIGHWAY_CONFIG  # noqa: E402
+from oracle import highway as oh  # noqa: E402
 
-
-def stack(envs):
-    sts = [e.get_state() for e in envs]
-    out = {k: np.stack([s[k] for s in sts]) for k in oh.STATE_F64 + oh.STATE_I32}
-    out["time"] = np.array([s["time"] for s in sts])
-    return out
-
-
-def run(cfg, E, steps, seed, gentle, meta=False, label=""):
-    env = HighwayVecEnv(cfg, E, device="cuda:0", autoreset=False)
-    oracles = [oh.OracleEnv(cfg) for _ in range(E)]
+seed, E, kind = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+cases = [(int(sys.argv[i]), int(sys.argv[i + 1])) for i in range(4, len(sys.argv), 2)]
+fn = T._gentle_actions if kind == "gentle" else T._random_actions
+cfg = copy.deepcopy(HIGHWAY_CONFIG)
+oracles = [oh.OracleEnv(cfg) for _ in range(E)]
+for e, o in enumerate(oracles):
+    o.reset(seed, env_id=e, episode=0)
+rng = np.random.default_rng(seed)
+env32 = T._vec(cfg, 1, autoreset=False)
+env64 = T._vec(cfg, 1, autoreset=False, real64=True)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+for t in range(max(c[0] for c in cases) + 1):
+    actions = fn(rng, E, t).astype(np.float32)
     for e, o in enumerate(oracles):
-        o.reset(seed, env_id=e, episode=0)
-    rng = np.random.default_rng(seed)
-    shown = 0
-    for t in range(steps):
-        st = stack(oracles)
-        env.set_state(st)
-        a = rng.uniform(-1, 1, (E, 2))
-        if gentle:
-            a[:, 1] *= 0.08
-        if meta:
-            a[:, 0] = rng.integers(0, 5, E); a[:, 1] = 0
-        a = a.astype(np.float32)
-        env.step(torch.from_numpy(a).cuda())
-        got = env.get_state()
-        for e, o in enumerate(oracles):
-            r, te, tr = o.step(a[e])
-            ref = o.get_state()
-            m = o.min_margin()
-            for k in ("x", "y", "speed", "heading"):
-                err = np.abs(got[k][e] - ref[k])
-                j = int(err.argmax())
-                if err[j] > 2e-3 and shown < 12 and m >= 1e-3:
-                    shown += 1
-                    print(f"[{label}] t={t} e={e} field={k} veh={j} err={err[j]:.5f} margin={m:.2e} "
-                          f"before: x={st['x'][e][j]:.3f} y={st['y'][e][j]:.3f} v={st['speed'][e][j]:.3f} h={st['heading'][e][j]:.4f} "
-                          f"crashed={st['crashed'][e][j]} imp={st['has_impact'][e][j]} ({st['impact_x'][e][j]:.4f},{st['impact_y'][e][j]:.4f}) "
-                          f"lane={st['lane'][e][j]}->{st['target_lane'][e][j]} | ref after: x={ref['x'][j]:.4f} y={ref['y'][j]:.4f} v={ref['speed'][j]:.4f} "
-                          f"h={ref['heading'][j]:.5f} crashed={ref['crashed'][j]} imp={ref['has_impact'][j]} ({ref['impact_x'][j]:.4f},{ref['impact_y'][j]:.4f}) | "
-                          f"gpu after: x={got['x'][e][j]:.4f} y={got['y'][e][j]:.4f} v={got['speed'][e][j]:.4f} h={got['heading'][e][j]:.5f} "
-                          f"crashed={got['crashed'][e][j]} imp={got['has_impact'][e][j]} ({got['impact_x'][e][j]:.4f},{got['impact_y'][e][j]:.4f}) a={a[e]}")
-                    break
-            if te or tr:
-                o.reset(seed, env_id=e, episode=1 + t)
-    env.close()
-
-
-def c(**over):
-    cfg = copy.deepcopy(HIGHWAY_CONFIG)
-    for k, v in over.items():
-        if isinstance(v, dict):
-            cfg[k].update(v)
-        else:
-            cfg[k] = v
-    return cfg
-
-
-run(c(lanes_count=2, vehicles_count=12, vehicles_density=3, observation=dict(vehicles_count=5, see_behind=True)), 32, 30, 4, False, label="dense")
-m = c(); m["action"] = {"type": "DiscreteMetaAction"}
-run(m, 24, 40, 5, False, meta=True, label="meta")
+        if (t, e) in cases:
+            st = o.get_state()
+            out = {f"st0_{k}": st[k] for k in oh.STATE_F64 + oh.STATE_I32}
+            out["st0_time"], out["st0_steps"], out["action"] = st["time"], st["steps"], actions[e]
+            for name, env in (("k32", env32), ("k64", env64)):
+                full = {k: st[k][None] for k in oh.STATE_F64 + oh.STATE_I32}
+                full["time"] = np.array([st["time"]])
+                env.set_state(full)
+                env.step(torch.from_numpy(actions[e][None]).cuda())
+                got = env.get_state()
+                for k in oh.STATE_F64 + oh.STATE_I32:
+                    out[f"{name}_{k}"] = got[k][0]
+            np.savez(os.path.join(ROOT, "gpurun_out", f"debug_case_{kind}_{seed}_{t}_{e}.npz"), **out)
+        r, te, tr = o.step(actions[e])
+        if te or tr:
+            o.reset(seed, env_id=e, episode=1 + t)
+print("done")

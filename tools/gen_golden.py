@@ -12,7 +12,9 @@ Run once in the build container (the reference tree does not exist on the GPU bo
   fixture holds ``tanh(table).detach()`` computed from the reference-constructed table.
 * ``ppo_*.npz``: ``ppo/agent.py`` imported as is: initial parameters for a seed, one evaluate +
   loss + backward + clip + Adam step on a seeded minibatch, GAE on a seeded trajectory, and a
-  full ``PPOAgent.update`` (all metrics + final parameters).
+  full ``PPOAgent.update`` (all metrics + final parameters).  ``ppo_wide_*.npz`` / ``ppo_wideupdate_*.npz``: the
+  same at the swept and benchmarked widths (hidden_dim 128-512, state_dim 60-600, batch 32-4096), with the
+  parameter-sized vectors stored in compact form (per-tensor norms, random projections, samples).
 """
 import os
 import sys
@@ -231,6 +233,107 @@ def gen_ppo():
     print("ppo fixtures written")
 
 
+def compact(vec, sizes):
+    """Compact, size-independent description of a flat parameter-shaped vector (the swept widths have up to
+    1.2 M parameters; storing them in full would put tens of MB under tests/golden): the L2 norm of every
+    parameter tensor, 8 seeded float64 random projections, and every 257th entry."""
+    v = np.asarray(vec, dtype=np.float64)
+    rng = np.random.default_rng(1234)
+    proj = np.array([float(rng.standard_normal(v.size) @ v) for _ in range(8)])
+    norms, off = [], 0
+    for n in sizes:
+        norms.append(float(np.sqrt((v[off:off + n] ** 2).sum())))
+        off += n
+    return {"norms": np.array(norms), "proj": proj, "samples": np.asarray(vec, dtype=np.float32)[::257].copy(),
+            "sum": float(v.sum()), "sumsq": float((v ** 2).sum())}
+
+
+def gen_ppo_wide():
+    """ppo_wide_*.npz: the same one-minibatch fixture as ppo_step_* at the widths the reference sweeps
+    (main.py:50-58: hidden_dim 128 / 256 / 384, batch 32 / 64) and BASELINE.json benchmarks (hidden_dim 512;
+    state_dim 240 / 360 / 600 = 30 rows of F + d_embed), with parameters and gradients in compact() form; the
+    initial parameters are regenerated by the test from the seed and checked against their compact form."""
+    sys.path.insert(0, REF)
+    from ppo.agent import PPOAgent
+    import torch.nn as nn
+    import torch.nn.functional as Fn
+
+    torch.set_num_threads(8)
+    cases = {"s60_h128_b32": (60, 128, 32, 11), "s240_h384_b64": (240, 384, 64, 12), "s600_h512_b64": (600, 512, 64, 13),
+             "s60_h512_b32": (60, 512, 32, 14), "s600_h128_b64": (600, 128, 64, 15), "s360_h256_b32": (360, 256, 32, 16),
+             "s240_h256_b64": (240, 256, 64, 17), "s60_h384_b64": (60, 384, 64, 18),
+             "s60_h512_b4096": (60, 512, 4096, 19), "s600_h256_b512": (600, 256, 512, 20)}
+    for name, (S, H, B, seed) in cases.items():
+        A = 2
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        agent = PPOAgent(S, A, lr=3e-4, hidden_dim=H, batch_size=B, epochs=2)
+        ac = agent.actor_critic
+        sizes = [p.numel() for p in ac.parameters()]
+        p0 = flat_params(ac)
+        g = torch.Generator().manual_seed(seed + 1)
+        states = torch.randn(B, S, generator=g) * 0.5
+        mean, std, value = ac.forward(states)
+        noise = torch.randn(B, A, generator=g)
+        z = (mean + std * noise).detach()
+        z[0, 0] = 4.0
+        logp, v, ent = ac.evaluate(states, torch.tanh(z), z)
+        old_logp = (logp + 0.3 * torch.randn(B, generator=g)).detach()
+        adv = torch.randn(B, generator=g)
+        ret = torch.randn(B, generator=g)
+        new_logp, sv, entropy = ac.evaluate(states, torch.tanh(z), z)
+        ratios = torch.exp(new_logp - old_logp)
+        actor_loss = -torch.min(ratios * adv, torch.clamp(ratios, 1 - agent.eps_clip, 1 + agent.eps_clip) * adv).mean()
+        critic_loss = Fn.mse_loss(sv.squeeze(-1), ret)
+        loss = actor_loss + agent.value_coef * critic_loss - agent.entropy_coef * entropy.mean()
+        agent.optimizer.zero_grad()
+        loss.backward()
+        grads = np.concatenate([p.grad.detach().numpy().reshape(-1) for p in ac.parameters()])
+        total_norm = float(nn.utils.clip_grad_norm_(ac.parameters(), agent.max_grad_norm))
+        agent.optimizer.step()
+        p1 = flat_params(ac)
+        out = {"dims": np.array([S, A, H, B, seed]), "sizes": np.array(sizes), "states": states.numpy(),
+               "mean": mean.detach().numpy(), "value": value.detach().numpy(), "pre_tanh": z.numpy(),
+               "logp": logp.detach().numpy(), "old_logp": old_logp.numpy(), "adv": adv.numpy(), "ret": ret.numpy(),
+               "loss": float(loss), "actor_loss": float(actor_loss), "critic_loss": float(critic_loss),
+               "clip_fraction": float((torch.abs(ratios - 1) > agent.eps_clip).float().mean()),
+               "total_norm": total_norm, "grad_absmax": float(np.abs(grads).max())}
+        for tag, vec in (("params0", p0), ("grads", grads), ("step1", p1 - p0)):
+            for k, x in compact(vec, sizes).items():
+                out[f"{tag}_{k}"] = x
+        np.savez_compressed(os.path.join(OUT, f"ppo_wide_{name}.npz"), **out)
+    # a full update() at hidden_dim 512 (BASELINE configs[3]): 512 stored transitions, bs 64, 2 epochs
+    S, H, n, bs, epochs, seed = 60, 512, 512, 64, 2, 77
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    agent = PPOAgent(S, 2, lr=3e-4, hidden_dim=H, batch_size=bs, epochs=epochs)
+    sizes = [p.numel() for p in agent.actor_critic.parameters()]
+    p0 = flat_params(agent.actor_critic)
+    rng = np.random.default_rng(seed)
+    st = (rng.standard_normal((n, S)) * 0.5).astype(np.float32)
+    rew = rng.random(n)
+    done = rng.random(n) < 0.03
+    stored = {k: [] for k in ("action", "pre_tanh", "logp", "value")}
+    for t in range(n):
+        a, z, lp, v = agent.select_action(st[t])
+        agent.memory.store(st[t], a, z, float(rew[t]), st[t], lp, bool(done[t]), v)
+        for k, x in zip(("action", "pre_tanh", "logp", "value"), (a, z, lp, v)):
+            stored[k].append(x)
+    np.random.seed(seed + 100)
+    metrics = agent.update(last_value=0.25)
+    p1 = flat_params(agent.actor_critic)
+    out = {"dims": np.array([S, 2, H, n, bs, epochs, seed + 100, seed]), "sizes": np.array(sizes), "states": st, "reward": rew,
+           "done": done, "action": np.array(stored["action"], dtype=np.float32),
+           "pre_tanh": np.array(stored["pre_tanh"], dtype=np.float32), "logp": np.array(stored["logp"], dtype=np.float32),
+           "value": np.array(stored["value"], dtype=np.float32), "last_value": 0.25,
+           "metric_names": np.array(list(metrics)), "metric_values": np.array([metrics[k] for k in metrics])}
+    for tag, vec in (("params0", p0), ("motion", p1 - p0)):
+        for k, x in compact(vec, sizes).items():
+            out[f"{tag}_{k}"] = x
+    np.savez_compressed(os.path.join(OUT, "ppo_wideupdate_s60_h512_n512.npz"), **out)
+    print("wide ppo fixtures written")
+
+
 def gen_sweep():
     """Experiment names of the reference's full grid (main.py:42-88).  main.py builds a DevicePool and an
     ExperimentRunner (gymnasium + highway_env) when imported, so define_experiments is executed from its source
@@ -310,6 +413,9 @@ def gen_checkpoint():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--ppo-wide-only" in sys.argv:
+        gen_ppo_wide()
+        sys.exit(0)
     if "--extra-only" in sys.argv:
         sys.path.insert(0, REF)
         install_gymnasium_stub()
@@ -320,6 +426,7 @@ if __name__ == "__main__":
     gym = install_gymnasium_stub()
     gen_embed(gym)
     gen_ppo()
+    gen_ppo_wide()
     gen_sweep()
     gen_checkpoint()
     gen_result_schema()
