@@ -383,6 +383,21 @@ int hrp_env_reset_host(hrp_env *h, uint64_t seed, float *obs_host)
     return 0;
 }
 
+int hrp_env_set_trace(hrp_env *h, double *trace_dev)
+{
+    if (!h) { hrp_set_error("hrp_env_set_trace: null handle"); return -1; }
+    h->P.trace = trace_dev;
+    return 0;
+}
+int hrp_env_trace_shape(const hrp_env *h, int32_t *frames, int32_t *slots, int32_t *fields)
+{
+    if (!h) { hrp_set_error("hrp_env_trace_shape: null handle"); return -1; }
+    if (frames) *frames = h->P.frames;
+    if (slots) *slots = HRP_VS;
+    if (fields) *fields = HRP_TRACE_FIELDS;
+    return 0;
+}
+
 int hrp_env_get_state(hrp_env *h, hrp_state *d)
 {
     if (!h || !d) { hrp_set_error("hrp_env_get_state: null argument"); return -1; }

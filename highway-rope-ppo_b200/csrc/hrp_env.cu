@@ -900,7 +900,24 @@ __device__ __forceinline__ void step_body(const EnvDev &P, const float *__restri
     }
     __syncwarp();
 
-    for (int frame = 0; frame < P.frames; ++frame) simulate_frame(P, S, u, lane, xref);
+    for (int frame = 0; frame < P.frames; ++frame) {
+        simulate_frame(P, S, u, lane, xref);
+        if (P.trace) {   // validation aid: the intra-step trajectory, for the frame-by-frame parity check
+            double *t = P.trace + (((size_t)e * P.frames + frame) * HRP_VS) * HRP_TRACE_FIELDS;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int k = lane + 32 * q;
+                if (k < P.V) {
+                    const Veh<R> &w = u[q];
+                    double *r = t + (size_t)k * HRP_TRACE_FIELDS;
+                    r[0] = w.x; r[1] = (double)w.y; r[2] = (double)w.v; r[3] = (double)w.h;
+                    r[4] = (double)w.impx; r[5] = (double)w.impy;
+                    r[6] = (double)((uint32_t)w.lane | ((uint32_t)w.tlane << 8) | ((uint32_t)w.crashed << 16) |
+                                    ((uint32_t)w.has_impact << 17));
+                }
+            }
+        }
+    }
 
     // HighwayEnv._reward / _is_terminated / _is_truncated
     int done = 0;

@@ -42,7 +42,11 @@ struct EnvDev {
     void *y, *heading, *speed, *tspeed, *delta, *impx, *impy;   // float arrays, double arrays when real64
     uint32_t *flags;  // lane | target_lane<<8 | crashed<<16 | has_impact<<17
     uint32_t *episode, *obs_draw;
+    // validation aid (hrp_env_set_trace): when non-null, [E][frames][HRP_VS][HRP_TRACE_FIELDS] doubles receive every
+    // vehicle's state at the end of every simulation frame of a step (x, y, speed, heading, impact_x, impact_y, flags)
+    double *trace;
 };
+#define HRP_TRACE_FIELDS 7
 
 // Philox4x32-10 (Salmon et al. SC'11), the counter-based generator behind spawn and shuffle.
 __host__ __device__ __forceinline__ void hrp_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -14,6 +14,7 @@
 // all-reduce) touch one contiguous range.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "hrp_internal.cuh"
 
@@ -258,8 +259,8 @@ heads_wgrad_partial_kernel(const float *__restrict__ dmean, const float *__restr
 __global__ void gather_batch_kernel(const float *__restrict__ states, const float *__restrict__ pre_tanh,
                                     const float *__restrict__ olp, const float *__restrict__ adv,
                                     const float *__restrict__ ret, const long long *__restrict__ idx, long long B, int S,
-                                    int A, float *__restrict__ x, float *__restrict__ z, float *__restrict__ o_olp,
-                                    float *__restrict__ o_adv, float *__restrict__ o_ret)
+                                    int A, float *__restrict__ x, float *__restrict__ x_lo, float *__restrict__ z,
+                                    float *__restrict__ o_olp, float *__restrict__ o_adv, float *__restrict__ o_ret)
 {
     hrp_pdl_release();   // the first GEMM of the step sets itself up meanwhile (it waits before it reads x)
     const int W = S + A + 3;
@@ -268,11 +269,38 @@ __global__ void gather_batch_kernel(const float *__restrict__ states, const floa
     long long b = i / W;
     int c = (int)(i - b * W);
     long long src = idx[b];
-    if (c < S) x[b * S + c] = states[(size_t)src * S + c];
+    if (c < S) {
+        const float v = states[(size_t)src * S + c];
+        x[b * S + c] = v;
+        x_lo[b * S + c] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // the TMA GEMM's pre-split operand
+    }
     else if (c < S + A) z[b * A + (c - S)] = pre_tanh[(size_t)src * A + (c - S)];
     else if (c == S + A) o_olp[b] = olp[src];
     else if (c == S + A + 1) o_adv[b] = adv[src];
     else o_ret[b] = ret[src];
+}
+
+// the weight operands of the TMA GEMMs (hrp_gemm_tma.cu): 16-byte aligned copies of shared.0 / shared.2 / the row-stacked
+// [actor_mean.0 ; critic.0] (the flat parameter buffer holds them at 8-byte aligned offsets, which a tensor map cannot
+// address), their 3xTF32 "lo" parts x - trunc_tf32(x), and the stacked bias [ba1 | bc1].  One launch per parameter
+// change (every optimizer step; once per rollout).
+__global__ void __launch_bounds__(256)
+prepare_weights_kernel(const float *__restrict__ params, Layout L, float *__restrict__ w1, float *__restrict__ w1_lo,
+                       float *__restrict__ w2, float *__restrict__ w2_lo, float *__restrict__ wac,
+                       float *__restrict__ wac_lo, float *__restrict__ bac)
+{
+    const long long n1 = (long long)L.H * L.S, n2 = (long long)L.H * L.H;
+    const long long total = n1 + 3 * n2 + 2 * L.H;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float v, *dst, *dlo = nullptr;
+    if (i < n1) { v = params[L.w1 + i]; dst = w1 + i; dlo = w1_lo + i; }
+    else if (i < n1 + n2) { long long j = i - n1; v = params[L.w2 + j]; dst = w2 + j; dlo = w2_lo + j; }
+    else if (i < n1 + 2 * n2) { long long j = i - n1 - n2; v = params[L.wa1 + j]; dst = wac + j; dlo = wac_lo + j; }
+    else if (i < n1 + 3 * n2) { long long j = i - n1 - 2 * n2; v = params[L.wc1 + j]; dst = wac + n2 + j; dlo = wac_lo + n2 + j; }
+    else { long long j = i - n1 - 3 * n2; v = j < L.H ? params[L.ba1 + j] : params[L.bc1 + j - L.H]; dst = bac + j; }
+    *dst = v;
+    if (dlo) *dlo = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -388,8 +416,9 @@ heads_loss_backward_kernel(const float *__restrict__ a1, const float *__restrict
                            const float *__restrict__ old_lp, const float *__restrict__ adv,
                            const float *__restrict__ ret, long long B, int A, float eps_clip, float value_coef,
                            float entropy_coef, float scale, float *__restrict__ dmean, float *__restrict__ dvalue,
-                           float *__restrict__ da1, float *__restrict__ dc1, float *__restrict__ dlog_std,
-                           float *__restrict__ metrics, float *__restrict__ part, unsigned *__restrict__ counter)
+                           float *__restrict__ da1, float *__restrict__ dc1, float *__restrict__ d_lo /* nullable */,
+                           float *__restrict__ dlog_std, float *__restrict__ metrics, float *__restrict__ part,
+                           unsigned *__restrict__ counter)
 {
     __shared__ float out_s[HLB_ROWS][5], dmean_s[HLB_ROWS][4], dvalue_s[HLB_ROWS];
     __shared__ float red[8][8];
@@ -503,8 +532,13 @@ heads_loss_backward_kernel(const float *__restrict__ a1, const float *__restrict
             float sacc = 0.f;
 #pragma unroll
             for (int a = 0; a < 4; ++a) sacc = fmaf(dmean_s[r][a], wk[a], sacc);
-            da1[o] = ma[r] > 0.f ? sacc : 0.f;
-            dc1[o] = mc[r] > 0.f ? dvalue_s[r] * wck : 0.f;
+            const float ga = ma[r] > 0.f ? sacc : 0.f, gc = mc[r] > 0.f ? dvalue_s[r] * wck : 0.f;
+            da1[o] = ga;
+            dc1[o] = gc;
+            if (d_lo) {   // the TMA GEMMs' pre-split operand: x - trunc_tf32(x), same [B, 2H] layout
+                d_lo[o] = ga - __uint_as_float(__float_as_uint(ga) & 0xFFFFE000u);
+                d_lo[o + (dc1 - da1)] = gc - __uint_as_float(__float_as_uint(gc) & 0xFFFFE000u);
+            }
         }
     }
     __syncthreads();
@@ -687,6 +721,12 @@ struct hrp_ppo {
     float *wt_ac, *wt_2;                     // transposed weights: [H, 2H] (actor_mean.0 | critic.0) and [H, H] (shared.2)
     float *part_w[3];                        // split-K partials of the three weight-gradient GEMMs
     float *part_b[3];                        // column-sum partials of the three bias gradients (<= 64 chunks)
+    // TMA GEMM path (hrp_gemm_tma.cu): "lo" twins of every GEMM operand and the prepared weight copies
+    float *x_lo, *h1_lo, *h2_lo, *ac_lo, *d12_lo, *dh2_lo, *dh1_lo;
+    float *w1p, *w1p_lo, *w2p, *w2p_lo, *wacp, *wacp_lo, *bacp;
+    bool tma_capable;                        // shapes / alignments a tensor map accepts
+    bool hold_prepared;                      // the prepared copies match `prepared_for` and may be reused
+    const float *prepared_for;
     float *part_h;                           // head-gradient partials (<= 64 chunks)
     float *loss_part;                        // heads_loss_backward_kernel partial sums [CTAs][8]
     unsigned *loss_counter;
@@ -702,6 +742,12 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
                 int accumulate, int splits, int nsplit, cudaStream_t s, int nseg = 0, const float *B2 = nullptr,
                 const float *bias2 = nullptr);
+
+// TMA-fed 3xTF32 path on pre-split operands (hrp_gemm_tma.cu)
+int hrp_tma_gemm(int M, int N, int K, const float *A, const float *A_lo, long long sam, long long sak, const float *B,
+                 const float *B_lo, long long sbn, long long sbk, float *C, float *C_lo, int ldc, const float *bias, int relu,
+                 const float *mask, int ldm, int splits, int bn_hint, cudaStream_t s);
+int hrp_split_lo(const float *x, float *lo, long long n, cudaStream_t s);
 
 // math mode of the hidden-layer GEMMs: 0 = fp32 SIMT, 1 = TF32 tcgen05, 3 = 3xTF32 tcgen05 (default)
 static int g_math_mode = 3;
@@ -757,6 +803,32 @@ static int colsum(ReducePlan &plan, float *part, const float *G, int ldg, long l
     return 0;
 }
 
+static bool use_tma(const hrp_ppo *h) { return g_math_mode == 3 && h->tma_capable && !getenv("HRP_NO_TMA"); }
+
+// aligned weight copies + lo parts + stacked bias for the TMA GEMMs; skipped while the caller holds them valid
+static int prepare_weights(hrp_ppo *h, const float *params, cudaStream_t s)
+{
+    if (h->hold_prepared && h->prepared_for == params) return 0;
+    const Layout &L = h->L;
+    const long long total = (long long)L.H * L.S + 3ll * L.H * L.H + 2 * L.H;
+    prepare_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(params, L, h->w1p, h->w1p_lo, h->w2p, h->w2p_lo,
+                                                                          h->wacp, h->wacp_lo, h->bacp);
+    HRP_CUDA_OK(cudaGetLastError());
+    h->prepared_for = params;
+    return 0;
+}
+
+// trunk + hidden head layers on the TMA path: x (and x_lo) -> h1, h2, ac = [a1 | c1], each with its lo twin
+static int forward_tma(hrp_ppo *h, const float *params, const float *x, const float *x_lo, long long B, cudaStream_t s)
+{
+    const Layout &L = h->L;
+    const int H = L.H, S = L.S, Bi = (int)B;
+    if (hrp_tma_gemm(Bi, H, S, x, x_lo, S, 1, h->w1p, h->w1p_lo, S, 1, h->h1, h->h1_lo, H, params + L.b1, 1, nullptr, 0, 1, 0, s) < 0) return -2;
+    if (hrp_tma_gemm(Bi, H, H, h->h1, h->h1_lo, H, 1, h->w2p, h->w2p_lo, H, 1, h->h2, h->h2_lo, H, params + L.b2, 1, nullptr, 0, 1, 0, s) < 0) return -2;
+    if (hrp_tma_gemm(Bi, 2 * H, H, h->h2, h->h2_lo, H, 1, h->wacp, h->wacp_lo, H, 1, h->ac, h->ac_lo, 2 * H, h->bacp, 1, nullptr, 0, 1, 0, s) < 0) return -2;
+    return 0;
+}
+
 // shared trunk and the two hidden head layers; the latter are one GEMM over the row-stacked weights
 // [actor_mean.0 ; critic.0] into h->ac = [a1 | c1]
 static int forward_impl(hrp_ppo *h, const float *params, const float *x, long long B, float *mean, float *value,
@@ -764,6 +836,17 @@ static int forward_impl(hrp_ppo *h, const float *params, const float *x, long lo
 {
     const Layout &L = h->L;
     int H = L.H, S = L.S, A = L.A, Bi = (int)B;
+    if (use_tma(h) && Bi >= 32) {
+        // external states: their lo part is formed here (inside the update it comes from the gather kernel)
+        if (int rc = prepare_weights(h, params, s)) return rc;
+        if (int rc = hrp_split_lo(x, h->x_lo, B * S, s)) return rc;
+        if (int rc = forward_tma(h, params, x, h->x_lo, B, s)) return rc;
+        if (!mean) return 0;
+        heads_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(h->ac, h->ac + H, params + L.wa2, params + L.ba2, params + L.wc2,
+                                                            params + L.bc2, 2 * H, B, H, A, mean, value);
+        HRP_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (gemm(false, true, Bi, H, S, x, S, params + L.w1, S, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
     if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s) < 0) return -2;
     if (g_math_mode != 0 && H % 64 == 0 && Bi >= 32) {
@@ -841,7 +924,10 @@ int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, in
     auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
     const size_t sizes[] = {B * S, B * A, B, B, B, B * H, B * H, 2 * B * H, B * A, B * A, B, B, 2 * B * H, B * H, B * H,
                             2 * H * H, H * H, cap * 2 * H * H, cap * H * H, cap * H * S, 64 * 2 * H, 64 * H, 64 * H,
-                            64 * ((A + 1) * H + A + 1), ((B + HLB_ROWS - 1) / HLB_ROWS) * 8, 32};
+                            64 * ((A + 1) * H + A + 1), ((B + HLB_ROWS - 1) / HLB_ROWS) * 8, 32,
+                            // lo twins (x, h1, h2, ac, d12, dh2, dh1) and prepared weights (w1, w2, wac: copy + lo; bac)
+                            B * S, B * H, B * H, 2 * B * H, 2 * B * H, B * H, B * H,
+                            H * S, H * S, H * H, H * H, 2 * H * H, 2 * H * H, 2 * H};
     size_t n = 0;
     for (size_t q : sizes) n += pad(q);
     cudaError_t ce = cudaMalloc(&h->ws, n * sizeof(float));
@@ -858,6 +944,13 @@ int hrp_ppo_create(int32_t state_dim, int32_t action_dim, int32_t hidden_dim, in
     for (int q = 0; q < 3; ++q) h->part_b[q] = take();
     h->part_h = take(); h->loss_part = take();
     h->loss_counter = (unsigned *)take();
+    h->x_lo = take(); h->h1_lo = take(); h->h2_lo = take(); h->ac_lo = take(); h->d12_lo = take(); h->dh2_lo = take();
+    h->dh1_lo = take();
+    h->w1p = take(); h->w1p_lo = take(); h->w2p = take(); h->w2p_lo = take(); h->wacp = take(); h->wacp_lo = take();
+    h->bacp = take();
+    // a tensor map needs 16-byte aligned row pitches; tiles of 32 / 64 columns
+    h->tma_capable = hidden_dim % 32 == 0 && state_dim % 4 == 0;
+    h->hold_prepared = false; h->prepared_for = nullptr;
     ce = cudaMemset(h->loss_counter, 0, 32 * sizeof(float));
     for (int q = 0; q < 2 && ce == cudaSuccess; ++q) ce = cudaStreamCreateWithFlags(&h->side[q], cudaStreamNonBlocking);
     for (int q = 0; q < 8 && ce == cudaSuccess; ++q) ce = cudaEventCreateWithFlags(&h->ev[q], cudaEventDisableTiming);
@@ -956,6 +1049,83 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         cudaError_t ce = cudaEventRecord(h->ev[e], from);
         return ce != cudaSuccess ? ce : cudaStreamWaitEvent(to, h->ev[e], 0);
     };
+    h->hold_prepared = false;   // the caller is about to change the parameters (optimizer step)
+    if (use_tma(h) && Bi >= 32) {
+        // ---- TMA path: every GEMM operand has a "lo" twin written by its producer; the weight-gradient GEMMs read
+        // the batch-major activations as MN-major operands and the input-gradient GEMMs read W[out, in] as the
+        // MN-major B operand (no transposed copies).
+        HRP_CUDA_OK(after(0, s, s1));
+        if (int rc = prepare_weights(h, params, s1)) return rc;          // side 1: needs the parameters only
+        HRP_CUDA_OK(cudaEventRecord(h->ev[3], s1));
+        const float *x_lo = h->x_lo;
+        if (idx) {
+            const long long *ix = (const long long *)idx;
+            long long tot = B * (S + A + 3);
+            gather_batch_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(states, pre_tanh, old_log_prob, adv, ret, ix,
+                                                                             B, S, A, h->x, h->x_lo, h->z, h->olp, h->adv,
+                                                                             h->ret);
+            HRP_CUDA_OK(cudaGetLastError());
+            x = h->x; z = h->z; olp = h->olp; ad = h->adv; rt = h->ret;
+        } else {
+            if (int rc = hrp_split_lo(x, h->x_lo, B * S, s)) return rc;
+        }
+        HRP_CUDA_OK(cudaStreamWaitEvent(s, h->ev[3], 0));
+        if (int rc = forward_tma(h, params, x, x_lo, B, s)) return rc;
+        HRP_CUDA_OK(hrp_launch_pdl(heads_loss_backward_kernel, dim3((unsigned)((B + HLB_ROWS - 1) / HLB_ROWS)), dim3(256), 0, s,
+                                   (const float *)h->ac, (const float *)(h->ac + H), H2, H, params + L.wa2, params + L.ba2,
+                                   params + L.wc2, params + L.bc2, params + L.log_std, z, olp, ad, rt, B, A, eps_clip,
+                                   value_coef, entropy_coef, loss_scale, h->dmean, h->dvalue, h->d12, h->d12 + H, h->d12_lo,
+                                   grad + L.log_std, metrics, h->loss_part, h->loss_counter));
+        ReducePlan plan;
+        plan.nseg = 0; plan.blocks = 0;
+        int splits = (int)((B + 255) / 256);
+        if (splits > h->splits_cap) splits = h->splits_cap;
+        if (splits < 1) splits = 1;
+        // dW[N_out, K_in] = dY^T X over the batch: A(m, k) = dY[k, m], B(n, k) = X[k, n], both MN-major
+        auto wgrad_tma = [&](float *part, int Nout, int Kin, const float *dY, const float *dY_lo, int lddy, const float *X,
+                             const float *X_lo, int ldx, float *dW, int n1, float *dW2, cudaStream_t st) -> int {
+            int used = hrp_tma_gemm(Nout, Kin, Bi, dY, dY_lo, 1, lddy, X, X_lo, 1, ldx, part, nullptr, Kin, nullptr, 0, nullptr,
+                                    0, splits, 0, st);
+            if (used < 0) return used;
+            plan_add(plan, part, (long long)Nout * Kin, used, dW, (long long)n1 * Kin, dW2);
+            return 0;
+        };
+        // side 0 -- heads
+        HRP_CUDA_OK(after(1, s, s0));
+        {
+            int chunks = (int)((B + 63) / 64);
+            if (chunks > 64) chunks = 64;
+            int rows_per = (int)((B + chunks - 1) / chunks);
+            dim3 grid((H + 31) / 32, chunks);
+            heads_wgrad_partial_kernel<<<grid, 256, 0, s0>>>(h->dmean, h->dvalue, h->ac, h->ac + H, H2, B, H, A, rows_per,
+                                                             h->part_h);
+            HRP_CUDA_OK(cudaGetLastError());
+            plan_add(plan, h->part_h, (long long)A * H + A + H + 1, chunks, grad + L.wa2, (long long)A * H + A, grad + L.wc2);
+        }
+        // side 1: [dWa1 ; dWc1] as one GEMM, [dba1 | dbc1] as one column sum
+        HRP_CUDA_OK(after(2, s, s1));
+        if (wgrad_tma(h->part_w[0], H2, H, h->d12, h->d12_lo, H2, h->h2, h->h2_lo, H, grad + L.wa1, H, grad + L.wc1, s1)) return -2;
+        if (colsum(plan, h->part_b[0], h->d12, H2, B, H2, grad + L.ba1, H, grad + L.bc1, s1)) return -2;
+        // main: d(h2) = [d(a1) | d(c1)] [Wa1 ; Wc1] (.) (h2 > 0): B(n, k) = wac[k, n]
+        if (hrp_tma_gemm(Bi, H, H2, h->d12, h->d12_lo, H2, 1, h->wacp, h->wacp_lo, 1, H, h->dh2, h->dh2_lo, H, nullptr, 0, h->h2, H,
+                         1, 0, s) < 0)
+            return -2;
+        HRP_CUDA_OK(after(4, s, s1));
+        if (wgrad_tma(h->part_w[1], H, H, h->dh2, h->dh2_lo, H, h->h1, h->h1_lo, H, grad + L.w2, H, nullptr, s1)) return -2;
+        if (colsum(plan, h->part_b[1], h->dh2, H, B, H, grad + L.b2, H, nullptr, s1)) return -2;
+        // main: d(h1) = d(h2) W2 (.) (h1 > 0); dW1; side 0: db1
+        if (hrp_tma_gemm(Bi, H, H, h->dh2, h->dh2_lo, H, 1, h->w2p, h->w2p_lo, 1, H, h->dh1, h->dh1_lo, H, nullptr, 0, h->h1, H, 1,
+                         0, s) < 0)
+            return -2;
+        HRP_CUDA_OK(after(5, s, s0));
+        if (colsum(plan, h->part_b[2], h->dh1, H, B, H, grad + L.b1, H, nullptr, s0)) return -2;
+        if (wgrad_tma(h->part_w[2], H, S, h->dh1, h->dh1_lo, H, x, x_lo, S, grad + L.w1, H, nullptr, s)) return -2;
+        HRP_CUDA_OK(after(6, s0, s));
+        HRP_CUDA_OK(after(7, s1, s));
+        final_reduce_kernel<<<plan.blocks, 256, 0, s>>>(plan);
+        HRP_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     // side stream 1: transposed weight copies for the input-gradient GEMMs (needs the parameters only)
     HRP_CUDA_OK(after(0, s, s1));
     {
@@ -968,7 +1138,7 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         const long long *ix = (const long long *)idx;
         long long tot = B * (S + A + 3);
         gather_batch_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(states, pre_tanh, old_log_prob, adv, ret, ix, B,
-                                                                         S, A, h->x, h->z, h->olp, h->adv, h->ret);
+                                                                         S, A, h->x, h->x_lo, h->z, h->olp, h->adv, h->ret);
         HRP_CUDA_OK(cudaGetLastError());
         x = h->x; z = h->z; olp = h->olp; ad = h->adv; rt = h->ret;
     }
@@ -976,8 +1146,8 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
     HRP_CUDA_OK(hrp_launch_pdl(heads_loss_backward_kernel, dim3((unsigned)((B + HLB_ROWS - 1) / HLB_ROWS)), dim3(256), 0, s,
                                (const float *)h->ac, (const float *)(h->ac + H), H2, H, params + L.wa2, params + L.ba2,
                                params + L.wc2, params + L.bc2, params + L.log_std, z, olp, ad, rt, B, A, eps_clip, value_coef,
-                               entropy_coef, loss_scale, h->dmean, h->dvalue, h->d12, h->d12 + H, grad + L.log_std, metrics,
-                               h->loss_part, h->loss_counter));
+                               entropy_coef, loss_scale, h->dmean, h->dvalue, h->d12, h->d12 + H, (float *)nullptr,
+                               grad + L.log_std, metrics, h->loss_part, h->loss_counter));
     const float *a1 = h->ac, *c1 = h->ac + H;
     ReducePlan plan;
     plan.nseg = 0; plan.blocks = 0;

@@ -264,6 +264,20 @@ class HighwayVecEnv:
                    "hrp_env_reset_host")
         self.launches += 1
 
+    # ------------------------------------------------------------------ validation aids
+    def enable_trace(self, on: bool = True) -> Optional[torch.Tensor]:
+        """Record every vehicle's state at the end of every simulation frame of the following steps (parity tests):
+        returns the float64 tensor [E, frames, V, 7] the kernel writes (x, y, speed, heading, impact_x, impact_y, flags)."""
+        if not on:
+            _lib.check(self._lib.hrp_env_set_trace(self._h, None), "hrp_env_set_trace")
+            self._trace = None
+            return None
+        fr, sl, fi = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(self._lib.hrp_env_trace_shape(self._h, C.byref(fr), C.byref(sl), C.byref(fi)), "hrp_env_trace_shape")
+        self._trace = torch.zeros((self.num_envs, fr.value, sl.value, fi.value), dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.hrp_env_set_trace(self._h, self._trace.data_ptr()), "hrp_env_set_trace")
+        return self._trace[:, :, : self.V, :]
+
     # ------------------------------------------------------------------ state injection
     def _state_arrays(self):
         E, V = self.num_envs, self.V

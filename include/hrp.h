@@ -144,6 +144,13 @@ int hrp_env_reset_host(hrp_env *env, uint64_t seed, float *obs_host);
 int hrp_env_step_host_on(hrp_env *env, const float *actions, float *obs_host, float *reward_host,
                          uint8_t *terminated_host, uint8_t *truncated_host, void *stream);
 
+/* validation aid: while trace_dev is non-NULL every hrp_env_step also writes the state of every vehicle at the end
+ * of every simulation frame -- trace_dev[E][frames][slots][fields] doubles (x, y, speed, heading, impact_x, impact_y,
+ * flags = lane | target_lane<<8 | crashed<<16 | has_impact<<17); hrp_env_trace_shape gives the three inner extents.
+ * The parity tests use it to compare a step with the oracle frame by frame.  NULL switches it off. */
+int hrp_env_set_trace(hrp_env *env, double *trace_dev);
+int hrp_env_trace_shape(const hrp_env *env, int32_t *frames, int32_t *slots, int32_t *fields);
+
 /* state injection / extraction; synchronous */
 int hrp_env_get_state(hrp_env *env, hrp_state *dst_host);
 int hrp_env_set_state(hrp_env *env, const hrp_state *src_host);

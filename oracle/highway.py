@@ -93,6 +93,7 @@ def lib():
         L.hw_force_decisions.restype = C.c_int32
         L.hw_force_decisions.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.hw_slow_vehicles.argtypes = [C.c_void_p, C.c_void_p]
+        L.hw_set_trace.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -162,8 +163,11 @@ class OracleEnv:
         self.F = self.cfg.obs_nfeat
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().hw_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:   # (module globals are gone at interpreter shutdown)
+            try:
+                _lib.hw_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def reset(self, seed: int, env_id: int = 0, episode: int = 0) -> None:
@@ -229,6 +233,18 @@ class OracleEnv:
         k = np.asarray(list(keys), dtype=np.uint64)
         if lib().hw_force_decisions(self._h, k.ctypes.data if len(k) else None, len(k)) != 0:
             raise ValueError("oracle: too many forced decisions")
+
+    def trace(self, on: bool = True) -> Optional[np.ndarray]:
+        """Per-frame snapshots of the following steps: the returned [frames, V, 7] float64 array is rewritten by
+        every ``step`` (x, y, speed, heading, impact_x, impact_y, flags)."""
+        if not on:
+            lib().hw_set_trace(self._h, None)
+            self._trace = None
+            return None
+        frames = self.cfg.simulation_frequency // self.cfg.policy_frequency
+        self._trace = np.zeros((frames, self.V, 7), dtype=np.float64)
+        lib().hw_set_trace(self._h, self._trace.ctypes.data)
+        return self._trace
 
     def slow_vehicles(self) -> np.ndarray:
         out = np.zeros(HW_MAX_VEHICLES, dtype=np.uint8)

@@ -78,6 +78,7 @@ struct hw_env {
     uint64_t forced[HW_MAX_FORCED];
     int nforced;
     uint8_t slow[HW_MAX_VEHICLES]; /* controlled vehicle acted below 0.5 m/s during the last step */
+    double *trace;                 /* test aid: [frames][V][HW_TRACE_FIELDS] per-frame snapshots of hw_step */
 };
 
 /* ---- decision bookkeeping (test aid only) --------------------------------
@@ -524,6 +525,15 @@ void hw_step(hw_env *e, const float *action, double *reward, int32_t *terminated
         for (int i = 0; i < e->V; ++i)
             for (int j = i + 1; j < e->V; ++j) handle_collisions(e, i, j, dt);
         e->steps += 1;
+        if (e->trace) {
+            double *t = e->trace + (size_t)frame * e->V * HW_TRACE_FIELDS;
+            for (int i = 0; i < e->V; ++i, t += HW_TRACE_FIELDS) {
+                const veh_t *v = &e->v[i];
+                t[0] = v->x; t[1] = v->y; t[2] = v->speed; t[3] = v->heading; t[4] = v->impact_x; t[5] = v->impact_y;
+                t[6] = (double)((uint32_t)v->lane | ((uint32_t)v->target_lane << 8) | ((uint32_t)(v->crashed != 0) << 16) |
+                                ((uint32_t)(v->has_impact != 0) << 17));
+            }
+        }
     }
     e->frame = HW_FRAME_END;
     /* HighwayEnv._rewards / _reward (A.9) */
@@ -707,6 +717,7 @@ int32_t hw_force_decisions(hw_env *e, const uint64_t *keys, int32_t n)
     return 0;
 }
 void hw_slow_vehicles(const hw_env *e, uint8_t *out) { memcpy(out, e->slow, (size_t)e->V); }
+void hw_set_trace(hw_env *e, double *buf) { e->trace = buf; }
 
 void hw_get_state(const hw_env *e, hw_state *s)
 {

@@ -32,7 +32,7 @@ extern "C" {
 #define HW_MAX_VEHICLES 128
 #define HW_MAX_FEATURES 8
 #define HW_MAX_MARGINAL 1024 /* marginal decisions listed per step */
-#define HW_MAX_FORCED 16   /* decisions that can be forced the other way at once */
+#define HW_MAX_FORCED 64   /* decisions that can be forced the other way at once */
 
 /* feature codes for the Kinematics observation (highway-env to_dict keys) */
 enum {
@@ -136,6 +136,11 @@ void    hw_record_margin(hw_env *env, double below);
 int32_t hw_marginal_keys(const hw_env *env, uint64_t *keys, double *margins, int32_t max);
 int32_t hw_force_decisions(hw_env *env, const uint64_t *keys, int32_t n);
 void    hw_slow_vehicles(const hw_env *env, uint8_t *out);
+/* while buf is non-NULL, hw_step writes every vehicle's state at the end of every simulation frame:
+ * buf[frames][V][HW_TRACE_FIELDS] = (x, y, speed, heading, impact_x, impact_y, lane | target_lane<<8 | crashed<<16 |
+ * has_impact<<17) */
+#define HW_TRACE_FIELDS 7
+void    hw_set_trace(hw_env *env, double *buf);
 
 #ifdef __cplusplus
 }

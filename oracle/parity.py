@@ -10,6 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 MARGIN = 1e-3
+MARGIN64 = 1e-9   # fp64 kernel against the fp64 oracle: only exact ties (resting contacts, margins of 0 to 1e-13) may differ
 TOL = dict(x=1e-3, y=1e-3, speed=2e-4, heading=1e-4, impact_x=1e-3, impact_y=1e-3, timer=1e-9, target_speed=1e-5)
 # fp64 validation kernel against the fp64 oracle.  Positions / impacts 2e-6: when two nearly parallel rectangles
 # collide, the separating-axis minimum between their (nearly identical) axes is a tie up to theta^2 ~ 1e-12 m that
@@ -103,7 +104,7 @@ def _priority(key, vehicles):
     return (0 if (vehicles and who & vehicles) else 1, -frame if frame < 250 else -999)
 
 
-def either_branch(o, st0, action, perm, got, tol, obs_tol, rew_tol, max_nodes=3000, max_depth=12, why=None):
+def either_branch(o, st0, action, perm, got, tol, obs_tol, rew_tol, max_nodes=3000, max_depth=12, why=None, margin=MARGIN):
     """Re-run the oracle step from ``st0`` with marginal decisions forced the other way; returns the forced keys
     under which the kernel's results equal the oracle's in full, or None.  Best-first search over sets of forced
     decisions: the node whose outcome differs least from the kernel's is expanded first (a flip that repairs one of
@@ -112,7 +113,7 @@ def either_branch(o, st0, action, perm, got, tol, obs_tol, rew_tol, max_nodes=30
     not extended, one that takes the outcome further from the kernel's is not extended either."""
     import heapq
 
-    o.record_margin(MARGIN)
+    o.record_margin(margin)
     seen, heap, found, nodes, tick = {()}, [], None, 0, 0
 
     def run(forced):
@@ -147,6 +148,95 @@ def either_branch(o, st0, action, perm, got, tol, obs_tol, rew_tol, max_nodes=30
             if nodes >= max_nodes:
                 break
     # leave the oracle on its own (unforced) outcome
+    o.force(())
+    o.record_margin(0.0)
+    o.set_state(st0)
+    o.step(action)
+    return found
+
+
+# ---- frame-by-frame either-branch search ------------------------------------------------------------------------
+# A pile-up of crashed vehicles is a chain of resting contacts: after an impact translation two rectangles touch
+# EXACTLY, so the contact tests of the following frames are decided by the last bit (margins of 0 to 1e-13 in the
+# oracle), every frame anew, and every outcome changes the states the next frame's tests see.  The set of decisions
+# that reproduces the kernel's trajectory cannot be found from the step's final state alone.  With the kernel's
+# per-frame trace (hrp_env_set_trace) and the oracle's (hw_set_trace) it can: walk the frames, and at the first frame
+# whose snapshots differ, flip marginal decisions OF THAT FRAME until the snapshots agree, then go on.
+_TRACE_TOL = np.array([TOL["x"], TOL["y"], TOL["speed"], TOL["heading"], TOL["impact_x"], TOL["impact_y"]])
+
+
+def _first_diff(ktrace, otrace, scale, ttol=None):
+    """(frame, vehicles) of the first per-frame snapshot that differs between kernel and oracle, or None."""
+    ttol = _TRACE_TOL if ttol is None else ttol
+    for f in range(otrace.shape[0]):
+        bad = np.nonzero(ktrace[f, :, 6] != otrace[f, :, 6])[0]
+        err = np.abs(ktrace[f, :, :6] - otrace[f, :, :6]) / scale[:, None]
+        over = np.nonzero((err > ttol[None, :]).any(axis=1))[0]
+        if len(bad) or len(over):
+            return f, {int(v) for v in bad} | {int(v) for v in over}
+    return None
+
+
+def frame_search(o, st0, action, perm, got, ktrace, tol, obs_tol, rew_tol, max_runs=1500, margin=MARGIN, trace_tol=None):
+    """Either-branch search guided by the kernel's per-frame trace ``ktrace`` [frames, V, 7].  Returns the forced keys
+    under which the oracle's step equals the kernel's in full (every frame's snapshot and the final results), or None."""
+    from . import highway as oh
+
+    otrace = o.trace(True)
+    o.record_margin(margin)
+    runs = 0
+    ttol = _TRACE_TOL if trace_tol is None else trace_tol
+
+    def run(forced):
+        nonlocal runs
+        runs += 1
+        o.set_state(st0)
+        o.force(forced)
+        r, te, tr = o.step(action)
+        want_obs, want_rows = o.observe(perm=perm, with_rows=True)
+        slow = o.slow_vehicles()
+        scale = np.ones(len(slow))
+        if slow.any():
+            x = o.get_state()["x"]
+            near = np.abs(x[:, None] - x[None, slow]).min(axis=1) < NEAR_SLOW_M
+            scale = np.where(slow | near, SLOW_FACTOR, 1.0)
+        return (_first_diff(ktrace, otrace, scale, ttol), compare(got, o, r, te, tr, want_obs, want_rows, tol, obs_tol, rew_tol),
+                o.marginal())
+
+    forced, found = (), None
+    diff, c, keys = run(forced)
+    while runs < max_runs:
+        if diff is None:
+            if c is None:
+                found = forced
+                break
+            f = 250   # every frame agrees: what is left are the decisions after the last frame (on-road test, observation)
+        else:
+            f = diff[0]
+        in_frame = (lambda k: oh.key_fields(k)[1] >= 250) if f == 250 else (lambda k: oh.key_fields(k)[1] == f)
+        # breadth-first over the decisions of frame f: a forced decision can expose further ones of the same frame (the
+        # separating-axis loop stops at the first separating axis; once that is flipped the next axis is evaluated)
+        queue, seen, step = [(forced, diff, c, keys)], {forced}, None
+        while queue and step is None and runs < max_runs:
+            base, bdiff, bc, bkeys = queue.pop(0)
+            vehicles = bdiff[1] if bdiff is not None else (bc["vehicles"] if bc else set())
+            for k in sorted((k for k in bkeys if in_frame(k) and k not in base), key=lambda k: _priority(k, vehicles)):
+                nxt = tuple(sorted(base + (k,)))
+                if nxt in seen:
+                    continue
+                seen.add(nxt)
+                d2, c2, k2 = run(nxt)
+                if (d2 is None and (f != 250 or c2 is None)) or (d2 is not None and f != 250 and d2[0] > f):
+                    step = (nxt, d2, c2, k2)
+                    break
+                if len(nxt) - len(forced) < 6 and (f == 250 or (d2 is not None and d2[0] == f)):
+                    queue.append((nxt, d2, c2, k2))
+                if runs >= max_runs:
+                    break
+        if step is None:
+            break
+        forced, diff, c, keys = step
+    o.trace(False)
     o.force(())
     o.record_margin(0.0)
     o.set_state(st0)

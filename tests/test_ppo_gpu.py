@@ -421,7 +421,9 @@ def test_swept_widths_match_reference(name):
     # Adam's first step: lr * g_clipped / (|g_clipped| + eps), ~ +-lr wherever |g| >> eps
     step1 = ac.flat.cpu().numpy() - flat0
     want = g["step1_samples"]
-    solid = np.abs(want) > 0.9 * 3e-4
+    # entries whose clipped gradient is far above Adam's eps = 1e-8 (the step is lr * g / (|g| + eps): below that a
+    # 1e-9 difference of the gradient moves it visibly; dead ReLU units have no gradient at all)
+    solid = np.abs(g["grads_samples"]) * min(1.0, 0.5 / float(g["total_norm"])) > 3e-6
     assert solid.mean() > 0.3
     np.testing.assert_allclose(step1[::257][solid], want[solid], atol=3e-6)
 

@@ -26,6 +26,7 @@ for e, o in enumerate(oracles):
     o.reset(seed, env_id=e, episode=0)
 rng = np.random.default_rng(seed)
 env32 = T._vec(cfg, 1, autoreset=False)
+trace32 = env32.enable_trace()
 env64 = T._vec(cfg, 1, autoreset=False, real64=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 for t in range(max(c[0] for c in cases) + 1):
@@ -43,6 +44,8 @@ for t in range(max(c[0] for c in cases) + 1):
                 got = env.get_state()
                 for k in oh.STATE_F64 + oh.STATE_I32:
                     out[f"{name}_{k}"] = got[k][0]
+                if name == "k32":
+                    out["k32_trace"] = trace32[0].cpu().numpy()
             np.savez(os.path.join(ROOT, "gpurun_out", f"debug_case_{kind}_{seed}_{t}_{e}.npz"), **out)
         r, te, tr = o.step(actions[e])
         if te or tr:
