@@ -65,7 +65,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed building libhrp_b200.so")
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-o", LIB_PATH]
-    res = subprocess.run(link + [obj for _, obj, _ in jobs] + ["-lcuda"], capture_output=True, text=True)
+    res = subprocess.run(link + [obj for _, obj, _ in jobs], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:

@@ -18,12 +18,22 @@
 // Accumulation: D[:, 0:BN] += A_hi [B_hi; B_lo] (one UMMA with N = 2 BN over the stacked B tile) and D[:, 0:BN] +=
 // A_lo B_hi; the two halves are added in the epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "hrp_internal.cuh"
 
+// phase clocks of CTA (0,0,0) when hrp_debug_tma_gemm_clocks(1) switched them on (tools/gemm_bench.py)
+__device__ long long g_gt_phase[16];
+__device__ int g_gt_phase_on;
+#define GT_PHASE(i) do { if (g_gt_phase_on && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_gt_phase[(i)] = clock64(); } while (0)
+
 namespace {
 
-constexpr int BM = 128, BK = 32;            // BK fp32 = 128 B = one swizzle row
+// K-block of 32 fp32 = 128 bytes per operand row (SWIZZLE_128B for K-major tiles); a stage of a 128 x 64 tile is
+// 48 KB, four stages 192 KB: ONE CTA per SM.  Measured alternatives (profiles/r02_gemm_bench.txt): 16-wide K-blocks
+// (SWIZZLE_64B, 24 KB stages, two CTAs per SM) run the same tile in 13.7 us instead of 9.2 us (twice the boxes and
+// barrier round trips per byte); two 48 KB stages cannot cover the ~1300-cycle TMA latency with a ~700-cycle K-block.
+constexpr int BM = 128, BK = 32;
 constexpr int GT_THREADS = 192;             // 6 warps
 constexpr int A_TILE = BM * BK * 4;         // 16 KB
 
@@ -56,6 +66,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, void *dst, u
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -72,18 +89,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), SWIZZLE_128B, version 1.
-//   K-major  tile [rows][32 fp32]: 8-row x 128-byte atoms 1024 B apart (SBO); LBO unused.
-//   MN-major tile, stored as boxes of [32 k][32 mn fp32] = 4 KB each (a box is 4 atoms of 8 k-rows x 128 bytes): the
-//   next 32 mn values are one box further (LBO = 4096 B), the next 8 k are one atom further (SBO = 1024 B).
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1.
+//   K-major  tile [rows][32 fp32], SWIZZLE_128B (layout type 2): 8-row x 128-byte atoms 1024 B apart (SBO); LBO unused.
+//   MN-major tile: 32-bit operands have ONE legal MN-major layout, SWIZZLE_128B_BASE32B (layout type 1: the 128-byte
+//   swizzle with 32-byte atoms, Swizzle<2,5,2>; TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), whose atom is 4 k-rows x
+//   128 bytes (32 mn values).  The tile is stored as boxes of [32 k][32 mn fp32] = 4 KB each: the next 32 mn values
+//   are one box further (LBO = 4096 B), the next 4 k are one atom further (SBO = 512 B); one UMMA (8 k) spans two atoms.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major)
 {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)(mn_major ? (4096 >> 4) : 1) << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(mn_major ? ((BK * 128) >> 4) : 1) << 16;
+    d |= (uint64_t)((mn_major ? 512 : 1024) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(mn_major ? 1 : 2) << 61;
     return d;
 }
 // cute::UMMA::InstrDescriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (2 at bits 7-9, 10-12), a_major bit 15, b_major bit 16
@@ -96,16 +115,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
 
 struct GemmMaps {
     CUtensorMap a, a_lo, b, b_lo;
+    CUtensorMap c, c_lo;   // output [splits][M][N] as boxes of [128 rows][32 columns], SWIZZLE_128B (TMA store)
 };
 
-template <int BN> __host__ __device__ constexpr int gt_stages() { return BN == 64 ? 4 : 3; }
+template <int BN> __host__ __device__ constexpr int gt_stages() { return BN == 64 ? 4 : 3; }   // 192 KB either way
 template <int BN> __host__ __device__ constexpr int gt_stage_bytes() { return 2 * (A_TILE + BN * BK * 4); }
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int k_chunk, float *__restrict__ C,
                 float *__restrict__ C_lo, int ldc, const float *__restrict__ bias, int relu,
-                const float *__restrict__ mask, int ldm)
+                const float *__restrict__ mask, int ldm, int tma_store)
 {
     constexpr int B_TILE = BN * BK * 4;
     constexpr int STAGE = gt_stage_bytes<BN>();
@@ -114,10 +134,12 @@ tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar_full[4], bar_empty[4], bar_done;
     __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[BN];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     hrp_pdl_release();
+    if (tid == 0) GT_PHASE(0);
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * k_chunk, kend = min(K, kbeg + k_chunk);
     const int nkb = (kend - kbeg + BK - 1) / BK;
@@ -133,6 +155,10 @@ tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int 
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a_lo)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b_lo)) : "memory");
+        if (tma_store) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.c)) : "memory");
+            if (C_lo) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.c_lo)) : "memory");
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -144,7 +170,9 @@ tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
+    if (tid == 0) GT_PHASE(1);   // set up (barriers, TMEM)
     hrp_pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here
+    if (tid == 0) GT_PHASE(2);   // predecessor complete
 
     if (warp == 0) {
         // ===== TMA producer: one thread; a stage = A, A_lo, B, B_lo boxes of one K-block
@@ -154,13 +182,13 @@ tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int 
                 if (kb >= STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((kb / STAGES) - 1) & 1));
                 uint8_t *st = smem + s * STAGE;
                 mbar_expect_tx(&bar_full[s], (uint32_t)STAGE);
-                if (A_MN) {   // boxes of [32 k][32 m]: coordinates (m, k)
+                if (A_MN) {   // boxes of [BK k][32 m]: coordinates (m, k)
 #pragma unroll
                     for (int j = 0; j < BM / 32; ++j) {
-                        tma_load_2d(&maps.a, st + j * 4096, &bar_full[s], m0 + 32 * j, k0);
-                        tma_load_2d(&maps.a_lo, st + A_TILE + j * 4096, &bar_full[s], m0 + 32 * j, k0);
+                        tma_load_2d(&maps.a, st + j * (BK * 128), &bar_full[s], m0 + 32 * j, k0);
+                        tma_load_2d(&maps.a_lo, st + A_TILE + j * (BK * 128), &bar_full[s], m0 + 32 * j, k0);
                     }
-                } else {      // one box [128 m][32 k]: coordinates (k, m)
+                } else {      // one box [128 m][BK k]: coordinates (k, m)
                     tma_load_2d(&maps.a, st, &bar_full[s], k0, m0);
                     tma_load_2d(&maps.a_lo, st + A_TILE, &bar_full[s], k0, m0);
                 }
@@ -168,8 +196,8 @@ tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int 
                 if (B_MN) {
 #pragma unroll
                     for (int j = 0; j < BN / 32; ++j) {
-                        tma_load_2d(&maps.b, sb + j * 4096, &bar_full[s], n0 + 32 * j, k0);
-                        tma_load_2d(&maps.b_lo, sb + B_TILE + j * 4096, &bar_full[s], n0 + 32 * j, k0);
+                        tma_load_2d(&maps.b, sb + j * (BK * 128), &bar_full[s], n0 + 32 * j, k0);
+                        tma_load_2d(&maps.b_lo, sb + B_TILE + j * (BK * 128), &bar_full[s], n0 + 32 * j, k0);
                     }
                 } else {
                     tma_load_2d(&maps.b, sb, &bar_full[s], k0, n0);
@@ -185,6 +213,8 @@ tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int 
             const int s = kb % STAGES;
             mbar_wait(&bar_full[s], (uint32_t)((kb / STAGES) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0 && kb == 0) GT_PHASE(3);   // first stage landed
+            if (lane == 0 && kb == 1) GT_PHASE(4);   // second stage landed (or MMAs of the first issued)
             if (lane == 0) {
                 const uint32_t a_s = smem_u32(smem + s * STAGE), b_s = a_s + 2 * A_TILE;
                 const uint64_t da_hi = make_desc(a_s, A_MN), db_hi = make_desc(b_s, B_MN);
@@ -199,20 +229,37 @@ tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int 
                     umma_tf32(tmem_d, da_lo + kk * a_step, db_hi + kk * b_step, idesc, 1u);     // + A_lo B_hi
                 }
                 umma_commit(&bar_empty[s]);
-                if (kb + 1 == nkb) umma_commit(&bar_done);
+                if (kb + 1 == nkb) { umma_commit(&bar_done); GT_PHASE(5); }   // last MMA issued
             }
             __syncwarp();
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lanes 32 (warp % 4) .., one accumulator row per thread
+        // ===== epilogue warps 2..5: TMEM lanes 32 (warp % 4) .., one accumulator row per thread.
+        // While the main loop runs they fetch what the epilogue needs from global memory: the bias slice into shared
+        // memory and (64-wide tiles) this thread's row of the ReLU mask into registers.
+        {
+            const int i = tid - 64;
+            if (i < BN) bias_s[i] = (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+        }
+        constexpr int MASK_REGS = BN == 64 ? 16 : 1;
+        float4 mk[MASK_REGS];
+        const bool mask_pre = BN == 64 && mask != nullptr && ldm % 4 == 0 && ((uintptr_t)mask & 15) == 0 && n0 + BN <= N;
+        if (mask_pre) {
+            const int r = m0 + 32 * (warp & 3) + lane;
+            const float4 *mrow = reinterpret_cast<const float4 *>(mask + (size_t)min(r, M - 1) * ldm + n0);
+#pragma unroll
+            for (int j = 0; j < MASK_REGS; ++j) mk[j] = __ldg(mrow + j);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // bias_s is complete
         if (nkb > 0) mbar_wait(&bar_done, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 64) GT_PHASE(6);   // accumulator complete
         const int q = warp & 3, row = 32 * q + lane, gm = m0 + row;
         float *Cz = C + (size_t)blockIdx.z * M * ldc;
         float *Clz = C_lo ? C_lo + (size_t)blockIdx.z * M * ldc : nullptr;
         const bool vec_ok = ldc % 4 == 0 && ((uintptr_t)Cz & 15) == 0 && (!Clz || ((uintptr_t)Clz & 15) == 0) &&
                             (!mask || (ldm % 4 == 0 && ((uintptr_t)mask & 15) == 0));
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 16) {
             uint32_t v[16], u[16];
             if (nkb > 0) {
@@ -235,12 +282,52 @@ tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int 
                 for (int j = 0; j < 16; ++j) v[j] = u[j] = 0u;
             }
             const int gn0 = n0 + c0;
+            if (tma_store) {
+                // stage the tile (and its lo part) in shared memory -- the operand stages are free once bar_done has
+                // fired -- as [128 rows][32 columns] panels in the SWIZZLE_128B layout (16-byte chunk ^ row % 8: the
+                // 32 rows of a warp spread over the banks), and let ONE TMA store per panel write it out: full
+                // 128-byte rows, edges clipped by the tensor map
+                float x[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    x[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]) + bias_s[c0 + j];
+                    if (relu) x[j] = fmaxf(x[j], 0.f);
+                }
+                if (mask_pre) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 m4 = mk[BN == 64 ? (c0 + j) / 4 : 0];
+                        x[j] = m4.x > 0.f ? x[j] : 0.f; x[j + 1] = m4.y > 0.f ? x[j + 1] : 0.f;
+                        x[j + 2] = m4.z > 0.f ? x[j + 2] : 0.f; x[j + 3] = m4.w > 0.f ? x[j + 3] : 0.f;
+                    }
+                } else if (mask && gm < M) {
+                    const float *mrow = mask + (size_t)gm * ldm + gn0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (gn0 + j < N) x[j] = __ldg(mrow + j) > 0.f ? x[j] : 0.f;
+                }
+                uint8_t *panel = smem + (c0 >> 5) * (BM * 128) + row * 128;
+                uint8_t *panel_lo = panel + BN * BM * 4;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const int ch = (((c0 & 31) + j) >> 2) ^ (row & 7);
+                    *reinterpret_cast<float4 *>(panel + ch * 16) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                    if (C_lo) {
+                        float4 l;
+                        l.x = x[j] - __uint_as_float(__float_as_uint(x[j]) & 0xFFFFE000u);
+                        l.y = x[j + 1] - __uint_as_float(__float_as_uint(x[j + 1]) & 0xFFFFE000u);
+                        l.z = x[j + 2] - __uint_as_float(__float_as_uint(x[j + 2]) & 0xFFFFE000u);
+                        l.w = x[j + 3] - __uint_as_float(__float_as_uint(x[j + 3]) & 0xFFFFE000u);
+                        *reinterpret_cast<float4 *>(panel_lo + ch * 16) = l;
+                    }
+                }
+                continue;
+            }
             if (gm < M && gn0 < N) {
                 float x[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    x[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
-                    if (bias && gn0 + j < N) x[j] += __ldg(bias + gn0 + j);
+                    x[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]) + bias_s[c0 + j];
                     if (relu) x[j] = fmaxf(x[j], 0.f);
                 }
                 float *crow = Cz + (size_t)gm * ldc + gn0;
@@ -276,6 +363,23 @@ tma_gemm_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, int 
                 }
             }
         }
+        if (tid == 64) GT_PHASE(7);   // tile staged / written
+        if (tma_store) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> bulk-copy reads
+            asm volatile("bar.sync 1, 128;" ::: "memory");                     // the four epilogue warps
+            if (warp == 2 && lane == 0) {
+#pragma unroll
+                for (int p = 0; p < BN / 32; ++p) {
+                    if (n0 + 32 * p < N) {
+                        tma_store_3d(&maps.c, smem + p * (BM * 128), n0 + 32 * p, m0, (int)blockIdx.z);
+                        if (C_lo) tma_store_3d(&maps.c_lo, smem + BN * BM * 4 + p * (BM * 128), n0 + 32 * p, m0, (int)blockIdx.z);
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory is read before the CTA goes
+                GT_PHASE(8);   // stores read out of shared memory
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -308,32 +412,67 @@ __global__ void __launch_bounds__(256) split_lo_kernel(const float *__restrict__
 bool tma_ok(const float *p, long long srow, long long sk, int rows, int K)
 {
     if (((uintptr_t)p & 15) != 0) return false;
+    if (K < 8 || rows < 8) return false;
     if (sk == 1) return srow % 4 == 0 && srow >= K;
     if (srow == 1) return sk % 4 == 0 && sk >= rows;
     return false;
 }
+// cuTensorMapEncodeTiled is a driver entry point: it is looked up through the runtime (cudaGetDriverEntryPoint), so the
+// library does not link against libcuda.so.1 and still loads on a machine without a driver (build check, CPU tests)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
 int encode(CUtensorMap *map, const float *p, long long srow, long long sk, int rows, int K, int box_rows)
 {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { hrp_set_error("cuTensorMapEncodeTiled is not available from this driver"); return -2; }
     const bool kmajor = sk == 1;
     cuuint64_t dims[2] = {(cuuint64_t)(kmajor ? K : rows), (cuuint64_t)(kmajor ? rows : K)};
     cuuint64_t strides[1] = {(cuuint64_t)((kmajor ? srow : sk) * 4)};
-    cuuint32_t box[2] = {32u, (cuuint32_t)(kmajor ? box_rows : 32)};
+    cuuint32_t box[2] = {(cuuint32_t)(kmajor ? BK : 32), (cuuint32_t)(kmajor ? box_rows : BK)};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p), dims, strides, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        const char *msg = nullptr;
-        cuGetErrorString(r, &msg);
-        hrp_set_error("cuTensorMapEncodeTiled failed: %s (rows %d, K %d, strides %lld / %lld)", msg ? msg : "?", rows, K, srow, sk);
+        hrp_set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows %d, K %d, strides %lld / %lld)", (int)r, rows, K, srow, sk);
         return -2;
     }
     return 0;
 }
 
+// output tensor [splits][M][N] (pitch ldc), stored as boxes of [128 rows][32 columns]
+int encode_out(CUtensorMap *map, float *p, int M, int N, int ldc, int splits)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { hrp_set_error("cuTensorMapEncodeTiled is not available from this driver"); return -2; }
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
+    cuuint64_t strides[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)M * ldc * 4};
+    cuuint32_t box[3] = {32u, (cuuint32_t)BM, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { hrp_set_error("cuTensorMapEncodeTiled (output) failed: CUresult %d (M %d, N %d, ldc %d)", (int)r, M, N, ldc); return -2; }
+    return 0;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 int launch(const GemmMaps &maps, dim3 grid, cudaStream_t s, int M, int N, int K, int k_chunk, float *C, float *C_lo, int ldc,
-           const float *bias, int relu, const float *mask, int ldm)
+           const float *bias, int relu, const float *mask, int ldm, int tma_store)
 {
     constexpr int SMEM = gt_stages<BN>() * gt_stage_bytes<BN>() + 1024;
     static bool configured[HRP_MAX_DEVICES] = {false};
@@ -346,7 +485,7 @@ int launch(const GemmMaps &maps, dim3 grid, cudaStream_t s, int M, int N, int K,
         configured[dev] = true;
     }
     HRP_CUDA_OK(hrp_launch_pdl(kern, grid, dim3(GT_THREADS), (size_t)SMEM, s, maps, M, N, K, k_chunk, C, C_lo, ldc, bias, relu,
-                               mask, ldm));
+                               mask, ldm, tma_store));
     return 0;
 }
 
@@ -384,6 +523,7 @@ int hrp_tma_gemm(int M, int N, int K, const float *A, const float *A_lo, long lo
     const int mt = (M + BM - 1) / BM;
     int bn = bn_hint;
     if (bn != 64 && bn != 128) bn = (N <= 64 || mt * ((N + 127) / 128) * splits < 100) ? 64 : 128;
+    if (C_lo && bn == 128 && gt_stages<128>() * gt_stage_bytes<128>() < 2 * BM * 128 * 4) bn = 64;   // staging must fit
     const bool a_mn = sak != 1, b_mn = sbk != 1;
     GemmMaps maps;
     if (encode(&maps.a, A, sam, sak, M, K, BM) || encode(&maps.a_lo, A_lo, sam, sak, M, K, BM) ||
@@ -391,7 +531,12 @@ int hrp_tma_gemm(int M, int N, int K, const float *A, const float *A_lo, long lo
         return -2;
     dim3 grid((N + bn - 1) / bn, mt, splits);
     int rc;
-#define HRP_GT_GO(BN_, AM, BMj) launch<BN_, AM, BMj>(maps, grid, s, M, N, K, k_chunk, C, C_lo, ldc, bias, relu, mask, ldm)
+    // output through TMA stores when a tensor map can describe it (16-byte aligned base and pitch)
+    int tma_store = ldc % 4 == 0 && ((uintptr_t)C & 15) == 0 && (!C_lo || ((uintptr_t)C_lo & 15) == 0) && !getenv("HRP_NO_TMA_STORE");
+    if (tma_store) {
+        if (encode_out(&maps.c, C, M, N, ldc, splits) || (C_lo && encode_out(&maps.c_lo, C_lo, M, N, ldc, splits))) return -2;
+    }
+#define HRP_GT_GO(BN_, AM, BMj) launch<BN_, AM, BMj>(maps, grid, s, M, N, K, k_chunk, C, C_lo, ldc, bias, relu, mask, ldm, tma_store)
     if (bn == 64) {
         if (!a_mn && !b_mn) rc = HRP_GT_GO(64, false, false);
         else if (!a_mn && b_mn) rc = HRP_GT_GO(64, false, true);
@@ -405,4 +550,23 @@ int hrp_tma_gemm(int M, int N, int K, const float *A, const float *A_lo, long lo
     }
 #undef HRP_GT_GO
     return rc < 0 ? rc : splits;
+}
+
+// debugging aids (not part of include/hrp.h): the TMA GEMM on caller-provided pre-split operands, and the phase clocks
+// of its CTA (0,0,0)
+extern "C" int hrp_debug_tma_gemm(int M, int N, int K, const float *A, const float *A_lo, long long sam, long long sak,
+                                  const float *B, const float *B_lo, long long sbn, long long sbk, float *C, float *C_lo, int ldc,
+                                  const float *bias, int relu, int splits, int bn_hint, void *stream)
+{
+    int rc = hrp_tma_gemm(M, N, K, A, A_lo, sam, sak, B, B_lo, sbn, sbk, C, C_lo, ldc, bias, relu, nullptr, 0, splits, bn_hint,
+                          (cudaStream_t)stream);
+    return rc < 0 ? rc : 0;
+}
+extern "C" int hrp_debug_split_lo(const float *x, float *lo, long long n, void *stream) { return hrp_split_lo(x, lo, n, (cudaStream_t)stream); }
+extern "C" int hrp_debug_tma_gemm_clocks(int on, long long *out16)
+{
+    HRP_CUDA_OK(cudaDeviceSynchronize());
+    if (out16) HRP_CUDA_OK(cudaMemcpyFromSymbol(out16, g_gt_phase, sizeof(long long) * 16));
+    HRP_CUDA_OK(cudaMemcpyToSymbol(g_gt_phase_on, &on, sizeof(int)));
+    return 0;
 }

@@ -288,7 +288,7 @@ template <int BN, bool DUAL>
 __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *bar_done_p, uint32_t tmem_d, int nkb, int M, int N,
                                             int m0, int n0, int bn0, float *__restrict__ C, int ldc,
                                             const float *__restrict__ biasp, int relu, const float *__restrict__ mask,
-                                            int ldm, int accumulate)
+                                            int ldm, int accumulate, float *__restrict__ C_lo)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // ---- epilogue: TMEM -> registers -> shared (row-major, padded) -> coalesced global rows.
@@ -339,7 +339,9 @@ __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *bar_done_p,
     __syncthreads();
     if (tid == 0) TC_PHASE(6);   // tile staged in shared memory
     float *Cz = C + (size_t)blockIdx.z * M * ldc;
-    const bool vec = n0 + BN <= N && ldc % 4 == 0 && ((uintptr_t)Cz & 15) == 0 &&
+    // optional "lo" twin of the output, x - trunc_tf32(x): the pre-split operand of the TMA-fed kernel (hrp_gemm_tma.cu)
+    float *Clz = C_lo ? C_lo + (size_t)blockIdx.z * M * ldc : nullptr;
+    const bool vec = n0 + BN <= N && ldc % 4 == 0 && ((uintptr_t)Cz & 15) == 0 && (!Clz || ((uintptr_t)Clz & 15) == 0) &&
                      (mask == nullptr || (ldm % 4 == 0 && ((uintptr_t)mask & 15) == 0));
     if (vec && tid < TC_THREADS) {
         // whole tile inside the matrix and 16-byte aligned rows: a warp writes 512 contiguous bytes per instruction.
@@ -367,7 +369,17 @@ __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *bar_done_p,
                 if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                 x.x = mk[j].x > 0.f ? x.x : 0.f; x.y = mk[j].y > 0.f ? x.y : 0.f;
                 x.z = mk[j].z > 0.f ? x.z : 0.f; x.w = mk[j].w > 0.f ? x.w : 0.f;
-                if (m0 + rb + j * RSTEP < M) *(float4 *)(crow + (size_t)j * RSTEP * ldc) = x;
+                if (m0 + rb + j * RSTEP < M) {
+                    *(float4 *)(crow + (size_t)j * RSTEP * ldc) = x;
+                    if (Clz) {
+                        float4 l;
+                        l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                        l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                        l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                        l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                        *(float4 *)(Clz + (crow - Cz) + (size_t)j * RSTEP * ldc) = l;
+                    }
+                }
             }
             crow += (size_t)RSTEP * GROUP * ldc;
             if (mask) mrow += (size_t)RSTEP * GROUP * ldm;
@@ -396,7 +408,10 @@ __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *bar_done_p,
                     float x = stage_c[r * LDS + c] + bv + prev[j];
                     if (relu) x = fmaxf(x, 0.f);
                     x = mk[j] > 0.f ? x : 0.f;
-                    if (gm < M) Cz[(size_t)gm * ldc + gn] = x;
+                    if (gm < M) {
+                        Cz[(size_t)gm * ldc + gn] = x;
+                        if (Clz) Clz[(size_t)gm * ldc + gn] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                    }
                 }
             }
         }
@@ -409,7 +424,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS)
 tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, long long sak,
                const float *__restrict__ B, long long sbn, long long sbk, float *__restrict__ C, int ldc,
                const float *__restrict__ bias, int relu, const float *__restrict__ mask, int ldm, int accumulate,
-               int k_chunk, int nseg, const float *__restrict__ B2, const float *__restrict__ bias2)
+               int k_chunk, int nseg, const float *__restrict__ B2, const float *__restrict__ bias2, float *__restrict__ C_lo)
 {
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;                  // hi (+ lo) copy of every operand tile
     constexpr int B_TILE_BYTES = BN * BK * 4;
@@ -611,7 +626,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
         }
     }
 
-    tc_epilogue<BN, NSPLIT == 3>(smem, &bar_done, tmem_d, nkb, M, N, m0, n0, bn0, C, ldc, biasp, relu, mask, ldm, accumulate);
+    tc_epilogue<BN, NSPLIT == 3>(smem, &bar_done, tmem_d, nkb, M, N, m0, n0, bn0, C, ldc, biasp, relu, mask, ldm, accumulate, C_lo);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -630,7 +645,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
 template <int AMODE, int BMODE, int NSPLIT, int BN, bool ASYNC = false>
 int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
            const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias, int relu,
-           const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2, const float *bias2)
+           const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2, const float *bias2, float *C_lo)
 {
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;
     constexpr int STAGES = tc_stages<NSPLIT, BN, ASYNC>();
@@ -648,7 +663,7 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
         configured[dev] = true;
     }
     HRP_CUDA_OK(hrp_launch_pdl(kern, grid, dim3(TC_LAUNCH_THREADS), (size_t)SMEM, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc,
-                               bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2));
+                               bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo));
     return 0;
 }
 
@@ -656,9 +671,9 @@ template <int AMODE, int BMODE>
 int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
              long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
              int relu, const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2,
-             const float *bias2)
+             const float *bias2, float *C_lo)
 {
-#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2
+#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo
     if (bn == 64) return nsplit == 3 ? launch<AMODE, BMODE, 3, 64>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 64>(HRP_TC_ARGS);
     return nsplit == 3 ? launch<AMODE, BMODE, 3, 128>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 128>(HRP_TC_ARGS);
 #undef HRP_TC_ARGS
@@ -668,9 +683,9 @@ int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K,
 int dispatch_async(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
                    long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
                    int relu, const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2,
-                   const float *bias2)
+                   const float *bias2, float *C_lo)
 {
-#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2
+#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo
     if (bn == 64)
         return nsplit == 3 ? launch<ST_K4, ST_K2, 3, 64, true>(HRP_TC_ARGS) : launch<ST_K4, ST_K2, 1, 64, true>(HRP_TC_ARGS);
     return nsplit == 3 ? launch<ST_K4, ST_K2, 3, 128, true>(HRP_TC_ARGS) : launch<ST_K4, ST_K2, 1, 128, true>(HRP_TC_ARGS);
@@ -685,7 +700,8 @@ inline bool aligned(const void *p, int bytes) { return ((uintptr_t)p % bytes) ==
 // nsplit: 3 = 3xTF32 (fp32-grade accuracy), 1 = single TF32 pass.
 int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
-                int accumulate, int splits, int nsplit, cudaStream_t s, int nseg, const float *B2, const float *bias2)
+                int accumulate, int splits, int nsplit, cudaStream_t s, int nseg, const float *B2, const float *bias2,
+                float *C_lo)
 {
     int k_chunk = K;
     if (splits > 1) {
@@ -707,11 +723,11 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     const bool a_k4 = akc && K % 4 == 0 && sam % 4 == 0 && aligned(A, 16);
     const bool b_k2 = bkc && K % 2 == 0 && sbn % 2 == 0 && aligned(B, 8) && (nseg == 0 || aligned(B2, 8));
     const bool b_k4 = bkc && K % 4 == 0 && sbn % 4 == 0 && aligned(B, 16) && (nseg == 0 || aligned(B2, 16));
-#define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2)
+#define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo)
     int rc;
     // cp.async staging pays off for the single-pass mode only (measured: 3xTF32 hidden forward 12.6 us register-staged
     // vs 14.5 us cp.async -- the lo tiles need a second pass through shared memory; TF32 H=512 19.6 -> 16.6 us)
-    if (a_k4 && b_k2 && nsplit == 1) rc = dispatch_async(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2);
+    if (a_k4 && b_k2 && nsplit == 1) rc = dispatch_async(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo);
     else if (a_k4 && b_k4) rc = HRP_TC_GO(ST_K4, ST_K4);
     else if (a_k4 && b_k2) rc = HRP_TC_GO(ST_K4, ST_K2);
     else if (a_k4 && sbn == 1) rc = HRP_TC_GO(ST_K4, ST_MN1);

@@ -741,13 +741,15 @@ struct hrp_ppo {
 int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
                 int accumulate, int splits, int nsplit, cudaStream_t s, int nseg = 0, const float *B2 = nullptr,
-                const float *bias2 = nullptr);
+                const float *bias2 = nullptr, float *C_lo = nullptr);
 
 // TMA-fed 3xTF32 path on pre-split operands (hrp_gemm_tma.cu)
 int hrp_tma_gemm(int M, int N, int K, const float *A, const float *A_lo, long long sam, long long sak, const float *B,
                  const float *B_lo, long long sbn, long long sbk, float *C, float *C_lo, int ldc, const float *bias, int relu,
                  const float *mask, int ldm, int splits, int bn_hint, cudaStream_t s);
 int hrp_split_lo(const float *x, float *lo, long long n, cudaStream_t s);
+bool hrp_tma_gemm_ok(int M, int N, int K, const float *A, long long sam, long long sak, const float *A_lo, const float *B,
+                     long long sbn, long long sbk, const float *B_lo);
 
 // math mode of the hidden-layer GEMMs: 0 = fp32 SIMT, 1 = TF32 tcgen05, 3 = 3xTF32 tcgen05 (default)
 static int g_math_mode = 3;
@@ -803,7 +805,18 @@ static int colsum(ReducePlan &plan, float *part, const float *G, int ldg, long l
     return 0;
 }
 
-static bool use_tma(const hrp_ppo *h) { return g_math_mode == 3 && h->tma_capable && !getenv("HRP_NO_TMA"); }
+// The TMA-fed GEMM path (hrp_gemm_tma.cu) is OPT-IN (HRP_TMA=1).  Measured on B200 (B = 4096, H = 256,
+// profiles/r02_gemm_bench.txt, r02_timeline_*.txt): alone, its kernel beats the register-staged one on every hidden
+// shape (9.2 against 13.4 us for 4096 x 256 x 256, 12.9 against 18.2 us for K = 512, 9 us against 24 us for the
+// batch-contracting weight gradients), but one CTA owns an SM (192 KB of operand stages): the next kernel of a
+// dependent-launch chain cannot set itself up beside it and the side-stream GEMMs cannot share its SMs, and the whole
+// optimizer step comes out at 136 us against 131 us, the policy forward at 40 against 37 us.  The default therefore
+// stays the register-staged kernel (96 KB, two CTAs per SM).
+static bool use_tma(const hrp_ppo *h)
+{
+    const char *e = getenv("HRP_TMA");
+    return g_math_mode == 3 && h->tma_capable && e && e[0] == '1';
+}
 
 // aligned weight copies + lo parts + stacked bias for the TMA GEMMs; skipped while the caller holds them valid
 static int prepare_weights(hrp_ppo *h, const float *params, cudaStream_t s)
@@ -823,9 +836,26 @@ static int forward_tma(hrp_ppo *h, const float *params, const float *x, const fl
 {
     const Layout &L = h->L;
     const int H = L.H, S = L.S, Bi = (int)B;
-    if (hrp_tma_gemm(Bi, H, S, x, x_lo, S, 1, h->w1p, h->w1p_lo, S, 1, h->h1, h->h1_lo, H, params + L.b1, 1, nullptr, 0, 1, 0, s) < 0) return -2;
+    // Which kernel serves which layer is a measured choice (tools/gemm_bench.py, tools/trace_update.py, B = 4096):
+    // the short-K first layer and the 2H-wide [actor | critic] layer are faster register-staged (6.0 / 14 us in the
+    // step against 9.3 / 18 us TMA-fed: two CTAs per SM, and no lo twin to write for [a1 | c1], which feeds the heads),
+    // the H x H trunk layer is faster TMA-fed (8.4 against 10.1 us).  HRP_TMA_ALL=1 sends all three through TMA.
+    static const bool tma_all = getenv("HRP_TMA_ALL") != nullptr;
+    (void)x_lo;
+    if (tma_all) {
+        if (hrp_tma_gemm(Bi, H, S, x, x_lo, S, 1, h->w1p, h->w1p_lo, S, 1, h->h1, h->h1_lo, H, params + L.b1, 1, nullptr, 0, 1, 0, s) < 0) return -2;
+    } else {
+        if (hrp_tc_gemm(Bi, H, S, x, S, 1, params + L.w1, S, 1, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, 3, s, 0, nullptr, nullptr, h->h1_lo) < 0) return -2;
+    }
     if (hrp_tma_gemm(Bi, H, H, h->h1, h->h1_lo, H, 1, h->w2p, h->w2p_lo, H, 1, h->h2, h->h2_lo, H, params + L.b2, 1, nullptr, 0, 1, 0, s) < 0) return -2;
-    if (hrp_tma_gemm(Bi, 2 * H, H, h->h2, h->h2_lo, H, 1, h->wacp, h->wacp_lo, H, 1, h->ac, h->ac_lo, 2 * H, h->bacp, 1, nullptr, 0, 1, 0, s) < 0) return -2;
+    // [a1 | c1] feeds the heads, not another GEMM: no lo twin
+    if (tma_all) {
+        if (hrp_tma_gemm(Bi, 2 * H, H, h->h2, h->h2_lo, H, 1, h->wacp, h->wacp_lo, H, 1, h->ac, nullptr, 2 * H, h->bacp, 1, nullptr, 0, 1, 0, s) < 0) return -2;
+    } else {
+        if (hrp_tc_gemm(Bi, 2 * H, H, h->h2, H, 1, params + L.wa1, H, 1, h->ac, 2 * H, params + L.ba1, 1, nullptr, 0, 0, 1, 3, s, H,
+                        params + L.wc1, params + L.bc1) < 0)
+            return -2;
+    }
     return 0;
 }
 
@@ -839,7 +869,8 @@ static int forward_impl(hrp_ppo *h, const float *params, const float *x, long lo
     if (use_tma(h) && Bi >= 32) {
         // external states: their lo part is formed here (inside the update it comes from the gather kernel)
         if (int rc = prepare_weights(h, params, s)) return rc;
-        if (int rc = hrp_split_lo(x, h->x_lo, B * S, s)) return rc;
+        if (getenv("HRP_TMA_ALL"))
+            if (int rc = hrp_split_lo(x, h->x_lo, B * S, s)) return rc;
         if (int rc = forward_tma(h, params, x, h->x_lo, B, s)) return rc;
         if (!mean) return 0;
         heads_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(h->ac, h->ac + H, params + L.wa2, params + L.ba2, params + L.wc2,
@@ -893,6 +924,19 @@ int hrp_gemm_strided(int32_t M, int32_t N, int32_t K, const float *A, int64_t sa
 {
     if (!A || !B || !C || M < 1 || N < 1 || K < 1 || ldc < N) { hrp_set_error("hrp_gemm_strided: bad arguments"); return -1; }
     if (mode != 1 && mode != 3) { hrp_set_error("hrp_gemm_strided: mode must be 1 (TF32) or 3 (3xTF32)"); return -1; }
+    if (mode == 3 && !getenv("HRP_NO_TMA") && hrp_tma_gemm_ok(M, N, K, A, sam, sak, A, B, sbn, sbk, B)) {   // (tests, tools)
+        // the TMA path wants the operands pre-split: form the lo parts in temporaries on the caller's stream
+        cudaStream_t s = (cudaStream_t)stream;
+        const size_t na = sak == 1 ? (size_t)M * sam : (size_t)K * sak, nb = sbk == 1 ? (size_t)N * sbn : (size_t)K * sbk;
+        float *lo = nullptr;
+        HRP_CUDA_OK(cudaMallocAsync(&lo, (na + nb + 64) * sizeof(float), s));
+        float *a_lo = lo, *b_lo = lo + (na + 31) / 32 * 32;
+        int rc = hrp_split_lo(A, a_lo, (long long)na, s);
+        if (!rc) rc = hrp_split_lo(B, b_lo, (long long)nb, s);
+        if (!rc) rc = hrp_tma_gemm(M, N, K, A, a_lo, sam, sak, B, b_lo, sbn, sbk, C, nullptr, ldc, bias, relu, nullptr, 0, 1, 0, s);
+        HRP_CUDA_OK(cudaFreeAsync(lo, s));
+        return rc < 0 ? rc : 0;
+    }
     int rc = hrp_tc_gemm(M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, nullptr, 0, 0, 1, mode,
                          (cudaStream_t)stream);
     return rc < 0 ? rc : 0;
@@ -967,6 +1011,14 @@ int hrp_ppo_destroy(hrp_ppo *h)
     for (int q = 0; q < 2; ++q) if (h->side[q]) cudaStreamDestroy(h->side[q]);
     for (int q = 0; q < 8; ++q) if (h->ev[q]) cudaEventDestroy(h->ev[q]);
     delete h;
+    return 0;
+}
+
+int hrp_ppo_hold_weights(hrp_ppo *h, int32_t hold)
+{
+    if (!h) { hrp_set_error("hrp_ppo_hold_weights: null handle"); return -1; }
+    h->hold_prepared = hold != 0;
+    if (!hold) h->prepared_for = nullptr;
     return 0;
 }
 
@@ -1078,7 +1130,10 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
                                    grad + L.log_std, metrics, h->loss_part, h->loss_counter));
         ReducePlan plan;
         plan.nseg = 0; plan.blocks = 0;
-        int splits = (int)((B + 255) / 256);
+        // split-K over the batch: 512 rows (16 K-blocks) per CTA.  The three weight-gradient GEMMs of H = 256 are then
+        // 64 + 64 + 16 CTAs, one wave of the 148 SMs together (a TMA GEMM CTA owns its SM: 192 KB of shared memory)
+        int splits = (int)((B + 511) / 512);
+        if (const char *e = getenv("HRP_WGRAD_ROWS")) splits = (int)((B + atoi(e) - 1) / atoi(e));
         if (splits > h->splits_cap) splits = h->splits_cap;
         if (splits < 1) splits = 1;
         // dW[N_out, K_in] = dY^T X over the batch: A(m, k) = dY[k, m], B(n, k) = X[k, n], both MN-major
@@ -1110,9 +1165,9 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
         if (hrp_tma_gemm(Bi, H, H2, h->d12, h->d12_lo, H2, 1, h->wacp, h->wacp_lo, 1, H, h->dh2, h->dh2_lo, H, nullptr, 0, h->h2, H,
                          1, 0, s) < 0)
             return -2;
-        HRP_CUDA_OK(after(4, s, s1));
-        if (wgrad_tma(h->part_w[1], H, H, h->dh2, h->dh2_lo, H, h->h1, h->h1_lo, H, grad + L.w2, H, nullptr, s1)) return -2;
-        if (colsum(plan, h->part_b[1], h->dh2, H, B, H, grad + L.b2, H, nullptr, s1)) return -2;
+        HRP_CUDA_OK(after(4, s, s0));   // side 0 (behind the heads): dW2, db2 -- side 1 is busy with [dWa1 ; dWc1]
+        if (wgrad_tma(h->part_w[1], H, H, h->dh2, h->dh2_lo, H, h->h1, h->h1_lo, H, grad + L.w2, H, nullptr, s0)) return -2;
+        if (colsum(plan, h->part_b[1], h->dh2, H, B, H, grad + L.b2, H, nullptr, s0)) return -2;
         // main: d(h1) = d(h2) W2 (.) (h1 > 0); dW1; side 0: db1
         if (hrp_tma_gemm(Bi, H, H, h->dh2, h->dh2_lo, H, 1, h->w2p, h->w2p_lo, 1, H, h->dh1, h->dh1_lo, H, nullptr, 0, h->h1, H, 1,
                          0, s) < 0)

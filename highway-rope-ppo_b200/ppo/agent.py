@@ -101,6 +101,11 @@ class ActorCritic:
         # exploration noise is keyed by (seed, global row, draw), so shards draw different noise and a sharded
         # rollout reproduces the single-process one
         self.row_base = 0
+        # the native weight copies of the tensor-core path are kept across forward / act calls while the parameters
+        # are unchanged: torch's version counter sees every in-place torch write to the flat buffer (load_state_dict,
+        # copy_ through a view), `native_updates` counts the optimizer steps the library applied through raw pointers
+        self.native_updates = 0
+        self._held_key = None
 
     def _ensure_workspace(self, batch: int) -> None:
         if batch <= self.max_batch:
@@ -160,6 +165,17 @@ class ActorCritic:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _sync_weight_copies(self) -> None:
+        """Before a forward / act call: let the library reuse its weight copies if nothing wrote the parameters."""
+        key = (self.flat._version, self.native_updates, self._h.value, self.workspace_generation)
+        if key != self._held_key:
+            self._lib.hrp_ppo_hold_weights(self._h, 0)   # refresh on this call ...
+            self._held_key = key
+            self._hold_next = True
+        elif getattr(self, "_hold_next", False):
+            self._lib.hrp_ppo_hold_weights(self._h, 1)   # ... and keep from the next one on
+            self._hold_next = False
+
     def _as_states(self, x) -> torch.Tensor:
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
@@ -177,6 +193,7 @@ class ActorCritic:
         self._ensure_workspace(B)
         mean = torch.empty((B, self.action_dim), dtype=torch.float32, device=self.device)
         value = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+        self._sync_weight_copies()
         _lib.check(self._lib.hrp_ppo_forward(self._h, self.flat.data_ptr(), xb.data_ptr(), B, mean.data_ptr(),
                                              value.data_ptr(), self._stream()), "hrp_ppo_forward")
         std = self.log_std.exp()
@@ -199,6 +216,7 @@ class ActorCritic:
                    "pre_tanh": torch.empty((B, A), dtype=torch.float32, device=self.device),
                    "log_prob": torch.empty(B, dtype=torch.float32, device=self.device),
                    "value": torch.empty(B, dtype=torch.float32, device=self.device)}
+        self._sync_weight_copies()
         if not deterministic and noise is None:
             # standard normals drawn in the kernel (Philox keyed by a seed taken from torch's generator at
             # construction, so set_random_seeds() still fixes the rollout; one draw counter per call)
@@ -505,6 +523,7 @@ class PPOAgent:
     # -- one optimizer step on minibatch ``idx`` (device int64) ----------------------------------
     def _minibatch_step(self, flat: Dict[str, torch.Tensor], idx: Optional[torch.Tensor], B: int, world: int) -> None:
         ac, opt, s = self.actor_critic, self.optimizer, self.actor_critic._stream()
+        ac.native_updates += 1   # the parameters change through raw pointers: the held weight copies are stale
         _lib.check(self._lib.hrp_ppo_loss_grad(
             ac._h, ac.flat.data_ptr(), flat["states"].data_ptr(), flat["pre_tanh"].data_ptr(),
             flat["log_prob"].data_ptr(), flat["adv"].data_ptr(), flat["ret"].data_ptr(), _lib.ptr(idx), B,
@@ -570,6 +589,7 @@ class PPOAgent:
                         self._minibatch_step(st["buf"], st["perm"][start:start + B], B, world)
                     st["graphs"][i] = g
                 g.replay()
+                ac.native_updates += 1
                 self.launches += 2
 
     # -- PPOAgent.update (agent.py:196-308) --------------------------------------------------------

@@ -25,7 +25,15 @@ CASES = [  # (M, N, K, a_k_contig, b_k_contig)
     (4096, 256, 256, True, False),   # dX = dY W: B(n,k) = W[k, n]
     (256, 256, 4096, False, False),  # dW = dY^T X: both batch-major
     (256, 60, 4096, False, False),   # dW1
-    (100, 70, 45, True, True),       # ragged edges everywhere
+    (4096, 512, 256, True, True),    # [actor | critic] hidden layer: 128-wide N tiles
+    (4096, 256, 512, True, False),   # d(h2): K = 2H against W[k, n]
+    (512, 256, 4096, False, False),  # [dWa1 ; dWc1]
+    (64, 256, 60, True, True),       # the reference's minibatch sizes (main.py:53): one partial M tile
+    (32, 128, 128, True, False),
+    (200, 96, 72, True, True),       # ragged M / N / K with 16-byte aligned pitches (tensor-map path)
+    (72, 200, 136, False, False),
+    (136, 72, 200, False, True),
+    (100, 70, 45, True, True),       # ragged edges everywhere, unaligned pitches (register-staged fallback)
     (129, 257, 33, False, True),
     (32, 32, 8, True, True),
 ]
