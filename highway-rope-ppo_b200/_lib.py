@@ -79,6 +79,7 @@ SIGNATURES: Dict[str, Any] = {
     "hrp_env_step_host_on": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hrp_env_set_trace": (C.c_int, [_vp, _vp]),
     "hrp_env_trace_shape": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "hrp_env_step_host_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hrp_env_get_state": (C.c_int, [_vp, C.POINTER(HrpState)]),
     "hrp_env_set_state": (C.c_int, [_vp, C.POINTER(HrpState)]),
     "hrp_philox4x32_10": (C.c_int, [_vp, _vp, _vp]),
@@ -102,6 +103,9 @@ SIGNATURES: Dict[str, Any] = {
     "hrp_comm_create": (C.c_int, [_i32, _i32, _i64, _i32, C.POINTER(_vp), _vp]),
     "hrp_comm_connect": (C.c_int, [_vp, _vp]),
     "hrp_comm_grad": (_vp, [_vp]),
+    "hrp_comm_grad_parity": (_vp, [_vp, _i32]),
+    "hrp_comm_parity": (C.c_int, [_vp]),
+    "hrp_comm_note_replay": (C.c_int, [_vp]),
     "hrp_clip_adam_step_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _f64, _f32, _vp, _vp]),
     "hrp_comm_status": (C.c_int, [_vp]),
     "hrp_comm_destroy": (C.c_int, [_vp]),

@@ -313,7 +313,7 @@ static bool is_pinned(const void *p)
 // `actions` may be pageable host, page-locked host or device memory (a device action, e.g. the policy kernel's
 // output on `s`, is used in place: no H2D copy and no synchronisation between the policy and the step)
 static int step_host_impl(hrp_env *h, const float *actions, float *obs_host, float *reward_host,
-                          uint8_t *terminated_host, uint8_t *truncated_host, cudaStream_t s)
+                          uint8_t *terminated_host, uint8_t *truncated_host, cudaStream_t s, bool sync = true)
 {
     if (!h || !actions || !obs_host || !reward_host || !terminated_host || !truncated_host) {
         hrp_set_error("hrp_env_step_host: null argument");
@@ -331,6 +331,10 @@ static int step_host_impl(hrp_env *h, const float *actions, float *obs_host, flo
     }
     const bool pin_o = is_pinned(obs_host);
     const bool pin_r = is_pinned(reward_host) && is_pinned(terminated_host) && is_pinned(truncated_host);
+    if (!sync && (!pin_o || !pin_r || !(dev_a || pin_a))) {
+        hrp_set_error("hrp_env_step_host_async: every host buffer must be page-locked (the copies complete after the call returns)");
+        return -1;
+    }
     const float *d_act = actions;
     if (!dev_a) {
         if (!pin_a) memcpy(h->h_actions, actions, E * 2 * sizeof(float));
@@ -344,6 +348,7 @@ static int step_host_impl(hrp_env *h, const float *actions, float *obs_host, flo
     HRP_CUDA_OK(cudaMemcpyAsync(pin_r ? reward_host : h->h_reward, h->d_reward, E * sizeof(float), cudaMemcpyDeviceToHost, s));
     HRP_CUDA_OK(cudaMemcpyAsync(pin_r ? terminated_host : h->h_term, h->d_term, E, cudaMemcpyDeviceToHost, s));
     HRP_CUDA_OK(cudaMemcpyAsync(pin_r ? truncated_host : h->h_trunc, h->d_trunc, E, cudaMemcpyDeviceToHost, s));
+    if (!sync) return 0;   // the caller synchronises with the stream (an event after this call) before it reads the results
     HRP_CUDA_OK(cudaStreamSynchronize(s));
     if (!pin_o) memcpy(obs_host, h->h_obs, no * sizeof(float));
     if (!pin_r) {
@@ -366,6 +371,12 @@ int hrp_env_step_host_on(hrp_env *h, const float *actions, float *obs_host, floa
                          uint8_t *terminated_host, uint8_t *truncated_host, void *stream)
 {
     return step_host_impl(h, actions, obs_host, reward_host, terminated_host, truncated_host, (cudaStream_t)stream);
+}
+
+int hrp_env_step_host_async(hrp_env *h, const float *actions, float *obs_host, float *reward_host,
+                            uint8_t *terminated_host, uint8_t *truncated_host, void *stream)
+{
+    return step_host_impl(h, actions, obs_host, reward_host, terminated_host, truncated_host, (cudaStream_t)stream, false);
 }
 
 int hrp_env_reset_host(hrp_env *h, uint64_t seed, float *obs_host)

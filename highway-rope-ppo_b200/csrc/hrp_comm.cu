@@ -3,15 +3,25 @@
 // Every rank (one process per GPU, same box) holds the gradient of its shard of the minibatch in a buffer that its
 // peers can read through NVLink (cudaIpc).  `hrp_clip_adam_step_p2p` is ONE cooperative kernel per optimizer step:
 //
-//   1. cross-GPU barrier: "my gradient is complete" flags written into every peer, wait for every peer's flag;
-//   2. every CTA sums its slice of the W gradients in rank order (peer loads over NVLink; the same order on every
-//      rank, so all ranks hold bit-identical sums), keeps the sum locally and accumulates its square;
-//   3. grid.sync(), fixed-order total -> clip coefficient (clip_grad_norm_, agent.py:249);
-//   4. Adam on the slice (agent.py:252), step counter;
-//   5. cross-GPU barrier: "I have finished reading" -- after it a rank may overwrite its gradient buffer.
+//   1. "my gradient of step e is complete": an epoch word written into every peer's flag block; every CTA polls the
+//      W words of its own block (no grid-wide barrier around the cross-GPU wait);
+//   2. REDUCE-SCATTER: rank r sums ONLY its 1/W slice of the W gradients, in rank order, with peer loads over NVLink
+//      (n (W-1)/W floats read per rank instead of n (W-1));
+//   3. ALL-GATHER by push: rank r stores its reduced slice into the `sum` buffer of every rank (its own included) and
+//      then raises the per-source epoch word "slice r of step e has arrived" in every peer -- the data flag IS the
+//      synchronisation, there is no separate barrier;
+//   4. every CTA waits for the W slice words, reads the complete sum (local memory now; the same values in the same
+//      order on every rank, hence bit-identical parameters), accumulates its square;
+//   5. grid.sync(), fixed-order total -> clip coefficient (clip_grad_norm_, agent.py:249), Adam (agent.py:252).
+//
+// There is NO "done reading" barrier: the gradient and the sum buffers are DOUBLE-BUFFERED by step parity.  A rank
+// overwrites its parity-p buffers at step e + 2, i.e. after its step e + 1 kernel has finished, which waited for every
+// peer's "gradient e + 1 complete" word, which a peer raises only after its own step e kernel (the last reader / writer
+// of the parity-p buffers of step e) has finished, by stream order.
 //
 // It replaces all_reduce(grad) + gradnorm + clip + Adam (NCCL launch + 1 kernel) of the NCCL path.  The flags carry
-// a monotonically increasing epoch kept in device memory, so the launch can be captured in a CUDA graph and replayed.
+// a monotonically increasing epoch kept in device memory, so the launch can be captured in a CUDA graph and replayed;
+// the parity is a launch parameter (the host alternates it; a captured graph keeps the parity it was captured with).
 // Kernels of different ranks spin on each other: every rank owns its GPU (never run two ranks on one device).
 #include <cooperative_groups.h>
 #include <math.h>
@@ -24,11 +34,11 @@
 struct hrp_comm {
     int world, rank, device;
     long long n;             // floats per gradient
-    float *local;            // [grad n | sum n | flags], the IPC-exported allocation
+    long long npad;          // n rounded up to 32 floats
+    float *local;            // [grad parity 0 | grad parity 1 | sum parity 0 | sum parity 1 | flags], the IPC-exported allocation
     void *peer_base[HRP_MAX_RANKS];
-    float *peer_grad[HRP_MAX_RANKS];
-    unsigned *peer_flags[HRP_MAX_RANKS];   // each rank's flag block: ready[HRP_MAX_RANKS], done[HRP_MAX_RANKS]
     unsigned *epoch;         // device: [0] counter of completed steps, [1] timeout bits of the cross-GPU waits
+    unsigned long long issued;   // optimizer steps enqueued so far (host): the parity of the next one
     bool connected;
 };
 
@@ -36,9 +46,10 @@ namespace {
 
 constexpr int P2P_MAX_CTAS = 120, P2P_THREADS = 512;
 
+// flag block of a rank, [2 kinds][HRP_MAX_RANKS] epoch words: kind 0 = "rank q's gradient is complete", kind 1 = "rank
+// q's reduced slice has arrived here"; word q is written by rank q
 struct PeerTable {
-    const float *grad[HRP_MAX_RANKS];
-    unsigned *flags[HRP_MAX_RANKS];
+    float *base[HRP_MAX_RANKS];   // every rank's exported allocation as mapped here
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
@@ -52,47 +63,81 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
     return v;
 }
 
-// flag block of a rank: ready[q] / done[q] are written by rank q.  The wait is bounded (about fifteen seconds of SM
-// clock): a rank that never arrives -- a crashed peer -- must not leave this GPU spinning; the timeout is recorded in
-// *status (bit `which`) and the step goes on with whatever the peer buffers hold, for the host to detect.
-__device__ __forceinline__ void cross_gpu_barrier(const PeerTable &T, int world, int rank, int which, unsigned epoch,
-                                                  unsigned *status)
+// wait until the W epoch words of `kind` in this rank's own flag block have reached `epoch`.  Called by a whole CTA:
+// thread q < W polls word q.  Bounded (about fifteen seconds of SM clock): a peer that never arrives -- a crashed
+// process -- must not leave this GPU spinning; the timeout is recorded in *status (bit `kind`) and the step goes on
+// with whatever the buffers hold, for the host to detect (hrp_comm_status).
+__device__ __forceinline__ void wait_words(const unsigned *mine, int world, int kind, unsigned epoch, unsigned *status)
 {
-    // called by the first `world` threads of CTA 0
-    const int q = threadIdx.x;
-    if (q < world) {
-        __threadfence_system();
-        st_release_sys(T.flags[q] + which * HRP_MAX_RANKS + rank, epoch);
-        const unsigned *mine = T.flags[rank] + which * HRP_MAX_RANKS + q;
+    if ((int)threadIdx.x < world) {
+        const unsigned *w = mine + kind * HRP_MAX_RANKS + threadIdx.x;
         const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-            __nanosleep(64);
-            if (clock64() - t0 > 30000000000ll) { atomicOr(status, 1u << which); break; }
+        while ((int)(ld_acquire_sys(w) - epoch) < 0) {
+            __nanosleep(32);
+            if (clock64() - t0 > 30000000000ll) { atomicOr(status, 1u << kind); break; }
         }
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(P2P_THREADS)
-clip_adam_p2p_kernel(const PeerTable T, int world, int rank, unsigned *__restrict__ epoch_dev, float *__restrict__ gsum,
+clip_adam_p2p_kernel(const PeerTable T, int world, int rank, int parity, long long npad, unsigned *__restrict__ epoch_dev,
                      float *__restrict__ p, float *__restrict__ m, float *__restrict__ v, int32_t *__restrict__ step,
                      long long n, double lr, double beta1, double beta2, double eps, float max_norm,
-                     float *__restrict__ part)
+                     float *__restrict__ part, unsigned *__restrict__ arrive)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ float red[P2P_THREADS / 32];
     __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+    __shared__ bool s_last;
+    // read before anything of this step is written (CTA 0 advances them at the very end, after the grid barrier)
     const unsigned epoch = *epoch_dev + 1u;
     const int k = step[0] + 1;
-    if (blockIdx.x == 0) cross_gpu_barrier(T, world, rank, 0, epoch, epoch_dev + 1);   // every gradient is complete
-    grid.sync();
+    unsigned *flags_of[HRP_MAX_RANKS];
+#pragma unroll
+    for (int q = 0; q < HRP_MAX_RANKS; ++q) flags_of[q] = q < world ? (unsigned *)(T.base[q] + 4 * npad) : nullptr;
+    unsigned *mine = flags_of[rank];
+    // 1. my gradient (written by the kernels before this one in the stream) is complete: tell every rank
+    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(flags_of[threadIdx.x] + 0 * HRP_MAX_RANKS + rank, epoch);
+    }
+    wait_words(mine, world, 0, epoch, epoch_dev + 1);
+    // 2. reduce-scatter: my slice [lo, hi) of the W gradients, rank order (identical on every rank)
+    const long long chunk = ((n + world - 1) / world + 3) / 4 * 4;
+    const long long lo = min(n, chunk * rank), hi = min(n, lo + chunk);
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = lo + i0; i < hi; i += stride) {
+        float g = 0.f;
+#pragma unroll
+        for (int q = 0; q < HRP_MAX_RANKS; ++q)
+            if (q < world) g += __ldcg(T.base[q] + (size_t)parity * npad + i);
+        // 3. all-gather by push: the reduced value goes into every rank's sum buffer
+#pragma unroll
+        for (int q = 0; q < HRP_MAX_RANKS; ++q)
+            if (q < world) __stcg(T.base[q] + (size_t)(2 + parity) * npad + i, g);
+    }
+    // the last CTA to finish its part of the slice raises "slice `rank` of step `epoch` has arrived" everywhere
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(arrive, 1u);
+        s_last = prev == gridDim.x - 1;
+        if (s_last) *arrive = 0u;
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(flags_of[threadIdx.x] + 1 * HRP_MAX_RANKS + rank, epoch);
+    }
+    // 4. the complete sum is local once every slice has arrived
+    wait_words(mine, world, 1, epoch, epoch_dev + 1);
+    const float *gsum = T.base[rank] + (size_t)(2 + parity) * npad;
     float s = 0.f;
     for (long long i = i0; i < n; i += stride) {
-        float g = 0.f;
-        for (int q = 0; q < world; ++q) g += __ldcg(T.grad[q] + i);      // rank order: identical on every rank
-        gsum[i] = g;
+        const float g = __ldcg(gsum + i);
         s = fmaf(g, g, s);
     }
 #pragma unroll
@@ -105,7 +150,7 @@ clip_adam_p2p_kernel(const PeerTable T, int world, int rank, unsigned *__restric
         part[blockIdx.x] = t;
     }
     grid.sync();
-    if (blockIdx.x == 0) cross_gpu_barrier(T, world, rank, 1, epoch, epoch_dev + 1);   // nobody reads my gradient any more
+    // 5. clip coefficient and Adam, as hrp_clip_adam_step
     if (threadIdx.x < 32) {
         float t = 0.f;
         for (int i = threadIdx.x * 4; i < min((int)gridDim.x, threadIdx.x * 4 + 4); ++i) t += __ldcg(part + i);
@@ -124,18 +169,18 @@ clip_adam_p2p_kernel(const PeerTable T, int world, int rank, unsigned *__restric
     const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), ep = (float)eps;
     const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
     for (long long i = i0; i < n; i += stride) {
-        float gi = gsum[i] * coef;
+        float gi = __ldcg(gsum + i) * coef;
         float mi = m[i] + w1 * (gi - m[i]);
         float vi = v[i] * b2 + w2 * gi * gi;
         m[i] = mi; v[i] = vi;
         float denom = sqrtf(vi) / bc2_sqrt + ep;
         p[i] = p[i] - step_size * (mi / denom);
     }
-    grid.sync();   // every CTA has read step[0] / *epoch_dev and passed both barriers
+    // every CTA read step[0] / *epoch_dev before the grid barrier above
     if (blockIdx.x == 0 && threadIdx.x == 0) { step[0] = k; *epoch_dev = epoch; }
 }
 
-inline size_t comm_floats(long long n) { return (size_t)(2 * ((n + 31) / 32 * 32) + 64); }
+inline size_t comm_floats(long long n) { return (size_t)(4 * ((n + 31) / 32 * 32) + 64); }
 
 }  // namespace
 
@@ -151,11 +196,12 @@ int hrp_comm_create(int32_t world, int32_t rank, int64_t n, int32_t device, hrp_
     HRP_CUDA_OK(cudaSetDevice(device));
     hrp_comm *c = new hrp_comm();
     c->world = world; c->rank = rank; c->device = device; c->n = n;
+    c->npad = (n + 31) / 32 * 32; c->issued = 0;
     size_t bytes = comm_floats(n) * sizeof(float);
     cudaError_t ce = cudaMalloc(&c->local, bytes);
     if (ce == cudaSuccess) ce = cudaMemset(c->local, 0, bytes);
-    if (ce == cudaSuccess) ce = cudaMalloc(&c->epoch, 2 * sizeof(unsigned));
-    if (ce == cudaSuccess) ce = cudaMemset(c->epoch, 0, 2 * sizeof(unsigned));
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->epoch, 4 * sizeof(unsigned));   // epoch, timeout bits, CTA arrival counter
+    if (ce == cudaSuccess) ce = cudaMemset(c->epoch, 0, 4 * sizeof(unsigned));
     cudaIpcMemHandle_t hd;
     if (ce == cudaSuccess) ce = cudaIpcGetMemHandle(&hd, c->local);
     if (ce != cudaSuccess) {
@@ -174,7 +220,6 @@ int hrp_comm_connect(hrp_comm *c, const void *handles)
 {
     if (!c || !handles) { hrp_set_error("hrp_comm_connect: null argument"); return -1; }
     HRP_CUDA_OK(cudaSetDevice(c->device));
-    const size_t pad = (size_t)((c->n + 31) / 32 * 32);
     for (int q = 0; q < c->world; ++q) {
         void *base = c->local;
         if (q != c->rank) {
@@ -183,15 +228,17 @@ int hrp_comm_connect(hrp_comm *c, const void *handles)
             HRP_CUDA_OK(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
         }
         c->peer_base[q] = base;
-        c->peer_grad[q] = (float *)base;
-        c->peer_flags[q] = (unsigned *)((float *)base + 2 * pad);
     }
     c->connected = true;
     return 0;
 }
 
-/* device pointer of this rank's gradient buffer (n floats): hrp_ppo_loss_grad writes it */
-float *hrp_comm_grad(hrp_comm *c) { return c ? c->local : nullptr; }
+/* device pointer of the gradient buffer (n floats) the NEXT hrp_clip_adam_step_p2p will exchange: hrp_ppo_loss_grad
+ * writes it.  The buffers alternate with the parity of the step. */
+float *hrp_comm_grad(hrp_comm *c) { return c ? c->local + (size_t)(c->issued & 1) * c->npad : nullptr; }
+/* the same for an explicit parity (0 / 1): callers that capture steps in CUDA graphs keep one graph per parity */
+float *hrp_comm_grad_parity(hrp_comm *c, int32_t parity) { return c ? c->local + (size_t)(parity & 1) * c->npad : nullptr; }
+int hrp_comm_parity(hrp_comm *c) { return c ? (int)(c->issued & 1) : -1; }
 
 int hrp_clip_adam_step_p2p(hrp_comm *c, float *params, float *exp_avg, float *exp_avg_sq, int32_t *step, double lr,
                            double beta1, double beta2, double eps, float max_grad_norm, float *scratch, void *stream)
@@ -211,20 +258,25 @@ int hrp_clip_adam_step_p2p(hrp_comm *c, float *params, float *exp_avg, float *ex
         if (max_ctas < 1) { hrp_set_error("hrp_clip_adam_step_p2p: kernel does not fit the device"); return -2; }
     }
     PeerTable T;
-    for (int q = 0; q < HRP_MAX_RANKS; ++q) {
-        T.grad[q] = q < c->world ? c->peer_grad[q] : nullptr;
-        T.flags[q] = q < c->world ? c->peer_flags[q] : nullptr;
-    }
-    long long n = c->n;
+    for (int q = 0; q < HRP_MAX_RANKS; ++q) T.base[q] = q < c->world ? (float *)c->peer_base[q] : nullptr;
+    long long n = c->n, npad = c->npad;
     int ctas = (int)((n + P2P_THREADS - 1) / P2P_THREADS);
     if (ctas > max_ctas) ctas = max_ctas;
-    int world = c->world, rank = c->rank;
-    unsigned *epoch = c->epoch;
-    float *gsum = c->local + (size_t)((n + 31) / 32 * 32);
-    void *args[] = {&T, &world, &rank, &epoch, &gsum, &params, &exp_avg, &exp_avg_sq, &step, &n, &lr, &beta1, &beta2, &eps,
-                    &max_grad_norm, &scratch};
+    int world = c->world, rank = c->rank, parity = (int)(c->issued & 1);
+    unsigned *epoch = c->epoch, *arrive = c->epoch + 2;
+    void *args[] = {&T, &world, &rank, &parity, &npad, &epoch, &params, &exp_avg, &exp_avg_sq, &step, &n, &lr, &beta1, &beta2,
+                    &eps, &max_grad_norm, &scratch, &arrive};
     HRP_CUDA_OK(cudaLaunchCooperativeKernel((const void *)clip_adam_p2p_kernel, dim3(ctas), dim3(P2P_THREADS), args, 0,
                                             (cudaStream_t)stream));
+    c->issued += 1;
+    return 0;
+}
+
+/* a captured graph replays the parity it was captured with: the host says which step it is about to replay */
+int hrp_comm_note_replay(hrp_comm *c)
+{
+    if (!c) { hrp_set_error("hrp_comm_note_replay: null argument"); return -1; }
+    c->issued += 1;
     return 0;
 }
 

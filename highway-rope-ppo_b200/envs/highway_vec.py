@@ -258,6 +258,20 @@ class HighwayVecEnv:
                                                terminated.ctypes.data, truncated.ctypes.data), "hrp_env_step_host")
         self.launches += 1
 
+    def step_host_async(self, actions: torch.Tensor, obs: np.ndarray, reward: np.ndarray, terminated: np.ndarray,
+                        truncated: np.ndarray) -> None:
+        """``step_host`` without the final synchronisation: the step kernel and the device-to-host copies are
+        enqueued on the current stream; the page-locked numpy buffers hold the results once that stream has reached
+        this point (record an event and wait for it).  ``actions`` is a CUDA tensor produced on the same stream."""
+        a = actions.contiguous()
+        if not a.is_cuda or a.dtype != torch.float32 or a.numel() != 2 * self.num_envs:
+            raise ValueError(f"actions must be a CUDA tensor of {self.num_envs} x 2 float32 values")
+        _lib.check(self._lib.hrp_env_step_host_async(self._h, a.data_ptr(), obs.ctypes.data, reward.ctypes.data,
+                                                     terminated.ctypes.data, truncated.ctypes.data,
+                                                     torch.cuda.current_stream(self.device).cuda_stream),
+                   "hrp_env_step_host_async")
+        self.launches += 1
+
     def reset_host(self, seed: int, obs: np.ndarray) -> None:
         self.seed = int(seed)
         _lib.check(self._lib.hrp_env_reset_host(self._h, self.seed & 0xFFFFFFFFFFFFFFFF, obs.ctypes.data),

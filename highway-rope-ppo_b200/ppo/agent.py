@@ -124,6 +124,8 @@ class ActorCritic:
             if self._h:
                 self._lib.hrp_ppo_destroy(self._h)
                 self._h = None
+            for hp, _ in self.__dict__.get("_lanes", {}).values():
+                self._lib.hrp_ppo_destroy(hp)
         except Exception:
             pass
 
@@ -205,10 +207,15 @@ class ActorCritic:
 
     # -- batched get_action: everything stays on the device -------------------------------------
     def act(self, states: torch.Tensor, noise: Optional[torch.Tensor] = None, deterministic: bool = False,
-            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
-        """``get_action`` for [B, S] states -> dict(action, pre_tanh [B, A]; log_prob, value [B])."""
+            out: Optional[Dict[str, torch.Tensor]] = None, lane: int = 0) -> Dict[str, torch.Tensor]:
+        """``get_action`` for [B, S] states -> dict(action, pre_tanh [B, A]; log_prob, value [B]).
+
+        ``lane`` > 0 selects a separate native workspace (same parameters) so that calls on different CUDA streams
+        may overlap: the two env groups of the pipelined host-buffer loop (bench.py e2e) act concurrently."""
         states = self._as_states(states)
         B = states.shape[0]
+        if lane:
+            return self._act_lane(states, B, out, lane, deterministic, noise)
         self._ensure_workspace(B)
         A = self.action_dim
         if out is None:
@@ -231,6 +238,33 @@ class ActorCritic:
                                          out["action"].data_ptr(), out["pre_tanh"].data_ptr(),
                                          out["log_prob"].data_ptr(), out["value"].data_ptr(), self._stream()),
                    "hrp_ppo_act")
+        return out
+
+    def _act_lane(self, states, B, out, lane, deterministic, noise):
+        """act() on an additional workspace (its GEMM scratch, weight copies and hold state are its own)."""
+        if deterministic or noise is not None:
+            raise ValueError("workspace lanes serve the sampling rollout path only")
+        lanes = self.__dict__.setdefault("_lanes", {})
+        h = lanes.get(lane)
+        if h is None or h[1] < B:
+            if h is not None:
+                torch.cuda.synchronize(self.device)
+                self._lib.hrp_ppo_destroy(h[0])
+            hp = C.c_void_p()
+            _lib.check(self._lib.hrp_ppo_create(self.state_dim, self.action_dim, self.hidden_dim, int(B), self.device.index,
+                                                C.byref(hp)), "hrp_ppo_create")
+            h = lanes[lane] = (hp, int(B))
+        A = self.action_dim
+        if out is None:
+            out = {"action": torch.empty((B, A), dtype=torch.float32, device=self.device),
+                   "pre_tanh": torch.empty((B, A), dtype=torch.float32, device=self.device),
+                   "log_prob": torch.empty(B, dtype=torch.float32, device=self.device),
+                   "value": torch.empty(B, dtype=torch.float32, device=self.device)}
+        self._draw += 1
+        _lib.check(self._lib.hrp_ppo_act_sample(h[0], self.flat.data_ptr(), states.data_ptr(), self._noise_seed, self._draw,
+                                                int(self.row_base), B, out["action"].data_ptr(), out["pre_tanh"].data_ptr(),
+                                                out["log_prob"].data_ptr(), out["value"].data_ptr(), self._stream()),
+                   "hrp_ppo_act_sample")
         return out
 
     # -- ActorCritic.get_action (agent.py:56-74): one state, numpy results -----------------------
@@ -457,9 +491,9 @@ class PPOAgent:
         return self.actor_critic.get_action(state, deterministic)
 
     def act(self, states: torch.Tensor, deterministic: bool = False, noise: Optional[torch.Tensor] = None,
-            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+            out: Optional[Dict[str, torch.Tensor]] = None, lane: int = 0) -> Dict[str, torch.Tensor]:
         self.launches += 1
-        return self.actor_critic.act(states, noise=noise, deterministic=deterministic, out=out)
+        return self.actor_critic.act(states, noise=noise, deterministic=deterministic, out=out, lane=lane)
 
     # -- distributed helpers (ppo/distributed.py) ---------------------------------------------------
     @staticmethod
@@ -500,14 +534,20 @@ class PPOAgent:
                 lib.hrp_comm_destroy(comm)
             self.use_p2p = False
             return False
-        ptr = lib.hrp_comm_grad(comm)
+        # the exchange double-buffers the gradient by step parity: two views of the exported allocation
+        self._comm_keep, self._grad_parity = [], []
+        for parity in (0, 1):
+            ptr = lib.hrp_comm_grad_parity(comm, parity)
 
-        class _Raw:  # torch.as_tensor wraps a raw device pointer through the CUDA array interface
-            __cuda_array_interface__ = {"shape": (P,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+            class _Raw:  # torch.as_tensor wraps a raw device pointer through the CUDA array interface
+                __cuda_array_interface__ = {"shape": (P,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
-        self._comm_keep = _Raw()
-        self.grad = torch.as_tensor(self._comm_keep, device=self.device)
-        assert self.grad.data_ptr() == int(ptr)
+            keep = _Raw()
+            view = torch.as_tensor(keep, device=self.device)
+            assert view.data_ptr() == int(ptr)
+            self._comm_keep.append(keep)
+            self._grad_parity.append(view)
+        self.grad = self._grad_parity[0]
         self._comm = comm
         return True
 
@@ -518,12 +558,14 @@ class PPOAgent:
             torch.cuda.synchronize(self.device)
             self.grad = torch.zeros(self.actor_critic.num_params, dtype=torch.float32, device=self.device)
             self._lib.hrp_comm_destroy(self._comm)
-            self._comm, self._comm_keep = None, None
+            self._comm, self._comm_keep, self._grad_parity = None, None, None
 
     # -- one optimizer step on minibatch ``idx`` (device int64) ----------------------------------
     def _minibatch_step(self, flat: Dict[str, torch.Tensor], idx: Optional[torch.Tensor], B: int, world: int) -> None:
         ac, opt, s = self.actor_critic, self.optimizer, self.actor_critic._stream()
         ac.native_updates += 1   # the parameters change through raw pointers: the held weight copies are stale
+        if world > 1 and self._comm is not None:
+            self.grad = self._grad_parity[self._lib.hrp_comm_parity(self._comm)]   # the buffer of this step's parity
         _lib.check(self._lib.hrp_ppo_loss_grad(
             ac._h, ac.flat.data_ptr(), flat["states"].data_ptr(), flat["pre_tanh"].data_ptr(),
             flat["log_prob"].data_ptr(), flat["adv"].data_ptr(), flat["ret"].data_ptr(), _lib.ptr(idx), B,
@@ -581,13 +623,18 @@ class PPOAgent:
                 st["warm"] = True
                 continue
             for i, start in enumerate(starts):
-                g = st["graphs"].get(i)
+                # the peer-memory exchange alternates its buffers with the step parity: one graph per (minibatch, parity)
+                parity = self._lib.hrp_comm_parity(self._comm) if (world > 1 and self._comm is not None) else 0
+                g = st["graphs"].get((i, parity))
                 if g is None:
                     B = min(bs, n - start)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        self._minibatch_step(st["buf"], st["perm"][start:start + B], B, world)
-                    st["graphs"][i] = g
+                        self._minibatch_step(st["buf"], st["perm"][start:start + B], B, world)   # (advances the parity)
+                    st["graphs"][(i, parity)] = g
+                elif world > 1 and self._comm is not None:
+                    _lib.check(self._lib.hrp_comm_note_replay(self._comm), "hrp_comm_note_replay")
+                    self.grad = self._grad_parity[parity]
                 g.replay()
                 ac.native_updates += 1
                 self.launches += 2

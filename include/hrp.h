@@ -151,6 +151,13 @@ int hrp_env_step_host_on(hrp_env *env, const float *actions, float *obs_host, fl
 int hrp_env_set_trace(hrp_env *env, double *trace_dev);
 int hrp_env_trace_shape(const hrp_env *env, int32_t *frames, int32_t *slots, int32_t *fields);
 
+/* the same WITHOUT the final synchronisation: kernel and device-to-host copies are enqueued on `stream` and the call
+ * returns; the results are in the host buffers once the stream has reached this point (record an event after the
+ * call and wait for it).  Every host buffer must be page-locked.  With two env handles on two streams one group's
+ * PCIe copies run under the other group's kernels (bench.py e2e). */
+int hrp_env_step_host_async(hrp_env *env, const float *actions, float *obs_host, float *reward_host,
+                            uint8_t *terminated_host, uint8_t *truncated_host, void *stream);
+
 /* state injection / extraction; synchronous */
 int hrp_env_get_state(hrp_env *env, hrp_state *dst_host);
 int hrp_env_set_state(hrp_env *env, const hrp_state *src_host);
@@ -242,17 +249,24 @@ int hrp_clip_adam_step(float *params_dev, const float *grad_dev, float *exp_avg_
                        void *stream);
 
 /* ---- the gradient exchange of the sharded PPO update, fused with clip + Adam (csrc/hrp_comm.cu) --------------
- * One process per GPU on one box.  hrp_comm_create allocates this rank's peer-readable gradient buffer and returns
- * its 64-byte cudaIpc handle; the caller gathers the handles of all ranks (rank-major) and passes them to
+ * One process per GPU on one box.  hrp_comm_create allocates this rank's peer-visible buffers and returns their
+ * 64-byte cudaIpc handle; the caller gathers the handles of all ranks (rank-major) and passes them to
  * hrp_comm_connect.  hrp_ppo_loss_grad then writes hrp_comm_grad(), and hrp_clip_adam_step_p2p replaces
- * all_reduce(grad) + hrp_clip_adam_step: ONE cooperative kernel that waits for every rank's gradient, sums the W
- * gradients in rank order over NVLink (bit-identical on every rank), clips, applies Adam and signals completion.
- * Every rank must call it once per optimizer step; ranks must own different devices. */
+ * all_reduce(grad) + hrp_clip_adam_step: ONE cooperative kernel that waits for every rank's gradient, reduces this
+ * rank's 1/W slice over NVLink in rank order, pushes the reduced slice to every rank (reduce-scatter + all-gather,
+ * the arrival flags are the only synchronisation), clips and applies Adam -- bit-identical parameters on every
+ * rank.  Gradient and sum buffers are double-buffered by step parity, so there is no "done reading" barrier:
+ * hrp_comm_grad() is the buffer of the NEXT step and alternates.  Every rank must call the step once per optimizer
+ * step; ranks must own different devices.  A caller that replays a captured step keeps one graph per parity and
+ * announces every replay with hrp_comm_note_replay. */
 typedef struct hrp_comm hrp_comm;
 int hrp_comm_create(int32_t world, int32_t rank, int64_t n_floats, int32_t device, hrp_comm **out,
                     void *ipc_handle_out64);
 int hrp_comm_connect(hrp_comm *comm, const void *ipc_handles /* world x 64 bytes */);
 float *hrp_comm_grad(hrp_comm *comm);
+float *hrp_comm_grad_parity(hrp_comm *comm, int32_t parity);
+int hrp_comm_parity(hrp_comm *comm);          /* parity of the next step (0 / 1) */
+int hrp_comm_note_replay(hrp_comm *comm);     /* a captured step is about to be replayed */
 int hrp_clip_adam_step_p2p(hrp_comm *comm, float *params_dev, float *exp_avg_dev, float *exp_avg_sq_dev,
                            int32_t *step_dev, double lr, double beta1, double beta2, double eps,
                            float max_grad_norm, float *scratch_dev /* >=128 floats */, void *stream);

@@ -593,3 +593,43 @@ def test_kernel_observation_clip_by_hand(highway_config):
     np.testing.assert_allclose(obs[2], [1.0, 0.04, -3.0 / 30.0, 0.0], atol=1e-6)
     assert np.all(obs[3:] == 0.0)
     env.close()
+
+
+def test_async_host_step_in_two_groups_equals_one_env(highway_config):
+    """hrp_env_step_host_async on two env groups / two streams (the pipelined host-buffer loop of bench.py): the groups
+    own global env ids [0, 32) and [32, 64) and must reproduce a single 64-env handle; results are complete after the
+    group's event."""
+    E, half = 64, 32
+    whole = _vec(highway_config, E)
+    groups = [_vec(highway_config, half, env_id_base=g * half) for g in range(2)]
+    streams = [torch.cuda.Stream(device="cuda:0") for _ in range(2)]
+    events = [torch.cuda.Event() for _ in range(2)]
+    pin = lambda *shape, dtype=torch.float32: torch.zeros(shape, dtype=dtype).pin_memory()
+    bufs = [dict(obs=pin(half, 15, 4), rew=pin(half), te=pin(half, dtype=torch.uint8), tr=pin(half, dtype=torch.uint8))
+            for _ in range(2)]
+    want = whole.reset(9).cpu()
+    for g in range(2):
+        groups[g].reset_host(9, bufs[g]["obs"].numpy())
+        assert torch.equal(bufs[g]["obs"], want[g * half:(g + 1) * half])
+    gen = torch.Generator(device="cuda:0").manual_seed(4)
+    for t in range(6):
+        act = torch.rand((E, 2), generator=gen, device="cuda:0") * 2 - 1
+        o, r, te, tr = whole.step(act)
+        torch.cuda.synchronize()
+        for g in range(2):
+            with torch.cuda.stream(streams[g]):
+                b = bufs[g]
+                groups[g].step_host_async(act[g * half:(g + 1) * half], b["obs"].numpy(), b["rew"].numpy(), b["te"].numpy(),
+                                          b["tr"].numpy())
+                events[g].record()
+        for g in range(2):
+            events[g].synchronize()
+            sl = slice(g * half, (g + 1) * half)
+            assert torch.equal(bufs[g]["obs"], o[sl].cpu()) and torch.equal(bufs[g]["rew"], r[sl].cpu()), (t, g)
+            assert torch.equal(bufs[g]["te"], te[sl].cpu()) and torch.equal(bufs[g]["tr"], tr[sl].cpu())
+    with pytest.raises(Exception):   # pageable buffers cannot complete after the call returns
+        groups[0].step_host_async(act[:half], np.zeros((half, 15, 4), np.float32), np.zeros(half, np.float32),
+                                  np.zeros(half, np.uint8), np.zeros(half, np.uint8))
+    whole.close()
+    for g in groups:
+        g.close()

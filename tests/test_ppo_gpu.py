@@ -329,13 +329,15 @@ def test_peer_memory_adam_step_with_one_rank_equals_the_plain_step():
     comm, handle = C.c_void_p(), (C.c_ubyte * 64)()
     _lib.check(lib.hrp_comm_create(1, 0, n, 0, C.byref(comm), handle))
     _lib.check(lib.hrp_comm_connect(comm, bytes(handle)))
-    ptr = lib.hrp_comm_grad(comm)
+    views = []
+    for parity in (0, 1):   # the exchange alternates two gradient buffers with the parity of the step
+        ptr = lib.hrp_comm_grad_parity(comm, parity)
 
-    class _Raw:
-        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
-    keep = _Raw()
-    grad_c = torch.as_tensor(keep, device="cuda:0")
+        views.append((_Raw(),))
+        views[-1] = (views[-1][0], torch.as_tensor(views[-1][0], device="cuda:0"))
     st = torch.cuda.current_stream().cuda_stream
     pa = torch.randn(n, generator=g, device="cuda:0") * 0.1
     pb = pa.clone()
@@ -345,7 +347,8 @@ def test_peer_memory_adam_step_with_one_rank_equals_the_plain_step():
     try:
         for it in range(5):
             grad = torch.randn(n, generator=g, device="cuda:0") * (0.5 if it % 2 else 5e-4)  # clipped and unclipped steps
-            grad_c.copy_(grad)
+            assert lib.hrp_comm_parity(comm) == it % 2 and lib.hrp_comm_grad(comm) == views[it % 2][1].data_ptr()
+            views[it % 2][1].copy_(grad)
             _lib.check(lib.hrp_clip_adam_step_p2p(comm, pa.data_ptr(), ma.data_ptr(), va.data_ptr(), sa.data_ptr(), 3e-4, 0.9,
                                                   0.999, 1e-8, 0.5, scr_a.data_ptr(), st))
             _lib.check(lib.hrp_clip_adam_step(pb.data_ptr(), grad.data_ptr(), mb.data_ptr(), vb.data_ptr(), sb.data_ptr(), n,
@@ -355,7 +358,7 @@ def test_peer_memory_adam_step_with_one_rank_equals_the_plain_step():
             assert int(sa.item()) == int(sb.item()) == it + 1
     finally:
         torch.cuda.synchronize()
-        del grad_c
+        del views
         lib.hrp_comm_destroy(comm)
     # error paths
     assert lib.hrp_comm_create(9, 0, n, 0, C.byref(comm), handle) == -1      # more ranks than one box holds
@@ -492,3 +495,38 @@ def test_tma_gemm_path_matches_the_reference_too(monkeypatch):
     agent._minibatch_step(dev, torch.arange(B, device="cuda:0"), B, 1)
     want = r["grad"].numpy()
     np.testing.assert_allclose(agent.grad.cpu().numpy(), want, atol=2e-4 * np.abs(want).max() + 1e-6)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_update_keeps_ranks_bit_identical(tmp_path):
+    """Two ranks (one process per GPU, NCCL rendezvous, the peer-memory exchange of csrc/hrp_comm.cu inside CUDA
+    graphs): after two sharded PPO updates every rank holds bit-identical parameters, and they agree with the NCCL
+    all-reduce path to summation-order accuracy (tools/p2p_check.py)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(root, "tools", "p2p_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "identical on every rank: True" in res.stdout, res.stdout[-3000:]
+
+
+def test_workspace_lanes_share_the_parameters():
+    """act(lane=k) runs on its own native workspace (two streams may act at once) with the same parameters, seed and
+    global-row keyed noise: the same call on lane 0 and on lane 1 gives the same sample."""
+    torch.manual_seed(8)
+    a = _agent(60, 2, 64, 512)
+    torch.manual_seed(8)
+    b = _agent(60, 2, 64, 512)
+    x = torch.randn(512, 60, device="cuda:0") * 0.3
+    s1 = torch.cuda.Stream()
+    want = a.act(x)
+    with torch.cuda.stream(s1):
+        s1.wait_stream(torch.cuda.current_stream())
+        got = b.act(x, lane=1)
+    s1.synchronize()
+    for k in ("action", "pre_tanh", "log_prob", "value"):
+        assert torch.equal(got[k], want[k]), k
