@@ -60,6 +60,9 @@ def parse():
     p.add_argument("--no-ppo", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--e2e-groups", type=int, default=1, choices=[1, 2],
+                   help="env groups of the host-buffer loop: 2 = two half-size groups on two streams (copies of one under "
+                        "the kernels of the other); measured slower than 1 on B200 (see DESIGN.md 5)")
     return p.parse_args()
 
 
@@ -231,6 +234,7 @@ def cpu_policy_env_steps(args, seconds, n_envs, steps=None, warmup=1):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    oh.use_lean_build()   # the plain algorithm: the parity tests' decision bookkeeping is compiled out
     cfg, embed, flat, S, A, H, N = _cpu_setup(args)
     vec = oh.OracleVecEnv(cfg, n_envs, seed=42, nthreads=cores)
     obs = np.zeros((n_envs, N, 4), dtype=np.float32)
@@ -475,13 +479,14 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         Ke = min(K, 200)
-        G = 2 if E % 2 == 0 and E >= 512 else 1
+        G = args.e2e_groups if E % 2 == 0 else 1
         Eg = E // G
         groups = []
         for gi in range(G):
             genv = make_vec_env(Condition[cond_name], HIGHWAY_CONFIG, d_embed, over, num_envs=Eg, device=dev, seed=42,
                                 env_id_base=rank * E + gi * Eg, strict_d_embed=False)
             gb = {"env": genv, "stream": torch.cuda.Stream(device=dev), "event": torch.cuda.Event(),
+                  "side": torch.cuda.Stream(device=dev), "acted": torch.cuda.Event(), "copied": torch.cuda.Event(),
                   "obs_h": torch.zeros((Eg, N, Fout), dtype=torch.float32).pin_memory(),
                   "act_h": torch.zeros((Eg, 2), dtype=torch.float32).pin_memory(),
                   "rew_h": torch.zeros(Eg, dtype=torch.float32).pin_memory(),
@@ -495,14 +500,20 @@ def run_ours(args):
         def group_step(gi):
             gb = groups[gi]
             gb["event"].synchronize()                                   # the group's previous results are on the host
+            gb["copied"].synchronize()
             with torch.cuda.stream(gb["stream"]):
                 gb["obs_d"].copy_(gb["obs_h"].view(Eg, S), non_blocking=True)          # H2D observation
                 agent.actor_critic.row_base = rank * E + gi * Eg
                 agent.act(gb["obs_d"], out=gb["out"], lane=1 + gi)
-                gb["act_h"].copy_(gb["out"]["action"], non_blocking=True)              # D2H action
+                gb["acted"].record()
+                # the step kernel writes observation / reward / flags straight into the page-locked host buffers
                 gb["env"].step_host_async(gb["out"]["action"], gb["obs_h"].numpy(), gb["rew_h"].numpy(), gb["te_h"].numpy(),
-                                          gb["tr_h"].numpy())                          # kernel + D2H obs / reward / flags
+                                          gb["tr_h"].numpy())
                 gb["event"].record()
+            with torch.cuda.stream(gb["side"]):                                        # D2H action, under the env kernel
+                gb["side"].wait_event(gb["acted"])
+                gb["act_h"].copy_(gb["out"]["action"], non_blocking=True)
+                gb["copied"].record()
 
         for _ in range(5):
             for gi in range(G):
@@ -516,6 +527,7 @@ def run_ours(args):
                 group_step(gi)
         for gb in groups:
             gb["event"].synchronize()
+            gb["copied"].synchronize()
         w = time.perf_counter() - w0          # host clock: the region ends with every result on the host
         barrier()
         t = torch.tensor([w], dtype=torch.float64, device=dev)
@@ -524,9 +536,10 @@ def run_ours(args):
         e2e = {"value": world * E * Ke / float(t.cpu()), "unit": UNIT,
                "h2d_bytes_per_step": E * S * 4, "d2h_bytes_per_step": E * 2 * 4 + E * S * 4 + E * 4 + 2 * E,
                "steps": Ke, "groups": G,
-               "api": "two groups of E/2 envs on two streams (PPOAgent.act(lane=g) on a pinned-host observation + "
-                      "HighwayVecEnv.step_host_async = hrp_env_step_host_async): the device action feeds the step, the host "
-                      "receives action, observation, reward and flags; one event wait per group-step"}
+               "api": "PPOAgent.act on a pinned-host observation (H2D copy) + HighwayVecEnv.step_host_async "
+                      "(hrp_env_step_host_async): the device action feeds the step, the kernel writes observation, reward "
+                      "and flags straight into the page-locked host buffers (zero-copy), the action is copied to the host "
+                      "under the env kernel; one event wait per step" + (" and group (two half-size groups on two streams)" if G == 2 else "")}
         agent.actor_critic.row_base = rank * E
         for gb in groups:
             gb["env"].close()
@@ -627,11 +640,14 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
-        # graphs that captured NCCL work must go before the communicator does; leave without the communicator
-        # teardown (it was seen to hang after captured collectives) once every rank is done
+        # graphs and peer mappings go before the communicator does.  With the peer-memory exchange no NCCL work is
+        # captured in the graphs and destroy_process_group() returns (tools/p2p_check.py prints it); the timer only
+        # guards the NCCL-in-graph fallback (HRP_P2P=0), where the teardown was seen to hang.
         agent.close()
         barrier()
         sys.stdout.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        dist.destroy_process_group()
         os._exit(0)
 
 

@@ -342,6 +342,25 @@ static int step_host_impl(hrp_env *h, const float *actions, float *obs_host, flo
                                     cudaMemcpyHostToDevice, s));
         d_act = h->d_actions;
     }
+    // Page-locked result buffers are mapped into the device's address space (unified addressing): the step kernel
+    // writes observation, reward and flags STRAIGHT into them -- coalesced posted writes over PCIe that drain while the
+    // kernel is still simulating other envs -- instead of into device buffers followed by device-to-host copies.
+    // HRP_ZERO_COPY=0 keeps the copies.
+    static const bool zero_copy = !(getenv("HRP_ZERO_COPY") && getenv("HRP_ZERO_COPY")[0] == '0');
+    if (zero_copy && pin_o && pin_r) {
+        float *o_dev = nullptr, *r_dev = nullptr;
+        uint8_t *te_dev = nullptr, *tr_dev = nullptr;
+        if (cudaHostGetDevicePointer((void **)&o_dev, obs_host, 0) == cudaSuccess &&
+            cudaHostGetDevicePointer((void **)&r_dev, reward_host, 0) == cudaSuccess &&
+            cudaHostGetDevicePointer((void **)&te_dev, terminated_host, 0) == cudaSuccess &&
+            cudaHostGetDevicePointer((void **)&tr_dev, truncated_host, 0) == cudaSuccess) {
+            if (int rc = hrp_launch_step(h->P, d_act, o_dev, r_dev, te_dev, tr_dev, nullptr, nullptr, s)) return rc;
+            if (!sync) return 0;
+            HRP_CUDA_OK(cudaStreamSynchronize(s));
+            return 0;
+        }
+        cudaGetLastError();   // not mapped: fall through to the copies
+    }
     if (int rc = hrp_launch_step(h->P, d_act, h->d_obs, h->d_reward, h->d_term, h->d_trunc, nullptr, nullptr, s))
         return rc;
     HRP_CUDA_OK(cudaMemcpyAsync(pin_o ? obs_host : h->h_obs, h->d_obs, no * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -48,7 +48,11 @@ template <> struct Ops<float> {
             *s = x * ps;
             *c = pc;
         } else {
-            sincosf(x, s, c);
+            // rare (a spinning crashed vehicle); one lane pulls its whole warp through this branch, so it is the SFU pair
+            // on the argument reduced to [-pi, pi] (|error| < 1e-6, inside the heading tolerance of the parity tests),
+            // not the library's full-range slow path
+            const float r = x - 6.283185307179586f * rintf(x * 0.15915494309189535f);
+            __sincosf(r, s, c);
         }
     }
     // ContinuousAction.get_action: float32 lmap of the clipped np.float32 action (exact float32 operation order)
@@ -738,12 +742,16 @@ __device__ void simulate_frame(const EnvDev &P, WarpS<R> &S, Veh<R> (&u)[2], int
         const R a0 = idm_free(w.v, clipf(w.ts, R(0), R(30)), w.delta);
         Rec<R> me;
         me.xr = (R)(w.x - xref); me.v = w.v; me.ch = w.ch; me.sh = w.sh;
-        const int sf = slot_front(S.band[w.lane], p), st = slot_front(S.band[w.tlane], p);
+        const int sf = slot_front(S.band[w.lane], p);
         const R i1 = idm_interaction_rec(me, S.rec[S.order[max(sf, 0)]]);
-        const R i2 = idm_interaction_rec(me, S.rec[S.order[max(st, 0)]]);
         R acc = a0 - (sf >= 0 ? i1 : R(0));
-        const R acc_t = a0 - (st >= 0 ? i2 : R(0));
-        acc = w.lane != w.tlane ? fmin(acc, acc_t) : acc;
+        // the front vehicle of the target lane matters only between lanes: the whole warp skips it otherwise
+        if (__any_sync(HRP_FULL, valid && w.lane != w.tlane)) {
+            const int st = slot_front(S.band[w.tlane], p);
+            const R i2 = idm_interaction_rec(me, S.rec[S.order[max(st, 0)]]);
+            const R acc_t = a0 - (st >= 0 ? i2 : R(0));
+            acc = w.lane != w.tlane ? fmin(acc, acc_t) : acc;
+        }
         const R acc_idm = clipf(acc, R(-6), R(6));
         const R acc_mdp = (R(1) / R(0.6)) * (w.ts - w.v);  // MDPVehicle: speed_control
         w.tb = act ? tb_new : w.tb;

@@ -21,6 +21,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "highway_oracle.c")
 _LIB = os.path.join(_HERE, "libhighway_oracle.so")
+_LIB_LEAN = os.path.join(_HERE, "libhighway_oracle_lean.so")   # CPU-baseline build: no decision bookkeeping
 
 HW_MAX_VEHICLES = 128
 HW_MAX_FEATURES = 8
@@ -61,7 +62,19 @@ def build(force: bool = False) -> str:
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(
             os.path.getmtime(_SRC), os.path.getmtime(os.path.join(_HERE, "highway_oracle.h"))):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-o", _LIB, _SRC, "-lm"])
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-DHW_NO_DECISION_AIDS", "-o", _LIB_LEAN, _SRC, "-lm"])
     return _LIB
+
+
+def use_lean_build() -> None:
+    """Switch this process to the CPU-baseline build of the oracle (bench.py's CPU arms): the same algorithm compiled
+    without the parity tests' decision bookkeeping.  Must be called before the first OracleEnv is created."""
+    global _lib
+    build()
+    assert _lib is None or getattr(_lib, "_lean", False), "the oracle library is already loaded"
+    if _lib is None:
+        _lib = _bind(C.CDLL(_LIB_LEAN))
+        _lib._lean = True
 
 
 _lib = None
@@ -70,7 +83,12 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        L = C.CDLL(build())
+        _lib = _bind(C.CDLL(build()))
+    return _lib
+
+
+def _bind(L):
+    if True:
         L.hw_create.restype = C.c_void_p
         L.hw_create.argtypes = [C.POINTER(HwCfg)]
         L.hw_destroy.argtypes = [C.c_void_p]
@@ -94,8 +112,7 @@ def lib():
         L.hw_force_decisions.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.hw_slow_vehicles.argtypes = [C.c_void_p, C.c_void_p]
         L.hw_set_trace.argtypes = [C.c_void_p, C.c_void_p]
-        _lib = L
-    return _lib
+    return L
 
 
 # highway-env defaults the reference config does not override

@@ -97,6 +97,10 @@ static inline uint64_t dkey(const hw_env *e, int kind, int a, int b, int c)
     return ((uint64_t)(kind & 0xff) << 32) | ((uint64_t)(e->frame & 0xff) << 24) | ((uint64_t)(a & 0xff) << 16) |
            ((uint64_t)(b & 0xff) << 8) | (uint64_t)(c & 0xff);
 }
+#ifdef HW_NO_DECISION_AIDS
+/* the CPU-baseline build (bench.py): the plain algorithm, without the test aids' bookkeeping */
+#define dec(e, kind, a, b, c, margin, res) (res)
+#else
 static int dec(hw_env *e, int kind, int a, int b, int c, double margin, int res)
 {
     margin = fabs(margin);
@@ -113,14 +117,19 @@ static int dec(hw_env *e, int kind, int a, int b, int c, double margin, int res)
     }
     return res;
 }
+#endif
 /* strict order of two vehicles along the road, one key per unordered pair */
 static int x_before(hw_env *e, int a, int b)
 {
+#ifdef HW_NO_DECISION_AIDS
+    return e->v[a].x < e->v[b].x;
+#else
     int lo = a < b ? a : b, hi = a < b ? b : a;
     int lt = e->v[lo].x < e->v[hi].x, gt = e->v[lo].x > e->v[hi].x; /* equal: neither is strictly before */
     int c = dec(e, HW_D_ORDER, lo, hi, 0, e->v[lo].x - e->v[hi].x, lt);
     if (c != lt) gt = !c; /* forced: strictly the other way */
     return a < b ? c : gt;
+#endif
 }
 
 /* ---- utils.py ------------------------------------------------------------ */

@@ -77,10 +77,10 @@ if rank == 0:
           f"{t_ref / (steps - 4) * 1e6:.0f} us (nccl)")
 ok = ranks_equal and moved > 1e-4 and grad_err < 1e-5 and (same if world == 2 else True)
 
-# ---- PPOAgent.update through CUDA graphs: 2 minibatches x 3 epochs (an odd number of steps per update, so the same
+# ---- PPOAgent.update through CUDA graphs: 3 minibatches x 3 epochs (an odd number of steps per epoch, so the same
 # minibatch is replayed with both parities of the double-buffered exchange), two updates
 def rollout(agent, seed):
-    T, E = 4, 2048
+    T, E = 6, 2048
     gg = torch.Generator(device=dev).manual_seed(seed)
     r = agent.memory.begin_rollout(T, E, S, A)
     r["states"].copy_(torch.randn(T + 1, E, S, generator=gg, device=dev) * 0.5)
@@ -105,7 +105,7 @@ gathered = [torch.empty_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
 upd_equal = all(torch.equal(gathered[0], x) for x in gathered)
 if rank == 0:
-    print(f"world {world}: two graph-replayed updates (12 optimizer steps, both parities): identical on every rank: {upd_equal}; "
+    print(f"world {world}: two graph-replayed updates (18 optimizer steps, both parities): identical on every rank: {upd_equal}; "
           f"exchange: {'peer-memory kernel' if upd._comm is not None else 'nccl'}; graphs captured: {len(upd._graph_state['graphs'])}")
 ok = ok and upd_equal
 upd.close()
