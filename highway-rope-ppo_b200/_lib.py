@@ -77,6 +77,8 @@ SIGNATURES: Dict[str, Any] = {
     "hrp_env_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "hrp_env_reset_host": (C.c_int, [_vp, _u64, _vp]),
     "hrp_env_step_host_on": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hrp_env_set_seeds": (C.c_int, [_vp, _vp]),
+    "hrp_env_set_step_mask": (C.c_int, [_vp, _vp]),
     "hrp_env_set_trace": (C.c_int, [_vp, _vp]),
     "hrp_env_trace_shape": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "hrp_env_step_host_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -413,6 +413,20 @@ int hrp_env_reset_host(hrp_env *h, uint64_t seed, float *obs_host)
     return 0;
 }
 
+int hrp_env_set_seeds(hrp_env *h, const uint64_t *seeds_dev)
+{
+    if (!h) { hrp_set_error("hrp_env_set_seeds: null handle"); return -1; }
+    h->P.seed_env = (const ull *)seeds_dev;
+    return 0;
+}
+
+int hrp_env_set_step_mask(hrp_env *h, const uint8_t *mask_dev)
+{
+    if (!h) { hrp_set_error("hrp_env_set_step_mask: null handle"); return -1; }
+    h->P.step_mask = mask_dev;
+    return 0;
+}
+
 int hrp_env_set_trace(hrp_env *h, double *trace_dev)
 {
     if (!h) { hrp_set_error("hrp_env_set_trace: null handle"); return -1; }

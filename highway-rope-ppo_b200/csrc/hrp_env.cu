@@ -396,7 +396,8 @@ template <typename R>
 __device__ void spawn_env(const EnvDev &P, WarpS<R> &S, Veh<R> (&u)[2], int e, int lane, uint32_t episode,
                           double &xref)
 {
-    ull gid = P.env_id_base + (ull)e;
+    const ull gid = P.seed_env ? 0ull : P.env_id_base + (ull)e;
+    const ull seed = P.seed_env ? P.seed_env[e] : P.seed;
     double val[2] = {0.0, 0.0};
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -404,8 +405,8 @@ __device__ void spawn_env(const EnvDev &P, WarpS<R> &S, Veh<R> (&u)[2], int e, i
         Veh<R> &w = u[q];
         if (k < P.V) {
             uint32_t r[4];
-            hrp_philox((uint32_t)k, episode, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)P.seed,
-                       (uint32_t)(P.seed >> 32), r);
+            hrp_philox((uint32_t)k, episode, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed,
+                       (uint32_t)(seed >> 32), r);
             int ln = (int)((double)u01f(r[0]) * (double)P.lanes);
             double speed, spacing;
             if (k == 0) {
@@ -567,11 +568,12 @@ __device__ void observe_env(const EnvDev &P, WarpS<R> &S, int e, int lane, float
         if (perm_in) {
             for (int i = lane; i < N - 1; i += 32) S.perm[i] = (unsigned char)perm_in[(size_t)e * (N - 1) + i];
         } else {
-            ull gid = P.env_id_base + (ull)e;
+            const ull gid = P.seed_env ? 0ull : P.env_id_base + (ull)e;
+            const ull seed = P.seed_env ? P.seed_env[e] : P.seed;
             for (int blk = lane; blk * 4 < N - 1; blk += 32) {
                 uint32_t r[4];
-                hrp_philox((uint32_t)blk, draw, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)P.seed,
-                           (uint32_t)(P.seed >> 32) ^ 0xA5A5A5A5u, r);
+                hrp_philox((uint32_t)blk, draw, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed,
+                           (uint32_t)(seed >> 32) ^ 0xA5A5A5A5u, r);
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
                     if (blk * 4 + t < N - 1) S.skey[blk * 4 + t] = r[t];
@@ -875,6 +877,7 @@ __device__ __forceinline__ void step_body(const EnvDev &P, const float *__restri
     hrp_pdl_release();
     hrp_pdl_wait();
     if (e >= P.E) return;
+    if (P.step_mask && !P.step_mask[e]) return;   // multiplexed experiments: this env is not taking a step now
     WarpS<R> &S = smem[warp];
     Veh<R> u[2];
     double xref;

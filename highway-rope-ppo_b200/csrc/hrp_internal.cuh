@@ -37,6 +37,10 @@ struct EnvDev {
     double ego_spacing, inv_density, gap_factor;
     int initial_lane;
     ull env_id_base, seed;
+    // multiplexed independent experiments (hrp_env_set_seeds): when non-null, env e draws from (seed_env[e], global env
+    // id 0), i.e. it is bit-for-bit the single-env handle an experiment with that seed would own
+    const ull *seed_env;
+    const uint8_t *step_mask;   // multiplexed experiments: when non-null, hrp_env_step leaves env e untouched unless step_mask[e]
     // SoA simulator state in HBM: [E][HRP_VS] per vehicle field, [E] per env field
     double *x, *timer, *time;
     void *y, *heading, *speed, *tspeed, *delta, *impx, *impy;   // float arrays, double arrays when real64

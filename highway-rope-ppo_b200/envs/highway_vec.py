@@ -278,6 +278,32 @@ class HighwayVecEnv:
                    "hrp_env_reset_host")
         self.launches += 1
 
+    # ------------------------------------------------------------------ multiplexed experiments
+    def set_env_seeds(self, seeds: Optional[torch.Tensor]) -> None:
+        """Per-env seeds (int64 / uint64 CUDA tensor [E], kept alive by this object): env e then behaves exactly like
+        the single-env handle of an experiment that called ``reset(seed=seeds[e])``.  ``None`` switches back to
+        (handle seed, global env id)."""
+        if seeds is None:
+            _lib.check(self._lib.hrp_env_set_seeds(self._h, None), "hrp_env_set_seeds")
+            self._seeds = None
+            return
+        if not seeds.is_cuda or seeds.numel() != self.num_envs or seeds.dtype not in (torch.int64, torch.uint64):
+            raise ValueError(f"seeds must be a CUDA int64 tensor of {self.num_envs} entries")
+        self._seeds = seeds.contiguous()
+        _lib.check(self._lib.hrp_env_set_seeds(self._h, self._seeds.data_ptr()), "hrp_env_set_seeds")
+
+    def set_step_mask(self, mask: Optional[torch.Tensor]) -> None:
+        """uint8 CUDA tensor [E] (kept alive by this object; rewrite its contents between steps): ``step`` leaves env e
+        untouched unless ``mask[e]``.  ``None``: every env steps."""
+        if mask is None:
+            _lib.check(self._lib.hrp_env_set_step_mask(self._h, None), "hrp_env_set_step_mask")
+            self._step_mask = None
+            return
+        if not mask.is_cuda or mask.numel() != self.num_envs or mask.dtype != torch.uint8:
+            raise ValueError(f"mask must be a CUDA uint8 tensor of {self.num_envs} entries")
+        self._step_mask = mask.contiguous()
+        _lib.check(self._lib.hrp_env_set_step_mask(self._h, self._step_mask.data_ptr()), "hrp_env_set_step_mask")
+
     # ------------------------------------------------------------------ validation aids
     def enable_trace(self, on: bool = True) -> Optional[torch.Tensor]:
         """Record every vehicle's state at the end of every simulation frame of the following steps (parity tests):

@@ -179,6 +179,8 @@ class ActorCritic:
             self._hold_next = False
 
     def _as_states(self, x) -> torch.Tensor:
+        if torch.is_tensor(x) and x.dtype == torch.float32 and x.device == self.device and x.is_contiguous():
+            return x
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
         x = x.to(device=self.device, dtype=torch.float32)
@@ -207,8 +209,10 @@ class ActorCritic:
 
     # -- batched get_action: everything stays on the device -------------------------------------
     def act(self, states: torch.Tensor, noise: Optional[torch.Tensor] = None, deterministic: bool = False,
-            out: Optional[Dict[str, torch.Tensor]] = None, lane: int = 0) -> Dict[str, torch.Tensor]:
-        """``get_action`` for [B, S] states -> dict(action, pre_tanh [B, A]; log_prob, value [B]).
+            out: Optional[Dict[str, torch.Tensor]] = None, lane: int = 0,
+            stream: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """``get_action`` for [B, S] states -> dict(action, pre_tanh [B, A]; log_prob, value [B]).  ``stream``: raw
+        ``cudaStream_t`` to enqueue on instead of torch's current stream (the multiplexer's stream ring).
 
         ``lane`` > 0 selects a separate native workspace (same parameters) so that calls on different CUDA streams
         may overlap: the two env groups of the pipelined host-buffer loop (bench.py e2e) act concurrently."""
@@ -224,6 +228,8 @@ class ActorCritic:
                    "log_prob": torch.empty(B, dtype=torch.float32, device=self.device),
                    "value": torch.empty(B, dtype=torch.float32, device=self.device)}
         self._sync_weight_copies()
+        if stream is None:
+            stream = self._stream()
         if not deterministic and noise is None:
             # standard normals drawn in the kernel (Philox keyed by a seed taken from torch's generator at
             # construction, so set_random_seeds() still fixes the rollout; one draw counter per call)
@@ -231,12 +237,12 @@ class ActorCritic:
             _lib.check(self._lib.hrp_ppo_act_sample(self._h, self.flat.data_ptr(), states.data_ptr(), self._noise_seed,
                                                     self._draw, int(self.row_base), B, out["action"].data_ptr(),
                                                     out["pre_tanh"].data_ptr(), out["log_prob"].data_ptr(),
-                                                    out["value"].data_ptr(), self._stream()), "hrp_ppo_act_sample")
+                                                    out["value"].data_ptr(), stream), "hrp_ppo_act_sample")
             return out
         _lib.check(self._lib.hrp_ppo_act(self._h, self.flat.data_ptr(), states.data_ptr(),
                                          None if deterministic else noise.data_ptr(), B,
                                          out["action"].data_ptr(), out["pre_tanh"].data_ptr(),
-                                         out["log_prob"].data_ptr(), out["value"].data_ptr(), self._stream()),
+                                         out["log_prob"].data_ptr(), out["value"].data_ptr(), stream),
                    "hrp_ppo_act")
         return out
 
@@ -594,12 +600,36 @@ class PPOAgent:
             self._graph_state = None
 
     # -- the epochs x minibatches loop as CUDA graphs --------------------------------------------------
+    def _capture(self, fn, world: int) -> "torch.cuda.CUDAGraph":
+        g = torch.cuda.CUDAGraph()
+        if world > 1:   # collectives inside: torch's context (full synchronisation, allocator quiesced) as before
+            with torch.cuda.graph(g):
+                fn()
+            return g
+        # single GPU: nothing inside allocates through torch, so skip the context's gc + empty_cache + device
+        # synchronisation (10 ms per capture; a sweep run at batch 32 captures often)
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_capture_stream", None) is None:
+            self._capture_stream = torch.cuda.Stream(self.device)
+        cap = self._capture_stream
+        cap.wait_stream(cur)
+        with torch.cuda.stream(cap):
+            g.capture_begin()
+            try:
+                fn()
+            finally:
+                g.capture_end()
+        cur.wait_stream(cap)
+        return g
+
     def _graphed_epochs(self, flat: Dict[str, torch.Tensor], perm_dev: torch.Tensor, n: int, bs: int,
                         world: int = 1) -> None:
-        """One CUDA graph per minibatch (the ~40 launches of loss/backward/clip/Adam), replayed for every epoch
-        and re-used by later updates of the same size.  The rollout is first copied into persistent buffers so
-        that the captured pointers stay valid.  The first epoch of a new configuration runs eagerly (it also
-        warms every kernel variant before anything is captured)."""
+        """The ~40 launches of one optimizer step (loss / backward / clip / Adam) as ONE CUDA graph per distinct
+        minibatch size (the full one and a ragged last one), replayed for every minibatch of every epoch and re-used by
+        later updates of the same shape: the graph reads its sample indices from a fixed buffer that a small
+        device-to-device copy of the permutation slice refills before each replay.  The rollout is first copied into
+        persistent buffers so that the captured pointers stay valid.  The first epoch of a new configuration runs
+        eagerly (it also warms every kernel variant before anything is captured)."""
         ac = self.actor_critic
         # the workspace generation, not its address: a re-created workspace may reuse the freed one's address
         key = (n, bs, world, ac.workspace_generation, float(self.eps_clip), float(self.value_coef), float(self.entropy_coef),
@@ -609,38 +639,44 @@ class PPOAgent:
             d = self.device
             st = {"key": key, "graphs": {}, "warm": False,
                   "buf": {k: torch.empty_like(v) for k, v in flat.items()},
-                  "perm": torch.empty(n, dtype=torch.int64, device=d)}
+                  "perm": torch.empty(n, dtype=torch.int64, device=d),
+                  "idx": torch.empty(min(bs, n), dtype=torch.int64, device=d)}
             self._graph_state = st
         for k, v in flat.items():
             st["buf"][k].copy_(v)
         st["perm"].copy_(perm_dev)
         starts = list(range(0, n, bs))
         for epoch in range(self.epochs):
-            if not st["warm"]:
-                for start in starts:
-                    B = min(bs, n - start)
-                    self._minibatch_step(st["buf"], st["perm"][start:start + B], B, world)
-                st["warm"] = True
-                continue
-            for i, start in enumerate(starts):
-                # the peer-memory exchange alternates its buffers with the step parity: one graph per (minibatch, parity)
+            for start in starts:
+                B = min(bs, n - start)
+                idx = st["idx"][:B]
+                idx.copy_(st["perm"][start:start + B])
+                if not st["warm"]:
+                    self._minibatch_step(st["buf"], idx, B, world)
+                    continue
+                # the peer-memory exchange alternates its buffers with the step parity: one graph per (size, parity)
                 parity = self._lib.hrp_comm_parity(self._comm) if (world > 1 and self._comm is not None) else 0
-                g = st["graphs"].get((i, parity))
+                g = st["graphs"].get((B, parity))
                 if g is None:
-                    B = min(bs, n - start)
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._minibatch_step(st["buf"], st["perm"][start:start + B], B, world)   # (advances the parity)
-                    st["graphs"][(i, parity)] = g
+                    # (capturing advances the parity)
+                    g = self._capture(lambda: self._minibatch_step(st["buf"], idx, B, world), world)
+                    st["graphs"][(B, parity)] = g
                 elif world > 1 and self._comm is not None:
                     _lib.check(self._lib.hrp_comm_note_replay(self._comm), "hrp_comm_note_replay")
                     self.grad = self._grad_parity[parity]
                 g.replay()
                 ac.native_updates += 1
                 self.launches += 2
+            st["warm"] = True
 
     # -- PPOAgent.update (agent.py:196-308) --------------------------------------------------------
     def update(self, last_value=0.0) -> Dict[str, float]:
+        return self.update_end(self.update_begin(last_value))
+
+    def update_begin(self, last_value=0.0):
+        """Enqueue the whole update on the current stream and return a handle for ``update_end``: no host
+        synchronisation (single-GPU), so that the updates of several agents on several streams overlap
+        (experiments/multiplex.py)."""
         mem, ac = self.memory, self.actor_critic
         r = mem.as_rollout()
         T, E = r["reward"].shape
@@ -694,7 +730,18 @@ class PPOAgent:
             var_y = torch.var(y_true) if n > 1 else torch.zeros((), device=self.device)
             var_r = torch.var(y_true - y_pred) if n > 1 else torch.zeros((), device=self.device)
         tail = torch.stack([var_y.float(), var_r.float()])
-        host = torch.cat([self._metrics, tail]).cpu().numpy()  # the update's single D2H
+        if getattr(self, "_metrics_host", None) is None:
+            self._metrics_host = torch.zeros(10, dtype=torch.float32).pin_memory()
+        self._metrics_host.copy_(torch.cat([self._metrics, tail]), non_blocking=True)   # the update's single D2H
+        done = torch.cuda.Event()
+        done.record()
+        mem.clear()
+        return done
+
+    def update_end(self, done) -> Dict[str, float]:
+        """Wait for the update enqueued by ``update_begin`` and return its metrics."""
+        done.synchronize()
+        host = self._metrics_host.numpy().copy()
         count = max(float(host[6]), 1.0)
         explained = float(1.0 - host[9] / host[8]) if host[8] > 0 else 0.0
         out = {"loss": float(host[0] / count), "policy_loss": float(host[1] / count),
@@ -705,7 +752,6 @@ class PPOAgent:
             "update_complete loss=%.4f policy_loss=%.4f value_loss=%.4f entropy=%.4f clip_frac=%.3f kl=%.5f "
             "explained_var=%.3f", out["loss"], out["policy_loss"], out["value_loss"], out["entropy"],
             out["clip_fraction"], out["approx_kl"], out["explained_variance"])
-        mem.clear()
         return out
 
     # -- checkpoints (agent.py:310-327): same file format and key names ----------------------------

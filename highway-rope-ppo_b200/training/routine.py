@@ -29,16 +29,21 @@ def ensure_artifacts_dir(custom_path: Optional[str] = None) -> str:
     return path
 
 
-def evaluate(env, agent, num_episodes: int = 10, render: bool = False, exp_seed: int = 0) -> float:
-    """Mean undiscounted return of the deterministic policy (tanh of the mean action)."""
+# The reference loop is written ONCE, as a coroutine that yields every interaction with the env and the agent as a
+# request -- ("reset", seed) -> observation; ("act", flat_state, deterministic) -> (action, pre_tanh, log_prob, value);
+# ("step", action) -> (next_obs, reward, terminated, truncated); ("value", flat_state) -> V(s); ("update", last_value)
+# -> metrics; ("save", path) -> None -- and two drivers answer the requests: `drive` with one env and one agent (the
+# reference's process-per-experiment shape), and experiments/multiplex.py with R experiments at once, batching the
+# requests of a tick into one env launch and one host synchronisation.  Same control flow, same arithmetic.
+def _evaluate_co(num_episodes: int, exp_seed: int):
     returns = []
     for ep in range(num_episodes):
-        state, _ = env.reset(seed=exp_seed + 1000 + ep)
+        state = yield ("reset", exp_seed + 1000 + ep)
         flat = state.reshape(-1)
         done, total = False, 0.0
         while not done:
-            action, _, _, _ = agent.select_action(flat, deterministic=True)
-            nxt, reward, terminated, truncated, _ = env.step(action)
+            action, _, _, _ = yield ("act", flat, True)
+            nxt, reward, terminated, truncated = yield ("step", action)
             done = terminated or truncated
             flat = nxt.reshape(-1)
             total += reward
@@ -46,11 +51,54 @@ def evaluate(env, agent, num_episodes: int = 10, render: bool = False, exp_seed:
     return float(np.mean(returns))
 
 
+def drive(co, env, agent):
+    """Answer a coroutine's requests with one env and one agent; returns the coroutine's return value."""
+    try:
+        req = next(co)
+        while True:
+            kind = req[0]
+            if kind == "act":
+                resp = agent.select_action(req[1], deterministic=req[2])
+            elif kind == "step":
+                nxt, reward, terminated, truncated, _ = env.step(req[1])
+                resp = (nxt, reward, terminated, truncated)
+            elif kind == "reset":
+                resp, _ = env.reset(seed=req[1])
+            elif kind == "value":
+                _, _, v = agent.actor_critic.forward(req[1])
+                resp = float(v.cpu().item())
+            elif kind == "update":
+                resp = agent.update(last_value=req[1])
+            elif kind == "save":
+                agent.save(req[1])
+                resp = None
+            else:
+                raise RuntimeError(f"unknown request {kind!r}")
+            req = co.send(resp)
+    except StopIteration as done:
+        return done.value
+
+
+def evaluate(env, agent, num_episodes: int = 10, render: bool = False, exp_seed: int = 0) -> float:
+    """Mean undiscounted return of the deterministic policy (tanh of the mean action)."""
+    return drive(_evaluate_co(num_episodes, exp_seed), env, agent)
+
+
 def train_with_experiment_name(env, agent, max_episodes: int = 500, target_reward: float = 0.0,
                                log_interval: int = 20, eval_interval: int = 50, steps_per_update: int = 2048,
                                experiment_name: str = "", exp_seed: int = 0, logger=None,
                                artifacts_dir: Optional[str] = None):
     """The reference's single-env training loop; returns (rewards, avg_rewards, metrics_history)."""
+    co = training_coroutine(agent.memory, max_episodes, target_reward, log_interval, eval_interval, steps_per_update,
+                            experiment_name, exp_seed, logger, artifacts_dir)
+    return drive(co, env, agent)
+
+
+def training_coroutine(memory, max_episodes: int = 500, target_reward: float = 0.0, log_interval: int = 20,
+                       eval_interval: int = 50, steps_per_update: int = 2048, experiment_name: str = "",
+                       exp_seed: int = 0, logger=None, artifacts_dir: Optional[str] = None):
+    """``train_with_experiment_name`` (reference ``training/routine.py:61-297``) as a request coroutine.  ``memory`` is
+    the agent's ``PPOMemory`` (host-side lists; stored into directly)."""
     logger = logger or logging.getLogger(f"experiment_{experiment_name}")
     tag = f"[{experiment_name}]" if experiment_name else ""
     logger.info(f"{tag} Starting training for experiment: {experiment_name}")
@@ -67,7 +115,7 @@ def train_with_experiment_name(env, agent, max_episodes: int = 500, target_rewar
     ckpt_dir = os.path.join(out_dir, "checkpoints")
     os.makedirs(ckpt_dir, exist_ok=True)
 
-    first = evaluate(env, agent, num_episodes=5, exp_seed=exp_seed)
+    first = yield from _evaluate_co(5, exp_seed)
     rewards.append(first)
     avg_rewards.append(first)
     history["eval_rewards"].append(first)
@@ -82,15 +130,15 @@ def train_with_experiment_name(env, agent, max_episodes: int = 500, target_rewar
         update_t0 = time.time()
         while collected < steps_per_update and episode_num < max_episodes:
             episode_num += 1
-            state, _ = env.reset(seed=exp_seed + episode_num)
+            state = yield ("reset", exp_seed + episode_num)
             flat = state.reshape(-1)
             ep_reward, done = 0.0, False
             while not done and collected < steps_per_update:
-                action, pre_tanh, log_prob, value = agent.select_action(flat)
-                nxt, reward, terminated, truncated, _ = env.step(action)
+                action, pre_tanh, log_prob, value = yield ("act", flat, False)
+                nxt, reward, terminated, truncated = yield ("step", action)
                 done = terminated or truncated  # truncation masks the bootstrap as well
                 flat_next = nxt.reshape(-1)
-                agent.memory.store(flat, action, pre_tanh, reward, flat_next, log_prob, done, value)
+                memory.store(flat, action, pre_tanh, reward, flat_next, log_prob, done, value)
                 flat = flat_next
                 ep_reward += reward
                 collected += 1
@@ -103,7 +151,7 @@ def train_with_experiment_name(env, agent, max_episodes: int = 500, target_rewar
                 logger.info("%s episode=%d reward=%.2f avg_reward=%.2f steps=%d time=%.2fs", tag, episode_num,
                             ep_reward, np.mean(episode_rewards[-log_interval:]), total_steps, time.time() - t0)
             if episode_num % eval_interval == 0:
-                eval_reward = evaluate(env, agent, num_episodes=5, exp_seed=exp_seed)
+                eval_reward = yield from _evaluate_co(5, exp_seed)
                 rewards.append(eval_reward)
                 eval_episodes.append(episode_num)
                 elapsed = time.time() - t0
@@ -116,17 +164,16 @@ def train_with_experiment_name(env, agent, max_episodes: int = 500, target_rewar
                 logger.info("%s eval episode=%d reward=%.2f avg_reward=%.2f time=%.2fs", tag, episode_num,
                             eval_reward, avg_r, elapsed)
                 if avg_r >= target_reward and not solved and len(rewards) >= 10:
-                    agent.save(os.path.join(ckpt_dir, f"ppo_highway_solved_{experiment_name}.pth"))
+                    yield ("save", os.path.join(ckpt_dir, f"ppo_highway_solved_{experiment_name}.pth"))
                     solved = True
                 if avg_r > best_avg:
                     best_avg = avg_r
-                    agent.save(os.path.join(ckpt_dir, f"ppo_highway_best_{experiment_name}.pth"))
+                    yield ("save", os.path.join(ckpt_dir, f"ppo_highway_best_{experiment_name}.pth"))
                     logger.info(f"{tag} New best model saved, avg reward={best_avg:.2f}")
         final_value = 0.0
         if not done:  # episode cut by the step budget: bootstrap from V(s_T)
-            _, _, v = agent.actor_critic.forward(flat)
-            final_value = float(v.cpu().item())
-        update_metrics = agent.update(last_value=final_value)
+            final_value = yield ("value", flat)
+        update_metrics = yield ("update", final_value)
         history["policy_updates"].append({"episode": episode_num, "steps": collected,
                                           "time": time.time() - update_t0, **update_metrics})
 

@@ -144,6 +144,18 @@ int hrp_env_reset_host(hrp_env *env, uint64_t seed, float *obs_host);
 int hrp_env_step_host_on(hrp_env *env, const float *actions, float *obs_host, float *reward_host,
                          uint8_t *terminated_host, uint8_t *truncated_host, void *stream);
 
+/* Multiplexed independent experiments (the replacement of utils/device_pool.py:45-72 + main.py:234-242: many single-env
+ * runs of the sweep share ONE handle instead of time-sharing the GPU as processes).  While seeds_dev[E] (device, owned by
+ * the caller, read at every reset / shuffle draw) is non-NULL, env e draws its spawn and shuffle randoms from
+ * (seeds_dev[e], global env id 0) instead of (seed, env_id_base + e): it is bit for bit the single-env handle that an
+ * experiment calling env.reset(seed=seeds[e]) would own.  The training loop rewrites seeds_dev[e] = exp_seed + episode
+ * before it resets env e through hrp_env_reset's mask (training/routine.py:132-133).  NULL switches it off. */
+int hrp_env_set_seeds(hrp_env *env, const uint64_t *seeds_dev);
+/* while mask_dev[E] (device, owned by the caller, read by every hrp_env_step) is non-NULL, a step leaves env e
+ * untouched -- state, counters, outputs -- unless mask_dev[e] != 0: multiplexed experiments are not in lock step (one
+ * is evaluating, one is in its PPO update, one has finished).  NULL: every env steps. */
+int hrp_env_set_step_mask(hrp_env *env, const uint8_t *mask_dev);
+
 /* validation aid: while trace_dev is non-NULL every hrp_env_step also writes the state of every vehicle at the end
  * of every simulation frame -- trace_dev[E][frames][slots][fields] doubles (x, y, speed, heading, impact_x, impact_y,
  * flags = lane | target_lane<<8 | crashed<<16 | has_impact<<17); hrp_env_trace_shape gives the three inner extents.

@@ -176,3 +176,77 @@ def test_meta_action_env_through_make_env(highway_config):
             break
     assert obs.shape == (15, 4) and total > 0
     env.close()
+
+
+def _sweep_like_experiments(n, max_episodes, steps_per_update):
+    """n single-env experiments shaped like the reference sweep (main.py:42-88): every condition, hidden 128 / 256,
+    batch 32 / 64, several seeds (RankPE twice with different seeds = different tables = separate env handles)."""
+    from highway_rope_ppo_b200.experiments.config import Condition, ConditionHP, Experiment
+
+    conds = [Condition.SORTED, Condition.SHUFFLED, Condition.SHUFFLED_ROPE, Condition.SHUFFLED_DISTPE,
+             Condition.SHUFFLED_RANKPE]
+    exps = []
+    for i in range(n):
+        cond = conds[i % len(conds)]
+        hp = ConditionHP(lr=(1e-4, 3e-4)[i % 2], hidden_dim=(128, 256)[(i // 2) % 2], batch_size=(32, 64)[(i // 3) % 2],
+                         epochs=(2, 3)[(i // 5) % 2], d_embed=4, steps_per_update=steps_per_update)
+        seed = 42 + 1000 * (i % 3)
+        over = {} if cond is Condition.SORTED else {"observation": {"order": "shuffled"}}
+        exps.append(Experiment(Experiment.make_name(cond, hp, seed) + f"_i{i}", cond, hp, seed=seed,
+                               max_episodes=max_episodes, env_config_overrides=over,
+                               extra={"eval_interval": 4, "log_interval": 2}))
+    return exps
+
+
+def test_multiplexed_experiments_reproduce_sequential_runs(highway_config, tmp_path):
+    """R = 16 experiments sharing env handles, one launch / one synchronisation per tick, updates
+    overlapped on their own streams (experiments/multiplex.py) end with exactly the parameters, Adam state, rewards
+    and update metrics of 16 sequential ExperimentRunner.launch calls (the replacement of utils/device_pool.py:45-72)."""
+    from highway_rope_ppo_b200.experiments.multiplex import MultiplexedRunner
+    from highway_rope_ppo_b200.experiments.runner import ExperimentRunner
+
+    exps = _sweep_like_experiments(16, max_episodes=8, steps_per_update=96)
+
+    def capture(cls, **kw):
+        agents = {}
+
+        class Capturing(cls):
+            def _create_agent(self, state_dim, action_dim, hp, logger, device):
+                agent = super()._create_agent(state_dim, action_dim, hp, logger, device)
+                agents[logger.name] = agent
+                return agent
+        return Capturing(highway_config, artifacts_dir=str(tmp_path / cls.__name__), **kw), agents
+
+    seq_runner, seq_agents = capture(ExperimentRunner)
+    seq = [seq_runner.launch(e) for e in exps]
+    mux_runner, mux_agents = capture(MultiplexedRunner, max_concurrent=16)
+    mux = mux_runner.launch_many(exps)
+    assert [r["experiment_name"] for r in mux] == [e.name for e in exps]
+    for a, b in zip(seq, mux):
+        assert a["status"] == b["status"] == "COMPLETED", (a.get("error_traceback"), b.get("error_traceback"))
+        assert a["rewards"] == b["rewards"] and a["avg_rewards"] == b["avg_rewards"], a["experiment_name"]
+        ha, hb = a["metrics_history"], b["metrics_history"]
+        assert ha["episode_rewards"] == hb["episode_rewards"]
+        assert len(ha["policy_updates"]) == len(hb["policy_updates"]) >= 2
+        for ua, ub in zip(ha["policy_updates"], hb["policy_updates"]):
+            assert {k: v for k, v in ua.items() if k != "time"} == {k: v for k, v in ub.items() if k != "time"}
+    for name, agent in seq_agents.items():
+        other = mux_agents[name]
+        assert torch.equal(agent.actor_critic.flat, other.actor_critic.flat), name
+        assert torch.equal(agent.optimizer.exp_avg, other.optimizer.exp_avg), name
+        assert torch.equal(agent.optimizer.exp_avg_sq, other.optimizer.exp_avg_sq), name
+    # the experiments really shared launches: far fewer simulator kernels than env interactions
+    print("env launches", mux_runner.env_launches, "for", mux_runner.env_requests, "env.reset / env.step calls in",
+          mux_runner.ticks, "ticks")
+    assert mux_runner.env_launches < 0.8 * mux_runner.env_requests
+
+
+def test_multiplexed_runner_reports_failures_per_experiment(highway_config, tmp_path):
+    from highway_rope_ppo_b200.experiments.config import Condition, ConditionHP, Experiment
+    from highway_rope_ppo_b200.experiments.multiplex import MultiplexedRunner
+
+    good = _sweep_like_experiments(2, max_episodes=2, steps_per_update=32)
+    bad = Experiment("bad", Condition.SHUFFLED_ROPE, ConditionHP(d_embed=16), seed=1, max_episodes=1)
+    res = MultiplexedRunner(highway_config, artifacts_dir=str(tmp_path)).launch_many([good[0], bad, good[1]])
+    assert [r["status"] for r in res] == ["COMPLETED", "FAILED", "COMPLETED"]
+    assert "rotate_dim" in res[1]["error_message"] and "error_traceback" in res[1]
