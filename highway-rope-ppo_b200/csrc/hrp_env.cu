@@ -111,21 +111,29 @@ template <typename R> __device__ __forceinline__ R wrap_to_pi(R x)
     if (x >= -pi && x < pi) return x;
     return x - R(2) * pi * floor((x + pi) / (R(2) * pi));
 }
-// first set bit above / last set bit below rank p of a 64-slot occupancy mask, on the two 32-bit halves (the
-// 64-bit shift / ffs / clz sequences the compiler emits for the one-line versions cost twice as many instructions)
+// first set bit above / last set bit below rank p of a 64-slot occupancy mask.  The mask is shifted so that the
+// vehicle's own bit lands on bit 0 (front) / bit 63 (rear) with one funnel shift on the two 32-bit halves -- the
+// 64-bit shift / ffs / clz sequences the compiler emits for the one-line versions cost three times as many instructions.
 __device__ __forceinline__ int slot_front(ull mask, int p)
 {
     const uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
-    const uint32_t mlo = p < 31 ? lo & (0xFFFFFFFEu << p) : 0u;                                   // bits p+1 .. 31
-    const uint32_t mhi = p < 32 ? hi : (p < 63 ? hi & (0xFFFFFFFEu << (p - 32)) : 0u);             // bits max(p+1, 32) .. 63
-    return mlo ? __ffs((int)mlo) - 1 : (mhi ? 31 + __ffs((int)mhi) : -1);
+    const bool big = p >= 32;
+    const uint32_t a = big ? hi : lo, b = big ? 0u : hi;       // (b:a) = mask >> (p & 32)
+    const uint32_t l2 = __funnelshift_r(a, b, p) & ~1u;         // the shift is taken mod 32; bit 0 = the vehicle itself
+    const uint32_t h2 = b >> (p & 31);
+    const int r = l2 ? __ffs((int)l2) - 1 : 31 + __ffs((int)h2);
+    return (l2 | h2) ? p + r : -1;
 }
 __device__ __forceinline__ int slot_rear(ull mask, int p)
 {
     const uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
-    const uint32_t mhi = p > 32 ? hi & ((1u << (p - 32)) - 1u) : 0u;                               // bits 32 .. p-1
-    const uint32_t mlo = p >= 32 ? lo : (p > 0 ? lo & ((1u << p) - 1u) : 0u);                      // bits 0 .. min(p, 32)-1
-    return mhi ? 63 - __clz((int)mhi) : (mlo ? 31 - __clz((int)mlo) : -1);
+    const int s = 63 - p;                                       // shift left so that bit p lands on bit 63
+    const bool big = s >= 32;
+    const uint32_t a = big ? lo : hi, b = big ? 0u : lo;       // (a:b) = mask << (s & 32)
+    const uint32_t h2 = __funnelshift_l(b, a, s) & 0x7FFFFFFFu;
+    const uint32_t l2 = b << (s & 31);
+    const int r = h2 ? 63 - __clz((int)h2) : 31 - __clz((int)l2);
+    return (l2 | h2) ? r - s : -1;
 }
 template <typename R> __device__ __forceinline__ int closest_lane(R y, int lanes)
 {
