@@ -60,9 +60,10 @@ def parse():
     p.add_argument("--no-ppo", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
-    p.add_argument("--e2e-groups", type=int, default=1, choices=[1, 2],
-                   help="env groups of the host-buffer loop: 2 = two half-size groups on two streams (copies of one under "
-                        "the kernels of the other); measured slower than 1 on B200 (see DESIGN.md 5)")
+    p.add_argument("--e2e-groups", type=int, default=1, choices=[1, 2, 4, 8],
+                   help="env groups of the host-buffer loop: G groups of E/G envs on G streams (copies and host turn-around "
+                        "of one under the kernels of the others)")
+    p.add_argument("--e2e-eager", action="store_true", help="host-buffer loop without CUDA graphs")
     return p.parse_args()
 
 
@@ -472,62 +473,33 @@ def run_ours(args):
                              "achieved_ginst_s": wi / env_kernel_s / 1e9, "peak_ginst_s": peak_issue / 1e9,
                              "frac": wi / env_kernel_s / peak_issue}
 
-    # e2e: the same step through the host-buffer API (pinned host obs -> policy -> host actions -> env -> host obs).
-    # The envs are split into two groups of E/2 on two streams, half a step apart: one group's PCIe copies run under
-    # the other group's kernels.  Per group-step: H2D observation, policy, D2H action, env kernel, D2H observation /
-    # reward / flags, ONE host synchronisation (an event) before the host touches the group's buffers again.
+    # e2e: the same step through the host-buffer API (training/host_pipeline.py): pinned host observation -> H2D ->
+    # policy -> env kernel -> observation / reward / flags written straight into pinned host buffers, action D2H; one
+    # CUDA graph launch and ONE host synchronisation (an event) per group-step.  With G groups of E/G envs on G streams
+    # one group's PCIe traffic and host turn-around hide under the other groups' kernels.
     e2e = None
     if not args.no_e2e:
+        from highway_rope_ppo_b200.training.host_pipeline import HostBufferPipeline
+
         Ke = min(K, 200)
-        G = args.e2e_groups if E % 2 == 0 else 1
+        G = args.e2e_groups if E % args.e2e_groups == 0 else 1
         Eg = E // G
-        groups = []
-        for gi in range(G):
-            genv = make_vec_env(Condition[cond_name], HIGHWAY_CONFIG, d_embed, over, num_envs=Eg, device=dev, seed=42,
-                                env_id_base=rank * E + gi * Eg, strict_d_embed=False)
-            gb = {"env": genv, "stream": torch.cuda.Stream(device=dev), "event": torch.cuda.Event(),
-                  "side": torch.cuda.Stream(device=dev), "acted": torch.cuda.Event(), "copied": torch.cuda.Event(),
-                  "obs_h": torch.zeros((Eg, N, Fout), dtype=torch.float32).pin_memory(),
-                  "act_h": torch.zeros((Eg, 2), dtype=torch.float32).pin_memory(),
-                  "rew_h": torch.zeros(Eg, dtype=torch.float32).pin_memory(),
-                  "te_h": torch.zeros(Eg, dtype=torch.uint8).pin_memory(), "tr_h": torch.zeros(Eg, dtype=torch.uint8).pin_memory(),
-                  "obs_d": torch.empty((Eg, S), device=dev),
-                  "out": {"action": torch.empty((Eg, A), device=dev), "pre_tanh": torch.empty((Eg, A), device=dev),
-                          "log_prob": torch.empty(Eg, device=dev), "value": torch.empty(Eg, device=dev)}}
-            genv.reset_host(42, gb["obs_h"].numpy())
-            groups.append(gb)
-
-        def group_step(gi):
-            gb = groups[gi]
-            gb["event"].synchronize()                                   # the group's previous results are on the host
-            gb["copied"].synchronize()
-            with torch.cuda.stream(gb["stream"]):
-                gb["obs_d"].copy_(gb["obs_h"].view(Eg, S), non_blocking=True)          # H2D observation
-                agent.actor_critic.row_base = rank * E + gi * Eg
-                agent.act(gb["obs_d"], out=gb["out"], lane=1 + gi)
-                gb["acted"].record()
-                # the step kernel writes observation / reward / flags straight into the page-locked host buffers
-                gb["env"].step_host_async(gb["out"]["action"], gb["obs_h"].numpy(), gb["rew_h"].numpy(), gb["te_h"].numpy(),
-                                          gb["tr_h"].numpy())
-                gb["event"].record()
-            with torch.cuda.stream(gb["side"]):                                        # D2H action, under the env kernel
-                gb["side"].wait_event(gb["acted"])
-                gb["act_h"].copy_(gb["out"]["action"], non_blocking=True)
-                gb["copied"].record()
-
+        genvs = [make_vec_env(Condition[cond_name], HIGHWAY_CONFIG, d_embed, over, num_envs=Eg, device=dev, seed=42,
+                              env_id_base=rank * E + gi * Eg, strict_d_embed=False) for gi in range(G)]
+        pipe = HostBufferPipeline(agent, genvs, use_graphs=not args.e2e_eager)
+        pipe.reset(42)
         for _ in range(5):
             for gi in range(G):
-                group_step(gi)
-        for gb in groups:
-            gb["event"].synchronize()
+                pipe.launch(gi)
+        for gi in range(G):
+            pipe.wait(gi)
         barrier()
         w0 = time.perf_counter()
         for _ in range(Ke):
             for gi in range(G):
-                group_step(gi)
-        for gb in groups:
-            gb["event"].synchronize()
-            gb["copied"].synchronize()
+                pipe.launch(gi)      # waits for the group's previous results to be on the host first
+        for gi in range(G):
+            pipe.wait(gi)
         w = time.perf_counter() - w0          # host clock: the region ends with every result on the host
         barrier()
         t = torch.tensor([w], dtype=torch.float64, device=dev)
@@ -535,14 +507,16 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * E * Ke / float(t.cpu()), "unit": UNIT,
                "h2d_bytes_per_step": E * S * 4, "d2h_bytes_per_step": E * 2 * 4 + E * S * 4 + E * 4 + 2 * E,
-               "steps": Ke, "groups": G,
-               "api": "PPOAgent.act on a pinned-host observation (H2D copy) + HighwayVecEnv.step_host_async "
-                      "(hrp_env_step_host_async): the device action feeds the step, the kernel writes observation, reward "
-                      "and flags straight into the page-locked host buffers (zero-copy), the action is copied to the host "
-                      "under the env kernel; one event wait per step" + (" and group (two half-size groups on two streams)" if G == 2 else "")}
+               "steps": Ke, "groups": G, "cuda_graphs": not args.e2e_eager,
+               "api": "HostBufferPipeline.launch / wait (training/host_pipeline.py): PPOAgent.act on a pinned-host "
+                      "observation (H2D copy) + HighwayVecEnv.step_host_async (hrp_env_step_host_async): the device action "
+                      "feeds the step, the kernel writes observation, reward and flags straight into the page-locked host "
+                      "buffers (zero-copy), the action is copied to the host under the env kernel; one graph launch and one "
+                      f"event wait per group-step, {G} group(s) of {Eg} envs on their own streams"}
+        pipe.close()
         agent.actor_critic.row_base = rank * E
-        for gb in groups:
-            gb["env"].close()
+        for genv in genvs:
+            genv.close()
 
     # PPO iteration (rollout of T steps + update: epochs x minibatches, gradient exchange if N > 1)
     ppo = None

@@ -339,10 +339,26 @@ heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, con
                  const float *__restrict__ log_std, const float *__restrict__ noise, int mode /*0 det, 1 noise[], 2 philox*/,
                  unsigned long long seed, unsigned long long draw, unsigned long long row_base, int ld, long long B,
                  int H, int A, float *__restrict__ action, float *__restrict__ pre_tanh,
-                 float *__restrict__ log_prob, float *__restrict__ value)
+                 float *__restrict__ log_prob, float *__restrict__ value, unsigned long long *draw_ctr)
 {
     hrp_pdl_release();
     hrp_pdl_wait();
+    if (draw_ctr) {
+        // device-resident draw counter (a captured launch cannot take a new `draw` argument per replay): every CTA
+        // reads draw_ctr[0], then takes a ticket from draw_ctr[1]; the CTA that takes the last ticket -- by then every
+        // CTA has read the counter -- advances it and clears the tickets for the next launch
+        __shared__ unsigned long long sdraw;
+        if (threadIdx.x == 0) {
+            sdraw = *(volatile unsigned long long *)draw_ctr + 1ull;   // the host path pre-increments too
+            __threadfence();
+            if (atomicAdd(draw_ctr + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+                draw_ctr[1] = 0ull;
+                draw_ctr[0] = sdraw;
+            }
+        }
+        __syncthreads();
+        draw = sdraw;
+    }
     long long b = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -897,14 +913,15 @@ static int forward_impl(hrp_ppo *h, const float *params, const float *x, long lo
 
 static int act_impl(hrp_ppo *h, const float *params, const float *states, const float *noise, int mode,
                     unsigned long long seed, unsigned long long draw, unsigned long long row_base, long long batch,
-                    float *action, float *pre_tanh, float *log_prob, float *value, cudaStream_t s)
+                    float *action, float *pre_tanh, float *log_prob, float *value, cudaStream_t s,
+                    unsigned long long *draw_ctr = nullptr)
 {
     const Layout &L = h->L;
     if (int rc = forward_impl(h, params, states, batch, nullptr, nullptr, s)) return rc;
     HRP_CUDA_OK(hrp_launch_pdl(heads_act_kernel, dim3((unsigned)((batch + 7) / 8)), dim3(256), 0, s, (const float *)h->ac,
                                (const float *)(h->ac + L.H), params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2,
                                params + L.log_std, noise, mode, seed, draw, row_base, 2 * L.H, (long long)batch, L.H, L.A,
-                               action, pre_tanh, log_prob, value));
+                               action, pre_tanh, log_prob, value, draw_ctr));
     return 0;
 }
 
@@ -1047,6 +1064,19 @@ int hrp_ppo_act_sample(hrp_ppo *h, const float *params, const float *states, uin
     if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
     return act_impl(h, params, states, nullptr, 2, seed, draw, row_base, batch, action, pre_tanh, log_prob, value,
                     (cudaStream_t)stream);
+}
+
+int hrp_ppo_act_sample_ctr(hrp_ppo *h, const float *params, const float *states, uint64_t seed, uint64_t *draw_ctr_dev,
+                           uint64_t row_base, int64_t batch, float *action, float *pre_tanh, float *log_prob,
+                           float *value, void *stream)
+{
+    if (!h || !params || !states || !action || !pre_tanh || !value || !draw_ctr_dev) {
+        hrp_set_error("hrp_ppo_act_sample_ctr: null argument");
+        return -1;
+    }
+    if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
+    return act_impl(h, params, states, nullptr, 2, seed, 0ull, row_base, batch, action, pre_tanh, log_prob, value,
+                    (cudaStream_t)stream, (unsigned long long *)draw_ctr_dev);
 }
 
 int hrp_gae(const float *reward, const float *value, const uint8_t *done, const float *last_value, int64_t T,

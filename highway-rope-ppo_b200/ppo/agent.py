@@ -210,16 +210,19 @@ class ActorCritic:
     # -- batched get_action: everything stays on the device -------------------------------------
     def act(self, states: torch.Tensor, noise: Optional[torch.Tensor] = None, deterministic: bool = False,
             out: Optional[Dict[str, torch.Tensor]] = None, lane: int = 0,
-            stream: Optional[int] = None) -> Dict[str, torch.Tensor]:
+            stream: Optional[int] = None, draw_counter: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """``get_action`` for [B, S] states -> dict(action, pre_tanh [B, A]; log_prob, value [B]).  ``stream``: raw
         ``cudaStream_t`` to enqueue on instead of torch's current stream (the multiplexer's stream ring).
+        ``draw_counter``: int64 CUDA tensor [2] = (draw, 0) that replaces the host-side draw counter of the sampling
+        path, so that the call can be captured in a CUDA graph and replayed (``new_draw_counter``); such a capture
+        always contains the weight preparation, i.e. a replay sees the current parameters.
 
         ``lane`` > 0 selects a separate native workspace (same parameters) so that calls on different CUDA streams
         may overlap: the two env groups of the pipelined host-buffer loop (bench.py e2e) act concurrently."""
         states = self._as_states(states)
         B = states.shape[0]
         if lane:
-            return self._act_lane(states, B, out, lane, deterministic, noise)
+            return self._act_lane(states, B, out, lane, deterministic, noise, draw_counter)
         self._ensure_workspace(B)
         A = self.action_dim
         if out is None:
@@ -227,9 +230,20 @@ class ActorCritic:
                    "pre_tanh": torch.empty((B, A), dtype=torch.float32, device=self.device),
                    "log_prob": torch.empty(B, dtype=torch.float32, device=self.device),
                    "value": torch.empty(B, dtype=torch.float32, device=self.device)}
-        self._sync_weight_copies()
+        if draw_counter is not None:
+            self._lib.hrp_ppo_hold_weights(self._h, 0)
+            self._held_key = None
+        else:
+            self._sync_weight_copies()
         if stream is None:
             stream = self._stream()
+        if not deterministic and noise is None and draw_counter is not None:
+            _lib.check(self._lib.hrp_ppo_act_sample_ctr(self._h, self.flat.data_ptr(), states.data_ptr(), self._noise_seed,
+                                                        draw_counter.data_ptr(), int(self.row_base), B,
+                                                        out["action"].data_ptr(), out["pre_tanh"].data_ptr(),
+                                                        out["log_prob"].data_ptr(), out["value"].data_ptr(), stream),
+                       "hrp_ppo_act_sample_ctr")
+            return out
         if not deterministic and noise is None:
             # standard normals drawn in the kernel (Philox keyed by a seed taken from torch's generator at
             # construction, so set_random_seeds() still fixes the rollout; one draw counter per call)
@@ -246,7 +260,11 @@ class ActorCritic:
                    "hrp_ppo_act")
         return out
 
-    def _act_lane(self, states, B, out, lane, deterministic, noise):
+    def new_draw_counter(self) -> torch.Tensor:
+        """A device-resident draw counter continuing this instance's host-side one (``act(draw_counter=...)``)."""
+        return torch.tensor([self._draw, 0], dtype=torch.int64, device=self.device)
+
+    def _act_lane(self, states, B, out, lane, deterministic, noise, draw_counter=None):
         """act() on an additional workspace (its GEMM scratch, weight copies and hold state are its own)."""
         if deterministic or noise is not None:
             raise ValueError("workspace lanes serve the sampling rollout path only")
@@ -266,6 +284,14 @@ class ActorCritic:
                    "pre_tanh": torch.empty((B, A), dtype=torch.float32, device=self.device),
                    "log_prob": torch.empty(B, dtype=torch.float32, device=self.device),
                    "value": torch.empty(B, dtype=torch.float32, device=self.device)}
+        if draw_counter is not None:
+            self._lib.hrp_ppo_hold_weights(h[0], 0)
+            _lib.check(self._lib.hrp_ppo_act_sample_ctr(h[0], self.flat.data_ptr(), states.data_ptr(), self._noise_seed,
+                                                        draw_counter.data_ptr(), int(self.row_base), B,
+                                                        out["action"].data_ptr(), out["pre_tanh"].data_ptr(),
+                                                        out["log_prob"].data_ptr(), out["value"].data_ptr(),
+                                                        self._stream()), "hrp_ppo_act_sample_ctr")
+            return out
         self._draw += 1
         _lib.check(self._lib.hrp_ppo_act_sample(h[0], self.flat.data_ptr(), states.data_ptr(), self._noise_seed, self._draw,
                                                 int(self.row_base), B, out["action"].data_ptr(), out["pre_tanh"].data_ptr(),
@@ -497,9 +523,11 @@ class PPOAgent:
         return self.actor_critic.get_action(state, deterministic)
 
     def act(self, states: torch.Tensor, deterministic: bool = False, noise: Optional[torch.Tensor] = None,
-            out: Optional[Dict[str, torch.Tensor]] = None, lane: int = 0) -> Dict[str, torch.Tensor]:
+            out: Optional[Dict[str, torch.Tensor]] = None, lane: int = 0, stream: Optional[int] = None,
+            draw_counter: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         self.launches += 1
-        return self.actor_critic.act(states, noise=noise, deterministic=deterministic, out=out, lane=lane)
+        return self.actor_critic.act(states, noise=noise, deterministic=deterministic, out=out, lane=lane, stream=stream,
+                                     draw_counter=draw_counter)
 
     # -- distributed helpers (ppo/distributed.py) ---------------------------------------------------
     @staticmethod

@@ -231,6 +231,12 @@ int hrp_ppo_act(hrp_ppo *h, const float *params_dev, const float *states_dev, co
 int hrp_ppo_act_sample(hrp_ppo *h, const float *params_dev, const float *states_dev, uint64_t seed, uint64_t draw,
                        uint64_t row_base, int64_t batch, float *action_dev, float *pre_tanh_dev,
                        float *log_prob_dev, float *value_dev, void *stream);
+/* hrp_ppo_act_sample with the draw counter resident on the device, for CUDA-graph capture (a captured launch cannot take
+ * a new scalar per replay): draw_ctr_dev[2] = {counter, 0}; a launch draws with counter + 1 -- the value a host loop that
+ * pre-increments `draw` (PPOAgent.act) would pass -- and leaves counter + 1 behind.  Everything else as above. */
+int hrp_ppo_act_sample_ctr(hrp_ppo *h, const float *params_dev, const float *states_dev, uint64_t seed,
+                           uint64_t *draw_ctr_dev, uint64_t row_base, int64_t batch, float *action_dev,
+                           float *pre_tanh_dev, float *log_prob_dev, float *value_dev, void *stream);
 /* PPOMemory.compute_advantages (agent.py:126-138) over [T,E] (time-major), reverse scan.
  * last_value_dev[E]; done as uint8.  Outputs advantages[T,E] (float32), returns[T,E]. */
 int hrp_gae(const float *reward_dev, const float *value_dev, const uint8_t *done_dev,

@@ -250,3 +250,44 @@ def test_multiplexed_runner_reports_failures_per_experiment(highway_config, tmp_
     res = MultiplexedRunner(highway_config, artifacts_dir=str(tmp_path)).launch_many([good[0], bad, good[1]])
     assert [r["status"] for r in res] == ["COMPLETED", "FAILED", "COMPLETED"]
     assert "rotate_dim" in res[1]["error_message"] and "error_traceback" in res[1]
+
+
+@pytest.mark.parametrize("groups,graphs", [(1, True), (2, True), (2, False)])
+def test_host_buffer_pipeline_equals_the_device_loop(highway_config, groups, graphs):
+    """training/host_pipeline.py: the graphed, grouped host-buffer loop (pinned observation in, pinned results out)
+    produces exactly the actions, observations, rewards and flags of the plain device-resident act + step loop."""
+    from highway_rope_ppo_b200.experiments.config import Condition
+    from highway_rope_ppo_b200.experiments.wrappers import make_vec_env
+    from highway_rope_ppo_b200.ppo.agent import PPOAgent
+    from highway_rope_ppo_b200.training.host_pipeline import HostBufferPipeline
+
+    E, steps = 256, 6
+    over = {"observation": {"order": "shuffled"}}
+    mk = lambda n, base: make_vec_env(Condition.SHUFFLED_ROPE, highway_config, 4, over, num_envs=n, seed=42, env_id_base=base)
+    torch.manual_seed(1)
+    agent = PPOAgent(60, 2, hidden_dim=64, batch_size=E)
+    torch.manual_seed(1)
+    ref_agent = PPOAgent(60, 2, hidden_dim=64, batch_size=E)
+    ref_env = mk(E, 0)
+    obs = ref_env.reset(42).clone()
+    want = []
+    for _ in range(steps):
+        out = ref_agent.act(obs.view(E, -1))
+        o, r, te, tr = ref_env.step(out["action"])
+        want.append((out["action"].cpu().numpy().copy(), o.cpu().numpy().copy(), r.cpu().numpy().copy(),
+                     te.cpu().numpy().copy(), tr.cpu().numpy().copy()))
+        obs = o.clone()
+    Eg = E // groups
+    pipe = HostBufferPipeline(agent, [mk(Eg, g * Eg) for g in range(groups)], use_graphs=graphs)
+    pipe.reset(42)
+    for t in range(steps):
+        for g in range(groups):
+            pipe.launch(g)
+        for g in range(groups):
+            b = pipe.wait(g)
+            sl = slice(g * Eg, (g + 1) * Eg)
+            a, o, r, te, tr = want[t]
+            assert np.array_equal(b["action"], a[sl]), (t, g)
+            assert np.array_equal(b["obs"], o[sl]) and np.array_equal(b["reward"], r[sl]), (t, g)
+            assert np.array_equal(b["terminated"], te[sl]) and np.array_equal(b["truncated"], tr[sl]), (t, g)
+    pipe.close()

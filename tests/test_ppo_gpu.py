@@ -530,3 +530,32 @@ def test_workspace_lanes_share_the_parameters():
     s1.synchronize()
     for k in ("action", "pre_tanh", "log_prob", "value"):
         assert torch.equal(got[k], want[k]), k
+
+
+def test_device_resident_draw_counter_equals_host_counter_and_replays_in_a_graph():
+    """hrp_ppo_act_sample_ctr: the sampling path with its draw counter in device memory draws exactly what the host
+    counter path draws, call after call, eagerly and as a replayed CUDA graph (the host-buffer pipeline relies on it)."""
+    torch.manual_seed(9)
+    a = _agent(60, 2, 64, 1024)
+    torch.manual_seed(9)
+    b = _agent(60, 2, 64, 1024)
+    x = torch.randn(1000, 60, device="cuda:0") * 0.3
+    want = [{k: v.clone() for k, v in a.act(x).items()} for _ in range(5)]
+    ctr = b.actor_critic.new_draw_counter()
+    out = {k: torch.empty_like(v) for k, v in want[0].items()}
+    for i in range(2):   # eager
+        b.act(x, out=out, draw_counter=ctr)
+        for k in out:
+            assert torch.equal(out[k], want[i][k]), (i, k)
+    assert ctr.tolist() == [2, 0]
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(g, stream=s):
+        b.act(x, out=out, draw_counter=ctr)
+    for i in range(2, 5):   # replays advance the counter themselves
+        g.replay()
+        torch.cuda.synchronize()
+        for k in out:
+            assert torch.equal(out[k], want[i][k]), (i, k)
+    assert ctr.tolist() == [5, 0]
