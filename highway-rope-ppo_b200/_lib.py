@@ -56,6 +56,14 @@ class HrpState(C.Structure):
                 ("obs_draw", C.POINTER(C.c_uint32))]
 
 
+class HrpActItem(C.Structure):
+    """``hrp_act_item``: one policy / one state of ``hrp_ppo_act_multi``."""
+    _fields_ = [("params_dev", C.c_void_p), ("state_dev", C.c_void_p), ("out_dev", C.c_void_p),
+                ("seed", C.c_uint64), ("draw", C.c_uint64), ("row", C.c_uint64),
+                ("state_dim", C.c_int32), ("action_dim", C.c_int32), ("hidden_dim", C.c_int32),
+                ("deterministic", C.c_int32)]
+
+
 STATE_F64 = ("x", "y", "heading", "speed", "target_speed", "delta", "timer", "impact_x", "impact_y")
 STATE_I32 = ("lane", "target_lane", "crashed", "has_impact")
 
@@ -96,6 +104,7 @@ SIGNATURES: Dict[str, Any] = {
     "hrp_ppo_forward": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "hrp_ppo_act": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hrp_ppo_act_sample": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _u64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hrp_ppo_act_multi": (C.c_int, [_vp, _i32, _vp]),
     "hrp_ppo_act_sample_ctr": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _u64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hrp_gae": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _vp, _vp, _vp]),
     "hrp_adv_stats": (C.c_int, [_vp, _i64, _vp, _vp]),

@@ -911,6 +911,104 @@ static int forward_impl(hrp_ppo *h, const float *params, const float *x, long lo
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// ActorCritic.get_action (agent.py:56-74) for ONE state each of many INDEPENDENT policies: the sweep's experiments run a
+// single env (main.py:50-58), so their rollout forward is a chain of matrix-VECTOR products -- nothing for a tensor core
+// (a 128-row tile would be 1/128 full), everything for bandwidth: 0.85 MB of weights per policy at H = 256.  A cluster of
+// ACT_CLUSTER CTAs owns one policy: each CTA forms its slice of a layer's outputs (a warp per output row, coalesced
+// weight rows, shuffle reduction in a fixed order), writes the slice into the activation vector of every CTA of the
+// cluster through distributed shared memory, and the cluster synchronises once per layer.  CTA 0 finishes with the two
+// heads, the tanh-Gaussian sample (the same Philox keying and Box-Muller as heads_act_kernel) and the log-prob.
+// One launch serves up to ACT_ITEMS policies of different widths (multiplexed experiments, experiments/multiplex.py).
+constexpr int ACT_CLUSTER = 4, ACT_THREADS = 512, ACT_ITEMS = 32, ACT_MAX_DIM = 1024;
+struct ActBatch { hrp_act_item it[ACT_ITEMS]; };
+
+__device__ __forceinline__ void act_layer(const float *__restrict__ W, const float *__restrict__ bias, const float *in, int K,
+                                          int O, float *out_local, int out_off, unsigned rank, bool relu)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = ACT_THREADS / 32;
+    const int per = (O + ACT_CLUSTER - 1) / ACT_CLUSTER;
+    const int lo = rank * per, hi = min(O, lo + per);
+    for (int o = lo + warp; o < hi; o += nw) {
+        const float *w = W + (size_t)o * K;
+        float acc0 = 0.f, acc1 = 0.f;
+        int k = lane;
+        for (; k + 32 < K; k += 64) {
+            acc0 = fmaf(w[k], in[k], acc0);
+            acc1 = fmaf(w[k + 32], in[k + 32], acc1);
+        }
+        if (k < K) acc0 = fmaf(w[k], in[k], acc0);
+        float acc = acc0 + acc1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(HRP_FULL, acc, d);
+        acc += bias[o];
+        if (relu) acc = fmaxf(acc, 0.f);
+        if (lane < ACT_CLUSTER) *cluster.map_shared_rank(out_local + out_off + o, lane) = acc;   // to every CTA of the cluster
+    }
+    cluster.sync();
+}
+
+__global__ void __cluster_dims__(ACT_CLUSTER, 1, 1) __launch_bounds__(ACT_THREADS)
+act_multi_kernel(const __grid_constant__ ActBatch batch)
+{
+    namespace cg = cooperative_groups;
+    __shared__ float xs[ACT_MAX_DIM], h1[ACT_MAX_DIM], h2[ACT_MAX_DIM], ac[2 * ACT_MAX_DIM];
+    const hrp_act_item &it = batch.it[blockIdx.y];
+    const unsigned rank = cg::this_cluster().block_rank();
+    const int S = it.state_dim, A = it.action_dim, H = it.hidden_dim;
+    const Layout L = make_layout(S, A, H);
+    const float *p = it.params_dev;
+    for (int i = threadIdx.x; i < S; i += ACT_THREADS) xs[i] = it.state_dev[i];
+    __syncthreads();
+    cg::this_cluster().sync();   // every CTA of the cluster is running before anyone writes into its shared memory
+    act_layer(p + L.w1, p + L.b1, xs, S, H, h1, 0, rank, true);
+    act_layer(p + L.w2, p + L.b2, h1, H, H, h2, 0, rank, true);
+    act_layer(p + L.wa1, p + L.ba1, h2, H, H, ac, 0, rank, true);
+    act_layer(p + L.wc1, p + L.bc1, h2, H, H, ac, H, rank, true);
+    if (rank != 0) return;
+    // heads: warp a < A forms mean[a], warp A the value
+    __shared__ float head[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp <= A) {
+        const float *w = warp < A ? p + L.wa2 + (size_t)warp * H : p + L.wc2;
+        const float *v = warp < A ? ac : ac + H;
+        float acc = 0.f;
+        for (int k = lane; k < H; k += 32) acc = fmaf(v[k], w[k], acc);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(HRP_FULL, acc, d);
+        if (lane == 0) head[warp] = acc + (warp < A ? p[L.ba2 + warp] : p[L.bc2]);
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const int a = lane < A ? lane : 0;
+    const float mu = head[a];
+    float nrm = 0.f;
+    if (!it.deterministic) {
+        uint32_t r[4];
+        hrp_philox((uint32_t)it.row, (uint32_t)(it.row >> 32), (uint32_t)it.draw, (uint32_t)(it.draw >> 32),
+                   (uint32_t)it.seed, (uint32_t)(it.seed >> 32) ^ 0x5A5A5A5Au, r);
+        const uint32_t r1 = a < 2 ? r[0] : r[2], r2 = a < 2 ? r[1] : r[3];
+        float u1 = ((float)(r1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float u2 = ((float)(r2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float rad = sqrtf(-2.f * logf(u1)), sn, cs;
+        sincospif(2.f * u2, &sn, &cs);
+        nrm = rad * ((a & 1) ? sn : cs);
+    }
+    const float ls = p[L.log_std + a], sd = expf(ls);
+    const float z = it.deterministic ? mu : mu + sd * nrm;
+    const float t = tanhf(z);
+    const float d = z - mu;
+    float lp = -(d * d) / (2.f * sd * sd) - ls - 0.91893853320467274f;
+    lp -= log1pf(-(t * t) + 1e-6f);
+    lp = lane < A ? lp : 0.f;
+    lp += __shfl_xor_sync(HRP_FULL, lp, 1);
+    lp += __shfl_xor_sync(HRP_FULL, lp, 2);
+    if (lane < A) { it.out_dev[lane] = t; it.out_dev[A + lane] = z; }
+    if (lane == 0) { it.out_dev[2 * A] = it.deterministic ? 0.f : lp; it.out_dev[2 * A + 1] = head[A]; }
+}
+
 static int act_impl(hrp_ppo *h, const float *params, const float *states, const float *noise, int mode,
                     unsigned long long seed, unsigned long long draw, unsigned long long row_base, long long batch,
                     float *action, float *pre_tanh, float *log_prob, float *value, cudaStream_t s,
@@ -1077,6 +1175,29 @@ int hrp_ppo_act_sample_ctr(hrp_ppo *h, const float *params, const float *states,
     if (batch < 1 || batch > h->max_batch) { hrp_set_error("batch %lld outside [1, %lld]", (long long)batch, h->max_batch); return -1; }
     return act_impl(h, params, states, nullptr, 2, seed, 0ull, row_base, batch, action, pre_tanh, log_prob, value,
                     (cudaStream_t)stream, (unsigned long long *)draw_ctr_dev);
+}
+
+int hrp_ppo_act_multi(const hrp_act_item *items, int32_t count, void *stream)
+{
+    if (!items || count < 0) { hrp_set_error("hrp_ppo_act_multi: bad arguments"); return -1; }
+    for (int32_t i = 0; i < count; ++i) {
+        const hrp_act_item &it = items[i];
+        if (!it.params_dev || !it.state_dev || !it.out_dev || it.state_dim < 1 || it.state_dim > ACT_MAX_DIM || it.hidden_dim < 1 ||
+            it.hidden_dim > ACT_MAX_DIM || it.action_dim < 1 || it.action_dim > 4) {
+            hrp_set_error("hrp_ppo_act_multi: item %d: null pointer, or state_dim / hidden_dim outside [1, %d], or "
+                          "action_dim outside [1, 4]", (int)i, ACT_MAX_DIM);
+            return -1;
+        }
+    }
+    for (int32_t lo = 0; lo < count; lo += ACT_ITEMS) {
+        ActBatch b;
+        const int n = count - lo < ACT_ITEMS ? count - lo : ACT_ITEMS;
+        for (int i = 0; i < n; ++i) b.it[i] = items[lo + i];
+        for (int i = n; i < ACT_ITEMS; ++i) b.it[i] = items[lo];
+        act_multi_kernel<<<dim3(ACT_CLUSTER, n), ACT_THREADS, 0, (cudaStream_t)stream>>>(b);
+        HRP_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
 }
 
 int hrp_gae(const float *reward, const float *value, const uint8_t *done, const float *last_value, int64_t T,

@@ -6,8 +6,8 @@ drives its own single env and its own agent, one synchronous kernel chain per en
 share an env configuration share ONE simulator handle -- experiment r is env r of it, with its own seed
 (``hrp_env_set_seeds``) and a per-launch step mask (``hrp_env_set_step_mask``) because the runs are not in lock step
 (one is evaluating, one is inside its PPO update, one has finished) -- so a tick of the whole set is one env launch,
-one device-to-host copy and one host synchronisation; the R policies act on a small ring of streams between two
-events, and every PPO update is enqueued on its experiment's own stream without a host synchronisation
+one device-to-host copy and one host synchronisation; the R policies act in ONE launch (``hrp_ppo_act_multi``: a
+cluster of CTAs per policy, matrix-vector products), and every PPO update is enqueued on its experiment's own stream without a host synchronisation
 (``PPOAgent.update_begin``), so the updates of different experiments overlap with each other and with the stepping of
 the rest.
 
@@ -26,6 +26,7 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 import torch
 
+from .. import _lib
 from ..envs.highway_vec import HighwayVecEnv
 from ..training.routine import training_coroutine
 from ..utils.reproducibility import set_random_seeds
@@ -95,7 +96,7 @@ class _Slot:
         self.stream: Optional[torch.cuda.Stream] = None
         self.pending_update = None
         self.live = False
-        self.obs_row = self.out = None   # device views: this experiment's observation row / policy result row
+        self.obs_row = self.res_row = None   # device views: this experiment's observation row / policy result row
 
     def fail(self, err: BaseException) -> None:
         self.logger.error(f"[{self.exp.name}] Experiment execution failed!", exc_info=True)
@@ -112,17 +113,16 @@ class MultiplexedRunner(ExperimentRunner):
     """``launch_many(experiments)`` = ``[launch(e) for e in experiments]`` with the experiments advancing together.
 
     ``max_concurrent`` bounds R (each experiment holds its network, Adam state, CUDA graphs and a rollout);
-    experiments beyond it start as earlier ones finish.  ``act_streams`` is the size of the stream ring the R policy
-    forwards of a tick are spread over."""
+    experiments beyond it start as earlier ones finish."""
 
     def __init__(self, base_env_config: dict, device_pool: Optional[Any] = None, artifacts_dir: Optional[str] = None,
-                 max_concurrent: int = 16, act_streams: int = 8):
+                 max_concurrent: int = 16):
         super().__init__(base_env_config, device_pool, artifacts_dir)
         self.max_concurrent = int(max_concurrent)
-        self.act_streams = int(act_streams)
         self.ticks = 0          # host synchronisation rounds of the last launch_many
         self.env_launches = 0   # simulator kernels of the last launch_many (one per group per tick and kind)
         self.env_requests = 0   # env.reset / env.step calls of the experiments those launches answered
+        self._lib = _lib.load()
 
     # ------------------------------------------------------------------ set-up of one experiment
     def _prepare(self, slot: _Slot, device: torch.device, groups: Dict[Any, _Group]) -> None:
@@ -194,14 +194,12 @@ class MultiplexedRunner(ExperimentRunner):
                 for s in g.slots:   # the policy of experiment e reads row e of the observation, writes row e of the results
                     row, A = g.res[s.e], 2
                     s.obs_row = g.env.obs[s.e].view(1, -1)
-                    s.out = {"action": row[0:A], "pre_tanh": row[A:2 * A], "log_prob": row[2 * A:2 * A + 1],
-                             "value": row[2 * A + 1:2 * A + 2]}
-            ring = [torch.cuda.Stream(device) for _ in range(max(1, min(self.act_streams, len(slots))))]
+                    s.res_row = row
             for slot in slots:
                 if slot.live:
                     self._advance(slot, None, first=True)
             while any(s.live for s in slots):
-                self._tick(slots, list(groups.values()), ring, device)
+                self._tick(slots, list(groups.values()), device)
         finally:
             torch.cuda.synchronize(device)
             for g in groups.values():
@@ -209,7 +207,7 @@ class MultiplexedRunner(ExperimentRunner):
             _rng_set(outer_rng)
         return [s.result for s in slots]
 
-    def _tick(self, slots: List[_Slot], groups: List[_Group], ring, device: torch.device) -> None:
+    def _tick(self, slots: List[_Slot], groups: List[_Group], device: torch.device) -> None:
         self.ticks += 1
         main = torch.cuda.current_stream(device)
         ready = False
@@ -272,26 +270,25 @@ class MultiplexedRunner(ExperimentRunner):
                     self._advance(s, g.obs_np[s.e].copy())
 
         # -- act: every policy reads its env's row of the device observation (the very bytes the loop holds on the
-        #    host) and writes into its row of the group's result buffer; one copy + one synchronisation for all
+        #    host) and writes into its row of the group's result buffer: ONE launch for all of them
+        #    (hrp_ppo_act_multi: a cluster of CTAs per policy), one copy per group, one synchronisation
         acts = asking("act")
         if acts:
-            fork = torch.cuda.Event()
-            fork.record(main)
-            used = set()
-            for i, s in enumerate(acts):
-                st = ring[i % len(ring)]
-                if i < len(ring):
-                    st.wait_event(fork)
-                    used.add(st)
+            items = (_lib.HrpActItem * len(acts))()
+            n = 0
+            for s in acts:
                 try:
                     s.agent.launches += 1
-                    s.agent.actor_critic.act(s.obs_row, deterministic=bool(s.req[2]), out=s.out, stream=st.cuda_stream)
+                    items[n] = s.agent.actor_critic.act_item(s.obs_row, s.res_row, bool(s.req[2]))
+                    n += 1
                 except Exception as err:
                     s.fail(err)
-            for st in used:
-                join = torch.cuda.Event()
-                join.record(st)
-                main.wait_event(join)
+            try:
+                _lib.check(self._lib.hrp_ppo_act_multi(items, n, main.cuda_stream), "hrp_ppo_act_multi")
+            except Exception as err:
+                for s in acts:
+                    if s.live:
+                        s.fail(err)
             for g in {s.group for s in acts}:
                 g.res_host.copy_(g.res, non_blocking=True)
             main.synchronize()

@@ -221,6 +221,8 @@ class ActorCritic:
         may overlap: the two env groups of the pipelined host-buffer loop (bench.py e2e) act concurrently."""
         states = self._as_states(states)
         B = states.shape[0]
+        if B == 1 and noise is None and not lane and draw_counter is None:
+            return self._act_one(states, deterministic, out, stream)
         if lane:
             return self._act_lane(states, B, out, lane, deterministic, noise, draw_counter)
         self._ensure_workspace(B)
@@ -259,6 +261,39 @@ class ActorCritic:
                                          out["log_prob"].data_ptr(), out["value"].data_ptr(), stream),
                    "hrp_ppo_act")
         return out
+
+    # -- one state: the matrix-vector kernel (what the reference's single-env loop calls once per env step) -------
+    def act_item(self, state: torch.Tensor, out_row: torch.Tensor, deterministic: bool) -> "_lib.HrpActItem":
+        """The ``hrp_act_item`` of one ``get_action`` call of this policy (advances the draw counter when sampling):
+        ``hrp_ppo_act_multi`` serves many such items, of different policies, in one launch."""
+        if not deterministic:
+            self._draw += 1
+        it = _lib.HrpActItem()
+        it.params_dev, it.state_dev, it.out_dev = self.flat.data_ptr(), state.data_ptr(), out_row.data_ptr()
+        it.seed, it.draw, it.row = self._noise_seed, self._draw, int(self.row_base)
+        it.state_dim, it.action_dim, it.hidden_dim = self.state_dim, self.action_dim, self.hidden_dim
+        it.deterministic = int(bool(deterministic))
+        return it
+
+    def _act_one(self, states, deterministic, out, stream):
+        A = self.action_dim
+        packed = (out is not None and out["action"].numel() == A and out["pre_tanh"].numel() == A
+                  and out["pre_tanh"].data_ptr() == out["action"].data_ptr() + 4 * A
+                  and out["log_prob"].data_ptr() == out["action"].data_ptr() + 8 * A
+                  and out["value"].data_ptr() == out["action"].data_ptr() + 8 * A + 4)
+        row = out["action"] if packed else torch.empty(2 * A + 2, dtype=torch.float32, device=self.device)
+        it = self.act_item(states, row, deterministic)
+        _lib.check(self._lib.hrp_ppo_act_multi(C.byref(it), 1, self._stream() if stream is None else stream),
+                   "hrp_ppo_act_multi")
+        if packed:
+            return out
+        res = {"action": row[0:A].view(1, A), "pre_tanh": row[A:2 * A].view(1, A), "log_prob": row[2 * A:2 * A + 1],
+               "value": row[2 * A + 1:2 * A + 2]}
+        if out is not None:
+            for k, v in res.items():
+                out[k].view(-1).copy_(v.view(-1))
+            return out
+        return res
 
     def new_draw_counter(self) -> torch.Tensor:
         """A device-resident draw counter continuing this instance's host-side one (``act(draw_counter=...)``)."""

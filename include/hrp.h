@@ -237,6 +237,20 @@ int hrp_ppo_act_sample(hrp_ppo *h, const float *params_dev, const float *states_
 int hrp_ppo_act_sample_ctr(hrp_ppo *h, const float *params_dev, const float *states_dev, uint64_t seed,
                            uint64_t *draw_ctr_dev, uint64_t row_base, int64_t batch, float *action_dev,
                            float *pre_tanh_dev, float *log_prob_dev, float *value_dev, void *stream);
+/* ActorCritic.get_action (agent.py:56-74) for ONE state each of `count` independent policies in one launch: the rollout
+ * forward of the sweep's single-env experiments (main.py:50-58, E = 1), which utils/device_pool.py:45-72 time-shares
+ * as processes and experiments/multiplex.py batches.  Matrix-vector products in fp32 FMA arithmetic (a cluster of CTAs per
+ * policy, weights streamed once); the policies may differ in every dimension.  out_dev[2 * action_dim + 2] receives
+ * action = tanh(z), pre_tanh = z, log_prob (0 when deterministic), value.  Sampling: Philox4x32-10 keyed by seed,
+ * counter (row, draw), as hrp_ppo_act_sample with row_base + row = `row`.  items is a HOST array. */
+typedef struct hrp_act_item {
+    const float *params_dev;   /* flat parameter buffer of this policy, ActorCritic.parameters() order */
+    const float *state_dev;    /* [state_dim] */
+    float *out_dev;            /* [2 * action_dim + 2] */
+    uint64_t seed, draw, row;
+    int32_t state_dim, action_dim, hidden_dim, deterministic;
+} hrp_act_item;
+int hrp_ppo_act_multi(const hrp_act_item *items, int32_t count, void *stream);
 /* PPOMemory.compute_advantages (agent.py:126-138) over [T,E] (time-major), reverse scan.
  * last_value_dev[E]; done as uint8.  Outputs advantages[T,E] (float32), returns[T,E]. */
 int hrp_gae(const float *reward_dev, const float *value_dev, const uint8_t *done_dev,

@@ -47,6 +47,21 @@ def test_cfg_struct_layout_matches_c(tmp_path):
     assert nums[2:] == [getattr(HrpCfg, f).offset for f in fields]
 
 
+def test_act_item_struct_layout_matches_c(tmp_path):
+    """hrp_act_item (hrp_ppo_act_multi) as gcc sees it == the ctypes mirror."""
+    from highway_rope_ppo_b200._lib import HrpActItem
+
+    src = tmp_path / "a.c"
+    fields = [f[0] for f in HrpActItem._fields_]
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hrp.h"\nint main(){printf("%zu", sizeof(hrp_act_item));'
+                   + "".join(f'printf(" %zu", offsetof(hrp_act_item, {f}));' for f in fields) + "return 0;}\n")
+    exe = tmp_path / "a"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    nums = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert nums[0] == C.sizeof(HrpActItem) == 64
+    assert nums[1:] == [getattr(HrpActItem, f).offset for f in fields]
+
+
 def test_philox_host_entry_point_known_answer():
     from highway_rope_ppo_b200 import _lib
 

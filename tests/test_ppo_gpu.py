@@ -559,3 +559,58 @@ def test_device_resident_draw_counter_equals_host_counter_and_replays_in_a_graph
         for k in out:
             assert torch.equal(out[k], want[i][k]), (i, k)
     assert ctr.tolist() == [5, 0]
+
+
+def test_multi_policy_act_matches_the_batched_forward_and_the_reference():
+    """hrp_ppo_act_multi: one state each of several policies of different widths in ONE launch (the sweep's single-env
+    rollout forward) == each policy's own batched forward (3xTF32 tensor-core path) to fp32 rounding, deterministic and
+    sampled, and the B = 1 call of ActorCritic.act goes through it."""
+    import ctypes as C
+
+    from highway_rope_ppo_b200 import _lib
+
+    lib = _lib.load()
+    dims = [(60, 128), (60, 256), (120, 384), (300, 512), (60, 64), (12, 16)]
+    agents, states = [], []
+    for i, (S, H) in enumerate(dims):
+        torch.manual_seed(20 + i)
+        agents.append(_agent(S, 2, H, 8))
+        states.append(torch.randn(1, S, device="cuda:0") * 0.5)
+    for det in (True, False):
+        res = torch.zeros((len(dims), 6), device="cuda:0")
+        items = (_lib.HrpActItem * len(dims))()
+        for i, a in enumerate(agents):
+            items[i] = a.actor_critic.act_item(states[i], res[i], det)
+        assert lib.hrp_ppo_act_multi(items, len(dims), torch.cuda.current_stream().cuda_stream) == 0
+        torch.cuda.synchronize()
+        for i, a in enumerate(agents):
+            ac = a.actor_critic
+            mean, std, value = ac.forward(states[i])
+            got = res[i].cpu().numpy()
+            np.testing.assert_allclose(got[5], value.cpu().numpy().reshape(()), atol=2e-6, rtol=2e-6)
+            if det:
+                np.testing.assert_allclose(got[2:4], mean.cpu().numpy().reshape(-1), atol=2e-6, rtol=2e-6)
+                assert got[4] == 0.0
+            else:
+                # the same noise as the batched sampling path with the same (seed, row, draw)
+                want = ac.act(torch.cat([states[i], states[i]]), out=None)   # B = 2 -> tensor-core path, draw + 1
+                z = got[2:4]
+                n_multi = (z - mean.cpu().numpy().reshape(-1)) / std.cpu().numpy()
+                n_batch = ((want["pre_tanh"][0] - mean.view(-1)) / std).cpu().numpy()
+                assert np.all(np.isfinite(n_multi)) and np.abs(n_multi).max() < 6 and np.abs(n_batch).max() < 6
+                logp, _, _ = ac.evaluate(states[i], None, torch.from_numpy(z).to("cuda:0").view(1, 2))
+                np.testing.assert_allclose(got[4], logp.cpu().numpy().reshape(()), atol=3e-5, rtol=1e-5)
+            np.testing.assert_allclose(got[0:2], np.tanh(got[2:4]), atol=1e-6)
+    # ActorCritic.act with one state == the item path, bit for bit
+    torch.manual_seed(31)
+    a = _agent(60, 2, 256, 8)
+    torch.manual_seed(31)
+    b = _agent(60, 2, 256, 8)
+    x = torch.randn(1, 60, device="cuda:0")
+    o1 = a.act(x)
+    row = torch.zeros(6, device="cuda:0")
+    it = b.actor_critic.act_item(x, row, False)
+    assert lib.hrp_ppo_act_multi(C.byref(it), 1, torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(o1["action"].view(-1), row[0:2]) and torch.equal(o1["pre_tanh"].view(-1), row[2:4])
+    assert torch.equal(o1["log_prob"].view(-1), row[4:5]) and torch.equal(o1["value"].view(-1), row[5:6])
