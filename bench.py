@@ -525,7 +525,8 @@ def run_ours(args):
 
         T = args.rollout
         o = env.reset(42)
-        _, o = rollout_and_update(env, agent, T, obs=o)  # warm-up
+        for _ in range(2):   # warm-up: the first rollout runs launch by launch, the second one captures the rollout graph
+            _, o = rollout_and_update(env, agent, T, obs=o)
         barrier()
         iters = 2
         evp = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(iters)]

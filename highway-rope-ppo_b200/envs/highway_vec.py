@@ -205,11 +205,15 @@ class HighwayVecEnv:
         return obs
 
     def step(self, actions: torch.Tensor, perm: Optional[torch.Tensor] = None,
-             row_vehicle: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+             row_vehicle: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+             reward_out: Optional[torch.Tensor] = None, terminated_out: Optional[torch.Tensor] = None,
+             truncated_out: Optional[torch.Tensor] = None):
         """One policy step of every env.  ``actions``: float32 [E, 2] on the device.
 
         Returns (obs [E,N,F_out], reward [E], terminated [E] uint8, truncated [E] uint8); the
-        tensors are the handle's own output buffers unless ``out`` is given for the observation.
+        tensors are the handle's own output buffers unless ``out`` (observation) / ``reward_out`` /
+        ``terminated_out`` / ``truncated_out`` name the caller's (contiguous, e.g. the slot of a rollout buffer: the
+        kernel then writes the rollout directly, no copy kernels between the step and the next policy forward).
         """
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
@@ -220,11 +224,14 @@ class HighwayVecEnv:
             perm = perm.to(device=self.device, dtype=torch.int32).contiguous()
             if perm.numel() != self.num_envs * (self.N - 1):
                 raise ValueError("perm must be [E, N-1]")
-        _lib.check(self._lib.hrp_env_step(self._h, actions.data_ptr(), obs.data_ptr(), self.reward.data_ptr(),
-                                          self.terminated.data_ptr(), self.truncated.data_ptr(), _lib.ptr(perm),
+        rew = self.reward if reward_out is None else reward_out
+        term = self.terminated if terminated_out is None else terminated_out
+        trunc = self.truncated if truncated_out is None else truncated_out
+        _lib.check(self._lib.hrp_env_step(self._h, actions.data_ptr(), obs.data_ptr(), rew.data_ptr(),
+                                          term.data_ptr(), trunc.data_ptr(), _lib.ptr(perm),
                                           _lib.ptr(row_vehicle), self._stream()), "hrp_env_step")
         self.launches += 1
-        return obs, self.reward, self.terminated, self.truncated
+        return obs, rew, term, trunc
 
     def observe(self, perm: Optional[torch.Tensor] = None, row_vehicle: Optional[torch.Tensor] = None,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -210,12 +210,15 @@ class ActorCritic:
     # -- batched get_action: everything stays on the device -------------------------------------
     def act(self, states: torch.Tensor, noise: Optional[torch.Tensor] = None, deterministic: bool = False,
             out: Optional[Dict[str, torch.Tensor]] = None, lane: int = 0,
-            stream: Optional[int] = None, draw_counter: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+            stream: Optional[int] = None, draw_counter: Optional[torch.Tensor] = None,
+            reuse_weight_copies: bool = False) -> Dict[str, torch.Tensor]:
         """``get_action`` for [B, S] states -> dict(action, pre_tanh [B, A]; log_prob, value [B]).  ``stream``: raw
         ``cudaStream_t`` to enqueue on instead of torch's current stream (the multiplexer's stream ring).
         ``draw_counter``: int64 CUDA tensor [2] = (draw, 0) that replaces the host-side draw counter of the sampling
         path, so that the call can be captured in a CUDA graph and replayed (``new_draw_counter``); such a capture
-        always contains the weight preparation, i.e. a replay sees the current parameters.
+        always contains the weight preparation, i.e. a replay sees the current parameters -- unless
+        ``reuse_weight_copies`` says that an earlier call of the SAME capture already prepared them (the second and
+        later steps of a captured rollout).
 
         ``lane`` > 0 selects a separate native workspace (same parameters) so that calls on different CUDA streams
         may overlap: the two env groups of the pipelined host-buffer loop (bench.py e2e) act concurrently."""
@@ -233,7 +236,7 @@ class ActorCritic:
                    "log_prob": torch.empty(B, dtype=torch.float32, device=self.device),
                    "value": torch.empty(B, dtype=torch.float32, device=self.device)}
         if draw_counter is not None:
-            self._lib.hrp_ppo_hold_weights(self._h, 0)
+            self._lib.hrp_ppo_hold_weights(self._h, 1 if reuse_weight_copies else 0)
             self._held_key = None
         else:
             self._sync_weight_copies()
@@ -408,7 +411,10 @@ class PPOMemory:
                  "log_prob": torch.empty((T, E), dtype=torch.float32, device=d),
                  "value": torch.empty((T, E), dtype=torch.float32, device=d),
                  "reward": torch.empty((T, E), dtype=torch.float32, device=d),
-                 "done": torch.empty((T, E), dtype=torch.uint8, device=d)}
+                 "done": torch.empty((T, E), dtype=torch.uint8, device=d),
+                 # what the step kernel writes; `done` = terminated | truncated, formed once per rollout
+                 "terminated": torch.empty((T, E), dtype=torch.uint8, device=d),
+                 "truncated": torch.empty((T, E), dtype=torch.uint8, device=d)}
         self.rollout = r
         return r
 
@@ -559,10 +565,10 @@ class PPOAgent:
 
     def act(self, states: torch.Tensor, deterministic: bool = False, noise: Optional[torch.Tensor] = None,
             out: Optional[Dict[str, torch.Tensor]] = None, lane: int = 0, stream: Optional[int] = None,
-            draw_counter: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+            draw_counter: Optional[torch.Tensor] = None, reuse_weight_copies: bool = False) -> Dict[str, torch.Tensor]:
         self.launches += 1
         return self.actor_critic.act(states, noise=noise, deterministic=deterministic, out=out, lane=lane, stream=stream,
-                                     draw_counter=draw_counter)
+                                     draw_counter=draw_counter, reuse_weight_copies=reuse_weight_copies)
 
     # -- distributed helpers (ppo/distributed.py) ---------------------------------------------------
     @staticmethod

@@ -194,31 +194,80 @@ def training_coroutine(memory, max_episodes: int = 500, target_reward: float = 0
 # --------------------------------------------------------------------------------------------
 # batched loops
 def collect_rollout(vec_env, agent, T: int, obs: Optional[torch.Tensor] = None,
-                    noise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                    noise: Optional[torch.Tensor] = None, use_graph: Optional[bool] = None) -> Dict[str, torch.Tensor]:
     """T lock-step policy steps of every env into ``agent.memory``'s device rollout.
 
-    The env kernel writes each observation straight into the rollout's next state slot and the
-    policy kernel writes action / log-prob / value straight into their [t] slots: no staging
-    copies.  Finished envs are respawned inside the step kernel (``autoreset``), so slot t+1 holds
-    the first observation of the new episode and ``done[t]`` masks the bootstrap, exactly like
-    the reference's reset-after-done loop (``routine.py:125-147``).
+    The env kernel writes each observation straight into the rollout's next state slot, reward and flags into their
+    [t] slots, and the policy kernel writes action / log-prob / value straight into theirs: no staging copies, five
+    kernels of this library per step.  Finished envs are respawned inside the step kernel (``autoreset``), so slot
+    t+1 holds the first observation of the new episode and ``done[t]`` masks the bootstrap, exactly like the
+    reference's reset-after-done loop (``routine.py:125-147``).
+
+    With in-kernel sampling (``noise is None``) the whole rollout -- 5 T launches -- is captured ONCE as a CUDA graph
+    (the sampling kernel's draw counter lives on the device) and replayed by later calls with the same env, agent and
+    shape: the host-side cost of a rollout is one graph launch.  ``use_graph=False`` issues the launches one by one.
     """
     E, S, A = vec_env.num_envs, vec_env.N * vec_env.F_out, agent.actor_critic.action_dim
+    ac = agent.actor_critic
     # exploration noise is keyed by the GLOBAL env id: a shard's rows start at its first global env
-    agent.actor_critic.row_base = int(getattr(vec_env, "env_id_base", 0))
+    ac.row_base = int(getattr(vec_env, "env_id_base", 0))
+    if use_graph is None:
+        use_graph = noise is None and getattr(agent, "use_cuda_graphs", True)
+    cache = getattr(agent, "_rollout_graph", None)
+    key = (id(vec_env), T, E, S, A, ac.workspace_generation, ac.row_base)
+    if use_graph and cache is not None and cache["key"] == key and agent.memory.rollout is None:
+        agent.memory.rollout = cache["r"]     # the buffers the captured launches write (PPOAgent.update dropped them)
     r = agent.memory.begin_rollout(T, E, S, A)
     states = r["states"]
     if obs is None:
         vec_env.observe(out=states[0].view(E, vec_env.N, vec_env.F_out))
     else:
         states[0].copy_(obs.reshape(E, S))
-    for t in range(T):
-        out = {"action": r["action"][t], "pre_tanh": r["pre_tanh"][t], "log_prob": r["log_prob"][t],
-               "value": r["value"][t]}
-        agent.act(states[t], noise=None if noise is None else noise[t], out=out)
-        _, rew, term, trunc = vec_env.step(r["action"][t], out=states[t + 1].view(E, vec_env.N, vec_env.F_out))
-        r["reward"][t].copy_(rew)
-        torch.bitwise_or(term, trunc, out=r["done"][t])
+
+    def steps(counter=None):
+        for t in range(T):
+            out = {"action": r["action"][t], "pre_tanh": r["pre_tanh"][t], "log_prob": r["log_prob"][t],
+                   "value": r["value"][t]}
+            if counter is None:
+                agent.act(states[t], noise=None if noise is None else noise[t], out=out)
+            else:
+                agent.act(states[t], out=out, draw_counter=counter, reuse_weight_copies=t > 0)
+            vec_env.step(r["action"][t], out=states[t + 1].view(E, vec_env.N, vec_env.F_out), reward_out=r["reward"][t],
+                         terminated_out=r["terminated"][t], truncated_out=r["truncated"][t])
+        torch.bitwise_or(r["terminated"], r["truncated"], out=r["done"])
+
+    if not use_graph or noise is not None:
+        steps()
+        return r
+    if cache is None or cache["key"] != key or cache["r"] is not r:
+        if cache is None or cache["key"] != key:
+            steps()                     # the first rollout of a shape runs eagerly (warms every kernel variant) ...
+            agent._rollout_graph = {"key": key, "r": r, "graph": None, "counter": ac.new_draw_counter(),
+                                    "expected": ac._draw}
+            return r
+        cache["r"], cache["graph"] = r, None
+    cache = agent._rollout_graph
+    if cache["expected"] != ac._draw:   # other act() calls advanced the host-side draw counter since the last replay
+        cache["counter"].copy_(torch.tensor([ac._draw, 0], dtype=torch.int64))
+    if cache["graph"] is None:          # ... the second one is captured
+        graph = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream(agent.device)
+        side = torch.cuda.Stream(agent.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            graph.capture_begin()
+            try:
+                steps(cache["counter"])
+            finally:
+                graph.capture_end()
+        cur.wait_stream(side)
+        cache["graph"] = graph
+    cache["graph"].replay()
+    ac._draw += T
+    cache["expected"] = ac._draw
+    ac._held_key = None
+    agent.launches += T
+    vec_env.launches += T
     return r
 
 

@@ -291,3 +291,36 @@ def test_host_buffer_pipeline_equals_the_device_loop(highway_config, groups, gra
             assert np.array_equal(b["obs"], o[sl]) and np.array_equal(b["reward"], r[sl]), (t, g)
             assert np.array_equal(b["terminated"], te[sl]) and np.array_equal(b["truncated"], tr[sl]), (t, g)
     pipe.close()
+
+
+def test_graph_captured_rollout_equals_the_eager_rollout(highway_config):
+    """collect_rollout: the whole T-step rollout replayed as one CUDA graph (device-resident draw counter) fills the
+    rollout buffers with exactly what the launch-by-launch loop writes, rollout after rollout, with updates between."""
+    from highway_rope_ppo_b200.experiments.config import Condition
+    from highway_rope_ppo_b200.experiments.wrappers import make_vec_env
+    from highway_rope_ppo_b200.ppo.agent import PPOAgent
+    from highway_rope_ppo_b200.training.routine import collect_rollout
+
+    E, T = 128, 6
+    over = {"observation": {"order": "shuffled"}}
+    runs = []
+    for use_graph in (False, True):
+        torch.manual_seed(4)
+        np.random.seed(4)
+        env = make_vec_env(Condition.SHUFFLED_ROPE, highway_config, 4, over, num_envs=E, seed=7)
+        agent = PPOAgent(60, 2, hidden_dim=64, batch_size=256, epochs=1)
+        obs = env.reset(7).clone()
+        got = []
+        for it in range(4):
+            r = collect_rollout(env, agent, T, obs, use_graph=use_graph)
+            got.append({k: v.clone() for k, v in r.items()})
+            obs = r["states"][T].clone()
+            if it == 1:
+                agent.act(obs.view(E, -1))   # an unrelated act() in between advances the draw counter
+            _, _, v = agent.actor_critic.forward(obs.view(E, -1))
+            agent.update(last_value=v.view(-1))
+        runs.append(got)
+        env.close()
+    for a, b in zip(*runs):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
