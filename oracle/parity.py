@@ -27,6 +27,12 @@ DISCRETE = ("lane", "target_lane", "crashed", "has_impact")
 SLOW_FACTOR = 1e3
 NEAR_SLOW_FACTOR = 1e3
 NEAR_SLOW_M = 60.0
+# A vehicle that REVERSES is laterally unstable under highway-env's own steering law: its deviation from the lane centre
+# and its heading grow by a factor 5 to 8 per simulation frame, in the oracle exactly as in the kernel, and a rounding
+# difference between the two grows at the same rate (profiles/r02_reversing_vehicle_trace.txt: fp64 kernel against fp64
+# oracle, 2e-16 m after frame 0, 6e-4 m after frame 14, while the oracle's own y goes from 2e-8 m to 5e-2 m).  Its error
+# is therefore bounded RELATIVE to the deviation the oracle itself reports at the end of the step, not absolutely.
+SLOW_REL = 0.05
 
 
 class Got:
@@ -60,8 +66,11 @@ def compare(got, o, r, te, tr, want_obs, want_rows, tol, obs_tol, rew_tol, worst
         near = np.abs(ref["x"][:, None] - ref["x"][None, slow]).min(axis=1) < NEAR_SLOW_M
         scale = np.where(slow, SLOW_FACTOR, np.where(near, NEAR_SLOW_FACTOR, 1.0))
     errs = {}
+    rel = {}
+    if slow.any():
+        rel = {"y": SLOW_REL * np.abs(ref["y"] - 4.0 * ref["lane"]) * slow, "heading": SLOW_REL * np.abs(ref["heading"]) * slow}
     for k, t in tol.items():
-        err = np.abs(got.state[k] - ref[k]) / scale
+        err = np.maximum(np.abs(got.state[k] - ref[k]) - rel.get(k, 0.0), 0.0) / scale
         errs[k] = float(err.max())
         over = np.nonzero(err > t)[0]
         if len(over):
