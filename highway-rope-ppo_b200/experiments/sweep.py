@@ -3,8 +3,9 @@
 
 The experiment grid, the run-name format (parsed by the reference's ``analysis.py`` / ``results.py``) and the
 selection rules (``--array-task-id`` batches, ``--run-single-experiment`` exact-then-prefix match) are the
-reference's.  What replaces ``joblib`` + ``DevicePool`` time-sharing is a static shard: rank r of W runs experiments
-r, r + W, r + 2W, ... of the selected list on its own GPU, one after the other.
+reference's.  What replaces ``joblib`` + ``DevicePool`` time-sharing is a static shard -- rank r of W runs experiments
+r, r + W, r + 2W, ... of the selected list on its own GPU -- and, within a GPU, ``experiments/multiplex.py``: R runs
+at a time on shared env handles instead of ``OVERSUB`` processes time-sharing the device.
 """
 from __future__ import annotations
 
@@ -68,7 +69,15 @@ def shard_for_rank(experiments: List[Experiment], rank: int, world: int) -> List
 
 
 def run_experiments(experiments: Iterable[Experiment], base_env_config: dict, artifacts_dir: Optional[str] = None,
-                    runner: Optional[ExperimentRunner] = None) -> List[Dict[str, Any]]:
+                    runner: Optional[ExperimentRunner] = None, multiplex: int = 0) -> List[Dict[str, Any]]:
+    """Run the experiments on this process's GPU: one after the other, or -- ``multiplex`` = R > 1 -- R at a time on
+    shared env handles (``experiments/multiplex.py``; bit-identical results, several times the runs per hour).  A
+    sweep over W GPUs is ``run_experiments(shard_for_rank(selected, rank, W), ..., multiplex=R)`` in each rank."""
+    if multiplex and multiplex > 1 and runner is None:
+        from .multiplex import MultiplexedRunner
+
+        return MultiplexedRunner(base_env_config, artifacts_dir=artifacts_dir, max_concurrent=multiplex).launch_many(
+            list(experiments))
     runner = runner or ExperimentRunner(base_env_config, artifacts_dir=artifacts_dir)
     return [runner.launch(exp) for exp in experiments]
 
