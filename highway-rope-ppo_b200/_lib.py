@@ -85,6 +85,7 @@ SIGNATURES: Dict[str, Any] = {
     "hrp_env_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "hrp_env_reset_host": (C.c_int, [_vp, _u64, _vp]),
     "hrp_env_step_host_on": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hrp_fetch_host": (C.c_int, [_vp, _vp, _u64, _vp]),
     "hrp_env_set_seeds": (C.c_int, [_vp, _vp]),
     "hrp_env_set_step_mask": (C.c_int, [_vp, _vp]),
     "hrp_env_set_trace": (C.c_int, [_vp, _vp]),

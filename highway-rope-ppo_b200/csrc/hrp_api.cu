@@ -71,6 +71,22 @@ static int push_real(void *dst_dev, const std::vector<double> &src, bool real64)
     return push((float *)dst_dev, t);
 }
 
+// Host-to-device copy of a page-locked buffer done by SMs instead of the copy engine: the kernel reads the mapped host
+// memory (cache-volatile 16-byte loads, every one of them in flight at once) and stores to device memory.  Same PCIe
+// time as cudaMemcpyAsync, but it is a KERNEL in the stream: the policy's first GEMM follows it with programmatic
+// dependent launch after ~1 us, where a copy-engine transfer costs ~14 us before a dependent kernel starts
+// (profiles/r02_timeline_pipeline_g1.txt).
+__global__ void __launch_bounds__(256) fetch_host_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16,
+                                                         const unsigned char *__restrict__ src8, unsigned char *__restrict__ dst8,
+                                                         size_t tail)
+{
+    hrp_pdl_release();
+    hrp_pdl_wait();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = __ldcv(src + i);
+    if (blockIdx.x == 0 && threadIdx.x < tail) dst8[threadIdx.x] = *((const volatile unsigned char *)src8 + threadIdx.x);
+}
+
 extern "C" {
 
 const char *hrp_last_error(void) { return g_err; }
@@ -550,6 +566,25 @@ int hrp_embed_apply(int32_t kind, int32_t embed_dim, int32_t use_euclidean, int3
     if (batch == 0) return 0;
     return hrp_launch_embed(kind, embed_dim, use_euclidean, ego_idx, max_dist, table_dev, obs_dev, out_dev, batch,
                             rows, cols, dist_override_dev, (cudaStream_t)stream);
+}
+
+int hrp_fetch_host(void *dst_dev, const void *src_host, uint64_t bytes, void *stream)
+{
+    if (!dst_dev || !src_host) { hrp_set_error("hrp_fetch_host: null argument"); return -1; }
+    if (bytes == 0) return 0;
+    if (((uintptr_t)dst_dev | (uintptr_t)src_host) & 15) { hrp_set_error("hrp_fetch_host: both pointers must be 16-byte aligned"); return -1; }
+    void *src_dev = nullptr;
+    if (cudaHostGetDevicePointer(&src_dev, const_cast<void *>(src_host), 0) != cudaSuccess) {
+        cudaGetLastError();
+        hrp_set_error("hrp_fetch_host: src_host is not page-locked, mapped host memory");
+        return -1;
+    }
+    const size_t n16 = bytes / 16, tail = bytes % 16;
+    const unsigned grid = (unsigned)((n16 + 255) / 256 < 1 ? 1 : ((n16 + 255) / 256 > 1184 ? 1184 : (n16 + 255) / 256));
+    HRP_CUDA_OK(hrp_launch_pdl(fetch_host_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const uint4 *)src_dev,
+                               (uint4 *)dst_dev, n16, (const unsigned char *)src_dev + 16 * n16,
+                               (unsigned char *)dst_dev + 16 * n16, tail));
+    return 0;
 }
 
 }  // extern "C"

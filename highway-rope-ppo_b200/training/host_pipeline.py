@@ -18,6 +18,8 @@ from typing import Any, Dict, List
 import numpy as np
 import torch
 
+from .. import _lib
+
 
 class HostBufferPipeline:
     """``groups``: HighwayVecEnv handles (their env counts may differ).  After ``reset(seed)``, ``launch(g)`` enqueues
@@ -25,8 +27,9 @@ class HostBufferPipeline:
     pinned tensors: ``obs`` [E_g, N, F_out] -- both the policy's input and the step's output --, ``action`` [E_g, 2],
     ``reward``, ``terminated``, ``truncated`` [E_g])."""
 
-    def __init__(self, agent, groups: List[Any], use_graphs: bool = True):
+    def __init__(self, agent, groups: List[Any], use_graphs: bool = True, kernel_fetch: bool = True):
         self.agent, self.envs, self.use_graphs = agent, list(groups), bool(use_graphs)
+        self.kernel_fetch, self._lib = bool(kernel_fetch), _lib.load()
         dev = agent.device
         self.groups: List[Dict[str, Any]] = []
         self.buffers: List[Dict[str, np.ndarray]] = []
@@ -45,7 +48,7 @@ class HostBufferPipeline:
             self.groups.append(g)
             self.buffers.append({"obs": g["obs_h"].numpy(), "action": g["act_h"].numpy(), "reward": g["rew_h"].numpy(),
                                  "terminated": g["te_h"].numpy(), "truncated": g["tr_h"].numpy()})
-        self.launches = 0   # kernels of this library enqueued (5 per group-step: 3 GEMMs, heads, env step)
+        self.launches = 0   # kernels of this library enqueued (per group-step: [fetch,] 3 GEMMs, heads, env step)
 
     def reset(self, seed: int) -> None:
         for g, b in zip(self.groups, self.buffers):
@@ -56,7 +59,11 @@ class HostBufferPipeline:
         env, ac = g["env"], self.agent.actor_critic
         Eg, S = env.num_envs, env.N * env.F_out
         cur = torch.cuda.current_stream(self.agent.device)
-        g["obs_d"].copy_(g["obs_h"].view(Eg, S), non_blocking=True)              # H2D observation
+        if self.kernel_fetch:    # H2D observation by a kernel (hrp_fetch_host): the first GEMM follows it within ~1 us
+            _lib.check(self._lib.hrp_fetch_host(g["obs_d"].data_ptr(), g["obs_h"].data_ptr(), Eg * S * 4, cur.cuda_stream),
+                       "hrp_fetch_host")
+        else:                    # ... or by the copy engine
+            g["obs_d"].copy_(g["obs_h"].view(Eg, S), non_blocking=True)
         ac.row_base = g["row_base"]
         self.agent.act(g["obs_d"], out=g["out"], lane=g["lane"], draw_counter=g["draw"])
         acted = torch.cuda.Event()
@@ -87,12 +94,12 @@ class HostBufferPipeline:
                     g["graph"] = graph
                     g["done"].record(g["stream"])
                     g["pending"] = True
-                    self.launches += 5
+                    self.launches += 5 + int(self.kernel_fetch)
                     return
                 g["graph"].replay()
             g["done"].record(g["stream"])
         g["pending"] = True
-        self.launches += 5
+        self.launches += 5 + int(self.kernel_fetch)
 
     def wait(self, gi: int) -> Dict[str, np.ndarray]:
         g = self.groups[gi]

@@ -144,6 +144,12 @@ int hrp_env_reset_host(hrp_env *env, uint64_t seed, float *obs_host);
 int hrp_env_step_host_on(hrp_env *env, const float *actions, float *obs_host, float *reward_host,
                          uint8_t *terminated_host, uint8_t *truncated_host, void *stream);
 
+/* Host-to-device copy of a page-locked (mapped) host buffer by a kernel instead of the copy engine -- the first link of
+ * the host-buffer policy step (the observation the reference loop holds on the host, training/routine.py:133-135): a
+ * dependent kernel (the policy's first GEMM) starts ~1 us after it, not ~14 us as after a cudaMemcpyAsync.  Both
+ * pointers 16-byte aligned. */
+int hrp_fetch_host(void *dst_dev, const void *src_host, uint64_t bytes, void *stream);
+
 /* Multiplexed independent experiments (the replacement of utils/device_pool.py:45-72 + main.py:234-242: many single-env
  * runs of the sweep share ONE handle instead of time-sharing the GPU as processes).  While seeds_dev[E] (device, owned by
  * the caller, read at every reset / shuffle draw) is non-NULL, env e draws its spawn and shuffle randoms from
