@@ -81,23 +81,25 @@ class HostBufferPipeline:
         g = self.groups[gi]
         if g["pending"]:
             self.wait(gi)
-        with torch.cuda.stream(g["stream"]):
+        # torch.cuda.set_stream, not the `with torch.cuda.stream(...)` context: entering and leaving the context each
+        # cost a cudaGetDeviceCount (~15 us) -- host time during which the GPU of a one-group pipeline has nothing to do
+        home = torch.cuda.current_stream(self.agent.device)
+        torch.cuda.set_stream(g["stream"])
+        try:
             if not self.use_graphs:
                 self._enqueue(g)
+            elif g["graph"] is None:
+                self._enqueue(g)          # eager first: warms every kernel variant and the workspace lane
+                g["stream"].synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=g["stream"]):
+                    self._enqueue(g)
+                g["graph"] = graph
             else:
-                if g["graph"] is None:
-                    self._enqueue(g)          # eager first: warms every kernel variant and the workspace lane
-                    g["stream"].synchronize()
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph, stream=g["stream"]):
-                        self._enqueue(g)
-                    g["graph"] = graph
-                    g["done"].record(g["stream"])
-                    g["pending"] = True
-                    self.launches += 5 + int(self.kernel_fetch)
-                    return
                 g["graph"].replay()
             g["done"].record(g["stream"])
+        finally:
+            torch.cuda.set_stream(home)
         g["pending"] = True
         self.launches += 5 + int(self.kernel_fetch)
 
