@@ -333,16 +333,19 @@ heads_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const f
 // z_a = mean_a + std_a * n_a with n ~ N(0,1) from Philox4x32-10(counter = (global row, draw), key = seed) through
 // Box-Muller (or takes n from noise[], or n = 0 when deterministic) and writes tanh(z_a), z_a; the log-prob terms of
 // the A lanes are added by shuffles.
+constexpr int HA_ROWS = 2;   // rows per warp of heads_act_kernel (their loads are in flight together)
 __global__ void __launch_bounds__(256)
 heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, const float *__restrict__ wa2,
                  const float *__restrict__ ba2, const float *__restrict__ wc2, const float *__restrict__ bc2,
                  const float *__restrict__ log_std, const float *__restrict__ noise, int mode /*0 det, 1 noise[], 2 philox*/,
                  unsigned long long seed, unsigned long long draw, unsigned long long row_base, int ld, long long B,
                  int H, int A, float *__restrict__ action, float *__restrict__ pre_tanh,
-                 float *__restrict__ log_prob, float *__restrict__ value, unsigned long long *draw_ctr)
+                 float *__restrict__ log_prob, float *__restrict__ value, unsigned long long *draw_ctr, int vec)
 {
+    extern __shared__ __align__(16) float hw[];   // the head weights, [A + 1][H]: read once per CTA, not once per row
     hrp_pdl_release();
     hrp_pdl_wait();
+    for (int i = threadIdx.x; i < (A + 1) * H; i += 256) hw[i] = i < A * H ? wa2[i] : wc2[i - A * H];
     if (draw_ctr) {
         // device-resident draw counter (a captured launch cannot take a new `draw` argument per replay): every CTA
         // reads draw_ctr[0], then takes a ticket from draw_ctr[1]; the CTA that takes the last ticket -- by then every
@@ -358,23 +361,65 @@ heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, con
         }
         __syncthreads();
         draw = sdraw;
+    } else {
+        __syncthreads();
     }
-    long long b = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (b >= B) return;
-    const float *ra = a1 + (size_t)b * ld, *rc = c1 + (size_t)b * ld;
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = lane; k < H; k += 32) {
-        const float xa = ra[k], xc = rc[k];
+    const int lane = threadIdx.x & 31;
+    const long long b0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * HA_ROWS;
+    if (b0 >= B) return;
+    float accs[HA_ROWS][5];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-            if (a < A) acc[a] = fmaf(xa, wa2[(size_t)a * H + k], acc[a]);
-        acc[4] = fmaf(xc, wc2[k], acc[4]);
+    for (int r = 0; r < HA_ROWS; ++r)
+#pragma unroll
+        for (int a = 0; a < 5; ++a) accs[r][a] = 0.f;
+    if (vec) {   // H % 128 == 0, 16-byte aligned rows: lane owns 4 consecutive k per 128
+        for (int k = 4 * lane; k < H; k += 128) {
+            float4 xa[HA_ROWS], xc[HA_ROWS];
+#pragma unroll
+            for (int r = 0; r < HA_ROWS; ++r) {
+                const long long b = min(b0 + r, B - 1);
+                xa[r] = *reinterpret_cast<const float4 *>(a1 + (size_t)b * ld + k);
+                xc[r] = *reinterpret_cast<const float4 *>(c1 + (size_t)b * ld + k);
+            }
+            const float4 wc = *reinterpret_cast<const float4 *>(hw + A * H + k);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                if (a < A) {
+                    const float4 w = *reinterpret_cast<const float4 *>(hw + a * H + k);
+#pragma unroll
+                    for (int r = 0; r < HA_ROWS; ++r)
+                        accs[r][a] = fmaf(xa[r].w, w.w, fmaf(xa[r].z, w.z, fmaf(xa[r].y, w.y, fmaf(xa[r].x, w.x, accs[r][a]))));
+                }
+#pragma unroll
+            for (int r = 0; r < HA_ROWS; ++r)
+                accs[r][4] = fmaf(xc[r].w, wc.w, fmaf(xc[r].z, wc.z, fmaf(xc[r].y, wc.y, fmaf(xc[r].x, wc.x, accs[r][4]))));
+        }
+    } else {
+        for (int k = lane; k < H; k += 32) {
+#pragma unroll
+            for (int r = 0; r < HA_ROWS; ++r) {
+                const long long b = min(b0 + r, B - 1);
+                const float xa = a1[(size_t)b * ld + k], xc = c1[(size_t)b * ld + k];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    if (a < A) accs[r][a] = fmaf(xa, hw[a * H + k], accs[r][a]);
+                accs[r][4] = fmaf(xc, hw[A * H + k], accs[r][4]);
+            }
+        }
     }
 #pragma unroll
-    for (int a = 0; a < 5; ++a)
+    for (int r = 0; r < HA_ROWS; ++r)
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) acc[a] += __shfl_xor_sync(HRP_FULL, acc[a], d);
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) accs[r][a] += __shfl_xor_sync(HRP_FULL, accs[r][a], d);
+#pragma unroll 1
+    for (int r = 0; r < HA_ROWS; ++r) {
+    const long long b = b0 + r;
+    if (b >= B) break;
+    float acc[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) acc[a] = r == 0 ? accs[0][a] : accs[HA_ROWS - 1][a];
     // lane a owns action dimension a (lanes >= A compute on dimension 0 and discard)
     const int a = lane < A ? lane : 0;
     float mu = acc[0];
@@ -414,6 +459,7 @@ heads_act_kernel(const float *__restrict__ a1, const float *__restrict__ c1, con
     if (lane == 0) {
         if (log_prob) log_prob[b] = mode ? lp : 0.f;
         value[b] = acc[4] + bc2[0];
+    }
     }
 }
 
@@ -1016,10 +1062,13 @@ static int act_impl(hrp_ppo *h, const float *params, const float *states, const 
 {
     const Layout &L = h->L;
     if (int rc = forward_impl(h, params, states, batch, nullptr, nullptr, s)) return rc;
-    HRP_CUDA_OK(hrp_launch_pdl(heads_act_kernel, dim3((unsigned)((batch + 7) / 8)), dim3(256), 0, s, (const float *)h->ac,
-                               (const float *)(h->ac + L.H), params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2,
+    const float *pa = h->ac, *pc = h->ac + L.H;
+    const int vec = L.H % 128 == 0 && (((uintptr_t)pa | (uintptr_t)pc) & 15) == 0 ? 1 : 0;   // row pitch 2 H: a multiple of 4 with H
+    const size_t smem = (size_t)(L.A + 1) * L.H * sizeof(float);
+    HRP_CUDA_OK(hrp_launch_pdl(heads_act_kernel, dim3((unsigned)((batch + 8 * HA_ROWS - 1) / (8 * HA_ROWS))), dim3(256), smem, s,
+                               pa, pc, params + L.wa2, params + L.ba2, params + L.wc2, params + L.bc2,
                                params + L.log_std, noise, mode, seed, draw, row_base, 2 * L.H, (long long)batch, L.H, L.A,
-                               action, pre_tanh, log_prob, value, draw_ctr));
+                               action, pre_tanh, log_prob, value, draw_ctr, vec));
     return 0;
 }
 
