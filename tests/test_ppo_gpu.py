@@ -152,7 +152,13 @@ def test_full_update_matches_reference(name):
     assert abs(metrics["approx_kl"] - want["approx_kl"]) <= 2e-3 * max(1e-2, abs(want["approx_kl"]))
     p1 = agent.actor_critic.flat.cpu().numpy()
     moved = np.abs(g["params1"] - g["params0"]).max()
-    assert np.abs(p1 - g["params1"]).max() <= 0.05 * moved + 1e-5
+    err = np.abs(p1 - g["params1"]).max()
+    print(f"update {name}: max parameter motion {moved:.3e}, max error {err:.3e} = {err / moved:.2e} of it")
+    # measured on B200 (3xTF32 GEMMs): 8e-6 of the largest parameter motion after the 12 optimizer steps of the small
+    # fixture, 1.6e-2 after the 64 steps of the H = 256 one (Adam divides every gradient entry by its running RMS, so an
+    # entry whose gradient is at rounding level still moves by ~lr per step, in a direction rounding decides); bounds at
+    # about twice / ten times the measured figures
+    assert err <= {"s12_h16_n100": 1e-4, "s60_h256_n2048": 0.03}[name] * moved
     assert len(agent.memory) == 0
 
 
@@ -451,7 +457,7 @@ def test_full_update_at_hidden_512_matches_reference():
     moved = float(np.abs(g["motion_samples"]).max())
     err = float(np.abs(motion[::257] - g["motion_samples"]).max())
     print("H=512 update: max parameter motion", moved, "max error of the sampled entries", err)
-    assert err <= 0.02 * moved + 1e-6
+    assert err <= 5e-4 * moved   # measured 3.3e-5 of the motion after these 16 optimizer steps
 
 
 def test_tma_gemm_path_matches_the_reference_too(monkeypatch):
