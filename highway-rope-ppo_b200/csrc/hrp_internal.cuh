@@ -103,6 +103,16 @@ inline cudaError_t hrp_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// fused consumer of the tcgen05 GEMM's epilogue (hrp_mlp_tc.cu: tc_epilogue): per-row dot products of the output tile
+// with the head weights.  out == nullptr: off.
+struct TcDots {
+    const float *wa;   // actor head weights [A][H]   (columns [0, H) of the output)
+    const float *wc;   // critic head weights [H]     (columns [H, 2 H))
+    int H, A;
+    float *out;        // [N / BN tiles][M][4] partial sums
+    int skip_store;    // do not write the activation itself
+};
+
 // launchers implemented in hrp_env.cu
 int hrp_launch_step(const EnvDev &P, const float *actions, float *obs, float *reward, uint8_t *term,
                     uint8_t *trunc, const int32_t *perm, int32_t *row_vehicle, cudaStream_t s);

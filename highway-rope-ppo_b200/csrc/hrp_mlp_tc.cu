@@ -284,11 +284,17 @@ __host__ __device__ constexpr int tc_stages()
 }
 
 // ---- epilogue shared by both main loops: TMEM -> registers -> shared (row-major, padded) -> coalesced global rows
+// Optional fused consumer (TcDots, hrp_ppo.cu's act path): the output is [a1 | c1], the hidden activations of the two
+// heads, and all the policy needs of it are A + 1 dot products per row -- mean_a = a1 . Wa2[a], value = c1 . Wc2.  A tile
+// lies entirely in a1 or in c1 (H % BN == 0, checked by the host); every thread multiplies its four columns of a row
+// by the head weights it keeps in registers, the CQ threads of the row add up by shuffles, and the tile leaves four
+// partial sums per row in out[tile][row][4]; a tiny kernel adds the tiles (heads_finish_kernel).  With skip_store the
+// activation itself is never written.
 template <int BN, bool DUAL>
 __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *bar_done_p, uint32_t tmem_d, int nkb, int M, int N,
                                             int m0, int n0, int bn0, float *__restrict__ C, int ldc,
                                             const float *__restrict__ biasp, int relu, const float *__restrict__ mask,
-                                            int ldm, int accumulate, float *__restrict__ C_lo)
+                                            int ldm, int accumulate, float *__restrict__ C_lo, const TcDots &dots)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // ---- epilogue: TMEM -> registers -> shared (row-major, padded) -> coalesced global rows.
@@ -353,6 +359,16 @@ __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *bar_done_p,
         float *crow = Cz + (size_t)(m0 + tid / CQ) * ldc + gn;
         const float *mrow = mask ? mask + (size_t)(m0 + tid / CQ) * ldm + gn : nullptr;
         const float *srow = stage_c + (tid / CQ) * LDS + 4 * cq;
+        float4 hwv[4];
+        if (dots.out) {
+            const bool actor = n0 < dots.H;
+            const int nd = actor ? dots.A : 1;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float *w = actor ? dots.wa + (size_t)a * dots.H + gn : dots.wc + (gn - dots.H);
+                hwv[a] = a < nd ? make_float4(w[0], w[1], w[2], w[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
 #pragma unroll 1
         for (int rb = tid / CQ; rb < BM; rb += RSTEP * GROUP) {
             float4 prev[GROUP], mk[GROUP];
@@ -369,7 +385,18 @@ __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *bar_done_p,
                 if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                 x.x = mk[j].x > 0.f ? x.x : 0.f; x.y = mk[j].y > 0.f ? x.y : 0.f;
                 x.z = mk[j].z > 0.f ? x.z : 0.f; x.w = mk[j].w > 0.f ? x.w : 0.f;
-                if (m0 + rb + j * RSTEP < M) {
+                if (dots.out) {
+                    float d[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        d[a] = fmaf(x.w, hwv[a].w, fmaf(x.z, hwv[a].z, fmaf(x.y, hwv[a].y, x.x * hwv[a].x)));
+#pragma unroll
+                        for (int off = CQ / 2; off > 0; off >>= 1) d[a] += __shfl_xor_sync(0xffffffffu, d[a], off);
+                    }
+                    if (cq == 0 && m0 + rb + j * RSTEP < M)
+                        *(float4 *)(dots.out + ((size_t)blockIdx.x * M + (m0 + rb + j * RSTEP)) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+                }
+                if (m0 + rb + j * RSTEP < M && !dots.skip_store) {
                     *(float4 *)(crow + (size_t)j * RSTEP * ldc) = x;
                     if (Clz) {
                         float4 l;
@@ -424,7 +451,8 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS)
 tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, long long sak,
                const float *__restrict__ B, long long sbn, long long sbk, float *__restrict__ C, int ldc,
                const float *__restrict__ bias, int relu, const float *__restrict__ mask, int ldm, int accumulate,
-               int k_chunk, int nseg, const float *__restrict__ B2, const float *__restrict__ bias2, float *__restrict__ C_lo)
+               int k_chunk, int nseg, const float *__restrict__ B2, const float *__restrict__ bias2, float *__restrict__ C_lo,
+               const TcDots dots)
 {
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;                  // hi (+ lo) copy of every operand tile
     constexpr int B_TILE_BYTES = BN * BK * 4;
@@ -626,7 +654,7 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
         }
     }
 
-    tc_epilogue<BN, NSPLIT == 3>(smem, &bar_done, tmem_d, nkb, M, N, m0, n0, bn0, C, ldc, biasp, relu, mask, ldm, accumulate, C_lo);
+    tc_epilogue<BN, NSPLIT == 3>(smem, &bar_done, tmem_d, nkb, M, N, m0, n0, bn0, C, ldc, biasp, relu, mask, ldm, accumulate, C_lo, dots);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -645,7 +673,8 @@ tc_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long sam, 
 template <int AMODE, int BMODE, int NSPLIT, int BN, bool ASYNC = false>
 int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam, long long sak,
            const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias, int relu,
-           const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2, const float *bias2, float *C_lo)
+           const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2, const float *bias2, float *C_lo,
+           const TcDots &dots)
 {
     constexpr int PARTS = NSPLIT == 3 ? 2 : 1;
     constexpr int STAGES = tc_stages<NSPLIT, BN, ASYNC>();
@@ -663,7 +692,7 @@ int launch(dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long 
         configured[dev] = true;
     }
     HRP_CUDA_OK(hrp_launch_pdl(kern, grid, dim3(TC_LAUNCH_THREADS), (size_t)SMEM, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc,
-                               bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo));
+                               bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo, dots));
     return 0;
 }
 
@@ -671,9 +700,9 @@ template <int AMODE, int BMODE>
 int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
              long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
              int relu, const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2,
-             const float *bias2, float *C_lo)
+             const float *bias2, float *C_lo, const TcDots &dots)
 {
-#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo
+#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo, dots
     if (bn == 64) return nsplit == 3 ? launch<AMODE, BMODE, 3, 64>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 64>(HRP_TC_ARGS);
     return nsplit == 3 ? launch<AMODE, BMODE, 3, 128>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 128>(HRP_TC_ARGS);
 #undef HRP_TC_ARGS
@@ -683,9 +712,9 @@ int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K,
 int dispatch_async(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K, const float *A, long long sam,
                    long long sak, const float *B, long long sbn, long long sbk, float *C, int ldc, const float *bias,
                    int relu, const float *mask, int ldm, int accumulate, int k_chunk, int nseg, const float *B2,
-                   const float *bias2, float *C_lo)
+                   const float *bias2, float *C_lo, const TcDots &dots)
 {
-#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo
+#define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo, dots
     if (bn == 64)
         return nsplit == 3 ? launch<ST_K4, ST_K2, 3, 64, true>(HRP_TC_ARGS) : launch<ST_K4, ST_K2, 1, 64, true>(HRP_TC_ARGS);
     return nsplit == 3 ? launch<ST_K4, ST_K2, 3, 128, true>(HRP_TC_ARGS) : launch<ST_K4, ST_K2, 1, 128, true>(HRP_TC_ARGS);
@@ -696,13 +725,23 @@ inline bool aligned(const void *p, int bytes) { return ((uintptr_t)p % bytes) ==
 
 }  // namespace
 
+// the N-tile width hrp_tc_gemm picks (the fused row-dot epilogue's caller sizes its partial buffer with it)
+int hrp_tc_gemm_bn(int M, int N, int splits, int nseg)
+{
+    const int mt = (M + BM - 1) / BM;
+    int bn = (N <= 64 || mt * ((N + 127) / 128) * (splits > 1 ? splits : 1) < 120) ? 64 : 128;
+    if (nseg > 0 && nseg % 128 != 0) bn = 64;
+    return bn;
+}
+
 // Strided tcgen05 GEMM; returns the number of K splits actually used (partials at C + z*M*ldc), <0 on error.
 // nsplit: 3 = 3xTF32 (fp32-grade accuracy), 1 = single TF32 pass.
 int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
                 int accumulate, int splits, int nsplit, cudaStream_t s, int nseg, const float *B2, const float *bias2,
-                float *C_lo)
+                float *C_lo, const TcDots *dots_in)
 {
+    const TcDots dots = dots_in ? *dots_in : TcDots{nullptr, nullptr, 0, 0, nullptr, 0};
     int k_chunk = K;
     if (splits > 1) {
         k_chunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
@@ -718,16 +757,20 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
         if (nseg % 128 != 0) bn = 64;   // a tile must not straddle the two B matrices
     }
     dim3 grid((N + bn - 1) / bn, mt, splits);
+    if (dots.out && (splits != 1 || dots.H % bn != 0 || N % bn != 0 || ldc % 4 != 0 || !aligned(C, 16) || mask || C_lo)) {
+        hrp_set_error("hrp_tc_gemm: the fused row-dot epilogue needs whole, aligned tiles that do not straddle H");
+        return -1;
+    }
     const bool akc = sak == 1, bkc = sbk == 1;
     // vectorised staging where strides and base addresses allow it
     const bool a_k4 = akc && K % 4 == 0 && sam % 4 == 0 && aligned(A, 16);
     const bool b_k2 = bkc && K % 2 == 0 && sbn % 2 == 0 && aligned(B, 8) && (nseg == 0 || aligned(B2, 8));
     const bool b_k4 = bkc && K % 4 == 0 && sbn % 4 == 0 && aligned(B, 16) && (nseg == 0 || aligned(B2, 16));
-#define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo)
+#define HRP_TC_GO(am, bm) dispatch<am, bm>(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo, dots)
     int rc;
     // cp.async staging pays off for the single-pass mode only (measured: 3xTF32 hidden forward 12.6 us register-staged
     // vs 14.5 us cp.async -- the lo tiles need a second pass through shared memory; TF32 H=512 19.6 -> 16.6 us)
-    if (a_k4 && b_k2 && nsplit == 1) rc = dispatch_async(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo);
+    if (a_k4 && b_k2 && nsplit == 1) rc = dispatch_async(bn, nsplit, grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo, dots);
     else if (a_k4 && b_k4) rc = HRP_TC_GO(ST_K4, ST_K4);
     else if (a_k4 && b_k2) rc = HRP_TC_GO(ST_K4, ST_K2);
     else if (a_k4 && sbn == 1) rc = HRP_TC_GO(ST_K4, ST_MN1);

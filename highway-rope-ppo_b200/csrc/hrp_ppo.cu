@@ -803,7 +803,8 @@ struct hrp_ppo {
 int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
                 int accumulate, int splits, int nsplit, cudaStream_t s, int nseg = 0, const float *B2 = nullptr,
-                const float *bias2 = nullptr, float *C_lo = nullptr);
+                const float *bias2 = nullptr, float *C_lo = nullptr, const TcDots *dots = nullptr);
+int hrp_tc_gemm_bn(int M, int N, int splits, int nseg);
 
 // TMA-fed 3xTF32 path on pre-split operands (hrp_gemm_tma.cu)
 int hrp_tma_gemm(int M, int N, int K, const float *A, const float *A_lo, long long sam, long long sak, const float *B,
@@ -1055,12 +1056,99 @@ act_multi_kernel(const __grid_constant__ ActBatch batch)
     if (lane == 0) { it.out_dev[2 * A] = it.deterministic ? 0.f : lp; it.out_dev[2 * A + 1] = head[A]; }
 }
 
+// The act path with the heads fused into the last GEMM (TcDots): the [a1 | c1] GEMM left, per N tile and row, the
+// partial dot products with the head weights; a thread per row adds the tiles in tile order, adds the biases and
+// samples exactly as heads_act_kernel does (same Philox counters, same Box-Muller pairing, same log-prob arithmetic).
+__global__ void __launch_bounds__(128)
+heads_finish_kernel(const float *__restrict__ part, int tiles_a, int tiles, const float *__restrict__ ba2,
+                    const float *__restrict__ bc2, const float *__restrict__ log_std, const float *__restrict__ noise, int mode,
+                    unsigned long long seed, unsigned long long draw, unsigned long long row_base, long long B, int A,
+                    float *__restrict__ action, float *__restrict__ pre_tanh, float *__restrict__ log_prob,
+                    float *__restrict__ value, unsigned long long *draw_ctr)
+{
+    hrp_pdl_release();
+    hrp_pdl_wait();
+    if (draw_ctr) {   // device-resident draw counter, as in heads_act_kernel
+        __shared__ unsigned long long sdraw;
+        if (threadIdx.x == 0) {
+            sdraw = *(volatile unsigned long long *)draw_ctr + 1ull;
+            __threadfence();
+            if (atomicAdd(draw_ctr + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+                draw_ctr[1] = 0ull;
+                draw_ctr[0] = sdraw;
+            }
+        }
+        __syncthreads();
+        draw = sdraw;
+    }
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, val = 0.f;
+    for (int t = 0; t < tiles; ++t) {
+        const float4 p = *reinterpret_cast<const float4 *>(part + ((size_t)t * B + b) * 4);
+        if (t < tiles_a) { mu[0] += p.x; mu[1] += p.y; mu[2] += p.z; mu[3] += p.w; }
+        else val += p.x;
+    }
+    uint32_t r[4] = {0u, 0u, 0u, 0u};
+    if (mode == 2) {
+        const unsigned long long gb = row_base + (unsigned long long)b;
+        hrp_philox((uint32_t)gb, (uint32_t)(gb >> 32), (uint32_t)draw, (uint32_t)(draw >> 32),
+                   (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5A5A5A5Au, r);
+    }
+    float lp = 0.f;
+    for (int a = 0; a < A; ++a) {
+        const float m = mu[a] + ba2[a];
+        float nrm = 0.f;
+        if (mode == 2) {
+            const uint32_t r1 = a < 2 ? r[0] : r[2], r2 = a < 2 ? r[1] : r[3];
+            float u1 = ((float)(r1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            float u2 = ((float)(r2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            float rad = sqrtf(-2.f * logf(u1)), sn, cs;
+            sincospif(2.f * u2, &sn, &cs);
+            nrm = rad * ((a & 1) ? sn : cs);
+        } else if (mode == 1) {
+            nrm = noise[b * A + a];
+        }
+        const float ls = log_std[a], sd = expf(ls);
+        const float z = mode ? m + sd * nrm : m;
+        const float t = tanhf(z);
+        const float d = z - m;
+        float l = -(d * d) / (2.f * sd * sd) - ls - 0.91893853320467274f;
+        l -= log1pf(-(t * t) + 1e-6f);
+        lp += l;
+        pre_tanh[b * A + a] = z;
+        action[b * A + a] = t;
+    }
+    if (log_prob) log_prob[b] = mode ? lp : 0.f;
+    value[b] = val + bc2[0];
+}
+
 static int act_impl(hrp_ppo *h, const float *params, const float *states, const float *noise, int mode,
                     unsigned long long seed, unsigned long long draw, unsigned long long row_base, long long batch,
                     float *action, float *pre_tanh, float *log_prob, float *value, cudaStream_t s,
                     unsigned long long *draw_ctr = nullptr)
 {
     const Layout &L = h->L;
+    {
+        // heads fused into the [a1 | c1] GEMM's epilogue whenever its tiles do not straddle H (HRP_FUSE_HEADS=0: off)
+        static const bool fuse_on = !(getenv("HRP_FUSE_HEADS") && getenv("HRP_FUSE_HEADS")[0] == '0');
+        const int H = L.H, Bi = (int)batch;
+        const int bn = hrp_tc_gemm_bn(Bi, 2 * H, 1, H);
+        if (fuse_on && g_math_mode != 0 && !(use_tma(h) && Bi >= 32) && H % 64 == 0 && Bi >= 32 && H % bn == 0) {
+            if (gemm(false, true, Bi, H, L.S, states, L.S, params + L.w1, L.S, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+            if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+            // partial sums in the (idle) backward scratch d12: [2 H / bn tiles][B][4] <= [B][2 H] floats
+            const TcDots dots{params + L.wa2, params + L.wc2, H, L.A, h->d12, 1};
+            if (hrp_tc_gemm(Bi, 2 * H, H, h->h2, H, 1, params + L.wa1, H, 1, h->ac, 2 * H, params + L.ba1, 1, nullptr, 0, 0, 1,
+                            g_math_mode == 1 ? 1 : 3, s, H, params + L.wc1, params + L.bc1, nullptr, &dots) < 0)
+                return -2;
+            HRP_CUDA_OK(hrp_launch_pdl(heads_finish_kernel, dim3((unsigned)((batch + 127) / 128)), dim3(128), 0, s,
+                                       (const float *)h->d12, H / bn, 2 * H / bn, params + L.ba2, params + L.bc2,
+                                       params + L.log_std, noise, mode, seed, draw, row_base, (long long)batch, L.A, action,
+                                       pre_tanh, log_prob, value, draw_ctr));
+            return 0;
+        }
+    }
     if (int rc = forward_impl(h, params, states, batch, nullptr, nullptr, s)) return rc;
     const float *pa = h->ac, *pc = h->ac + L.H;
     const int vec = L.H % 128 == 0 && (((uintptr_t)pa | (uintptr_t)pc) & 15) == 0 ? 1 : 0;   // row pitch 2 H: a multiple of 4 with H
