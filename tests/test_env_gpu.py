@@ -633,3 +633,63 @@ def test_async_host_step_in_two_groups_equals_one_env(highway_config):
     whole.close()
     for g in groups:
         g.close()
+
+
+def test_per_env_seeds_and_step_mask_reproduce_single_env_handles(highway_config):
+    """hrp_env_set_seeds / hrp_env_set_step_mask (the multiplexed sweep, experiments/multiplex.py): env e of a shared
+    handle, seeded with seeds[e] and stepped only when mask[e], is bit for bit the single-env handle of a run that
+    called reset(seed=seeds[e]) -- state, observation, reward, flags and the shuffle draws -- while its neighbours are
+    reset and stepped on their own schedules."""
+    cfg = _cfg(highway_config, observation=dict(order="shuffled"))
+    R, T = 5, 12
+    seeds = [42, 1042, 7, 2**40 + 3, 99]
+    rng = np.random.default_rng(3)
+    actions = rng.uniform(-1, 1, (T, R, 2)).astype(np.float32)
+    active = rng.random((T, R)) < 0.7
+    active[0] = True
+    resets = {(4, 1): 555, (7, 3): 556}          # (t, env) -> new seed: a run starts another episode
+    # reference: R single-env handles driven one by one
+    want = []
+    singles = [_vec(cfg, 1, autoreset=False) for _ in range(R)]
+    for e, env in enumerate(singles):
+        env.reset(seeds[e])
+    for t in range(T):
+        row = []
+        for e, env in enumerate(singles):
+            if (t, e) in resets:
+                env.reset(resets[(t, e)])
+            if active[t, e]:
+                o, r, te, tr = env.step(torch.from_numpy(actions[t, e:e + 1]).cuda())
+                row.append((o.cpu().numpy()[0].copy(), float(r[0]), int(te[0]), int(tr[0])))
+            else:
+                row.append(None)
+        want.append(row)
+    want_state = [env.get_state() for env in singles]
+    for env in singles:
+        env.close()
+    # one shared handle
+    env = _vec(cfg, R, autoreset=False)
+    sd = torch.tensor(seeds, dtype=torch.int64, device="cuda:0")
+    mask = torch.zeros(R, dtype=torch.uint8, device="cuda:0")
+    env.set_env_seeds(sd)
+    env.set_step_mask(mask)
+    env.reset()
+    for t in range(T):
+        for (tt, e), s in resets.items():
+            if tt == t:
+                sd[e] = s
+                m = torch.zeros(R, dtype=torch.uint8, device="cuda:0")
+                m[e] = 1
+                env.reset(mask=m)
+        mask.copy_(torch.from_numpy(active[t].astype(np.uint8)))
+        o, r, te, tr = env.step(torch.from_numpy(actions[t]).cuda())
+        o, r, te, tr = o.cpu().numpy(), r.cpu().numpy(), te.cpu().numpy(), tr.cpu().numpy()
+        for e in range(R):
+            if want[t][e] is not None:
+                wo, wr, wte, wtr = want[t][e]
+                assert np.array_equal(o[e], wo) and float(r[e]) == wr and int(te[e]) == wte and int(tr[e]) == wtr, (t, e)
+    got = env.get_state()
+    for e in range(R):
+        for k in oh.STATE_F64 + oh.STATE_I32:
+            assert np.array_equal(got[k][e], want_state[e][k][0]), (e, k)
+    env.close()

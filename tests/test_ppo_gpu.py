@@ -620,3 +620,28 @@ def test_multi_policy_act_matches_the_batched_forward_and_the_reference():
     torch.cuda.synchronize()
     assert torch.equal(o1["action"].view(-1), row[0:2]) and torch.equal(o1["pre_tanh"].view(-1), row[2:4])
     assert torch.equal(o1["log_prob"].view(-1), row[4:5]) and torch.equal(o1["value"].view(-1), row[5:6])
+
+
+@pytest.mark.parametrize("A,H,B", [(1, 128, 256), (2, 256, 4096), (4, 384, 1000), (3, 64, 64), (2, 512, 130)])
+def test_fused_heads_act_path_matches_the_unfused_forward(A, H, B):
+    """The act path with the heads fused into the [a1 | c1] GEMM's epilogue (TcDots + heads_finish_kernel; taken whenever
+    the N tiles do not straddle H) against forward() (separate heads kernel): deterministic actions are the means,
+    values agree, for 1 to 4 action dimensions, whole and ragged M tiles, 64- and 128-wide N tiles; and the sampled
+    path's log-prob is the one evaluate() assigns to its own pre-tanh sample."""
+    torch.manual_seed(40 + A)
+    agent = _agent(60, A, H, B)
+    ac = agent.actor_critic
+    x = torch.randn(B, 60, device="cuda:0") * 0.4
+    mean, std, value = ac.forward(x)
+    det = ac.act(x, deterministic=True)
+    scale = float(mean.abs().max()) + 1e-3
+    np.testing.assert_allclose(det["pre_tanh"].cpu().numpy(), mean.cpu().numpy(), atol=3e-6 * max(1.0, scale))
+    np.testing.assert_allclose(det["value"].cpu().numpy(), value[:, 0].cpu().numpy(), atol=3e-6 * max(1.0, float(value.abs().max())))
+    np.testing.assert_allclose(det["action"].cpu().numpy(), np.tanh(det["pre_tanh"].cpu().numpy()), atol=1e-6)
+    out = ac.act(x)
+    logp, _, _ = ac.evaluate(x, None, out["pre_tanh"])
+    # log(1 - tanh(z)^2 + 1e-6) is ill-conditioned for a saturated action (|z| > 4: 1 - t^2 ~ 1e-4, one ulp of t moves it
+    # by 1e-3 relative), per action dimension
+    np.testing.assert_allclose(out["log_prob"].cpu().numpy(), logp.cpu().numpy(), atol=1e-4 * A, rtol=3e-5)
+    n = ((out["pre_tanh"] - mean) / std).flatten()
+    assert abs(float(n.mean())) < 0.2 and 0.7 < float(n.std()) < 1.3
