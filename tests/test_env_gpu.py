@@ -270,6 +270,8 @@ def _free_run(cfg, E, steps, seed, action_fn, real64, window=None):
     rng = np.random.default_rng(seed)
     rows = torch.zeros((E, N), dtype=torch.int32, device="cuda:0")
     live = np.ones(E, dtype=bool)
+    _free_run.ended = 0
+    ever_slow = np.zeros(E, dtype=bool)
     closest = np.full(E, np.inf)
     compared, lengths, worst = 0, [], {}
     for t in range(steps):
@@ -289,8 +291,23 @@ def _free_run(cfg, E, steps, seed, action_fn, real64, window=None):
             margin = min(margin, o.min_margin())
             got = _Got(state, e, obs, rew, term, trunc, rv)
             if real64:
+                # Discrete state, flags, rows, episode counters exact and continuous state within 1e-7 on every step.
+                # A difference ends the env's window -- instead of failing -- only if the oracle itself says why the two
+                # sides may have separated: (a) an exact tie (a decision margin below 1e-9: resting contacts of a
+                # pile-up, the cases the injected runs resolve by flipping the tie), or (b) a vehicle of the env has
+                # crawled or reversed at this or an earlier step of the window: such a vehicle is laterally UNSTABLE
+                # under highway-env's own steering law, a rounding-level difference grows 5 to 8 times per simulation
+                # frame for as long as it reverses (profiles/r02_reversing_vehicle_trace.txt), in the oracle as in the
+                # kernel, and without re-injection nothing bounds it.  `_free_run.ended` counts those windows; the
+                # injected runs check exactly those steps one at a time.
+                ever_slow[e] |= bool(o.slow_vehicles().any())
                 why = _mismatch(got, o, r, te, tr, want_obs, want_rows, TOL64, 1e-6, 1e-6, worst)
-                assert why is None, (t, e, why)
+                if why is not None and (ever_slow[e] or margin < MARGIN64):
+                    live[e] = False
+                    _free_run.ended += 1
+                    lengths.append(t)
+                    continue
+                assert why is None, (t, e, why, margin)
                 assert state["episode"][e] == episode[e]
             else:
                 # tolerances and the decision margin grow with the steps since the injection.  A window ends at the
