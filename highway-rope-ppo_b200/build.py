@@ -48,6 +48,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     obj_dir = os.path.join(LIB_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)
     base = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    if os.environ.get("HRP_PHASE_CLOCKS") == "1":   # profiling build: per-phase SM clocks of the GEMM kernels (tools/gemm_one.py)
+        base += ["-DHRP_PHASE_CLOCKS"]
     if verbose:
         base += ["-Xptxas", "-v"]
     jobs = []

@@ -25,7 +25,12 @@
 // phase clocks of CTA (0,0,0) when hrp_debug_tma_gemm_clocks(1) switched them on (tools/gemm_bench.py)
 __device__ long long g_gt_phase[16];
 __device__ int g_gt_phase_on;
+// (compiled in only by a profiling build: HRP_PHASE_CLOCKS=1 python highway-rope-ppo_b200/build.py --force)
+#ifdef HRP_PHASE_CLOCKS
 #define GT_PHASE(i) do { if (g_gt_phase_on && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_gt_phase[(i)] = clock64(); } while (0)
+#else
+#define GT_PHASE(i) do { } while (0)
+#endif
 
 namespace {
 

@@ -31,7 +31,13 @@
 
 // phase clocks of CTA (0,0,0), thread 0 (+ the MMA warp's lane 0): see hrp_debug_gemm_phases
 __device__ long long g_tc_phase[16];
+// -- compiled in only by a profiling build (HRP_PHASE_CLOCKS=1 python highway-rope-ppo_b200/build.py --force, for
+// tools/gemm_one.py); the production kernel carries no clock reads or global stores for them
+#ifdef HRP_PHASE_CLOCKS
 #define TC_PHASE(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == TC_THREADS)) g_tc_phase[(i)] = clock64(); } while (0)
+#else
+#define TC_PHASE(i) do { } while (0)
+#endif
 
 namespace {
 
