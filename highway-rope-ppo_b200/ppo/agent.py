@@ -693,10 +693,10 @@ class PPOAgent:
 
     def _graphed_epochs(self, flat: Dict[str, torch.Tensor], perm_dev: torch.Tensor, n: int, bs: int,
                         world: int = 1) -> None:
-        """The ~40 launches of one optimizer step (loss / backward / clip / Adam) as ONE CUDA graph per distinct
-        minibatch size (the full one and a ragged last one), replayed for every minibatch of every epoch and re-used by
-        later updates of the same shape: the graph reads its sample indices from a fixed buffer that a small
-        device-to-device copy of the permutation slice refills before each replay.  The rollout is first copied into
+        """The ~40 launches of one optimizer step (loss / backward / clip / Adam) as a CUDA graph, replayed for every
+        epoch and re-used by later updates of the same shape: one graph per minibatch when there are at most 32 of them,
+        else ONE graph per distinct minibatch size (the full one and a ragged last one) that reads its sample indices
+        from a fixed buffer which a small device-to-device copy of the permutation slice refills before each replay.  The rollout is first copied into
         persistent buffers so that the captured pointers stay valid.  The first epoch of a new configuration runs
         eagerly (it also warms every kernel variant before anything is captured)."""
         ac = self.actor_critic
@@ -715,21 +715,29 @@ class PPOAgent:
             st["buf"][k].copy_(v)
         st["perm"].copy_(perm_dev)
         starts = list(range(0, n, bs))
+        # few minibatches (the big-batch configuration: 32 of 4096): one graph per minibatch, its permutation slice baked
+        # in, nothing between the replays.  Many (a sweep run at batch 32: 64 and more): one graph per distinct size,
+        # fed through the index buffer, because capturing dominates there.
+        shared = len(starts) > 32
         for epoch in range(self.epochs):
-            for start in starts:
+            for i, start in enumerate(starts):
                 B = min(bs, n - start)
-                idx = st["idx"][:B]
-                idx.copy_(st["perm"][start:start + B])
+                if shared:
+                    idx = st["idx"][:B]
+                    idx.copy_(st["perm"][start:start + B])
+                else:
+                    idx = st["perm"][start:start + B]
                 if not st["warm"]:
                     self._minibatch_step(st["buf"], idx, B, world)
                     continue
-                # the peer-memory exchange alternates its buffers with the step parity: one graph per (size, parity)
+                # the peer-memory exchange alternates its buffers with the step parity: one graph per (.., parity)
                 parity = self._lib.hrp_comm_parity(self._comm) if (world > 1 and self._comm is not None) else 0
-                g = st["graphs"].get((B, parity))
+                gkey = (B if shared else ("mb", i), parity)
+                g = st["graphs"].get(gkey)
                 if g is None:
                     # (capturing advances the parity)
                     g = self._capture(lambda: self._minibatch_step(st["buf"], idx, B, world), world)
-                    st["graphs"][(B, parity)] = g
+                    st["graphs"][gkey] = g
                 elif world > 1 and self._comm is not None:
                     _lib.check(self._lib.hrp_comm_note_replay(self._comm), "hrp_comm_note_replay")
                     self.grad = self._grad_parity[parity]
