@@ -107,3 +107,21 @@ def test_every_run_name_is_readable_by_the_reference_offline_tools():
         assert float(d["lr"]) == mine["lr"] == e.hp.lr and int(d["hidden_dim"]) == mine["hidden_dim"] == e.hp.hidden_dim
         assert int(d["epochs"]) == e.hp.epochs and int(d["batch_size"]) == e.hp.batch_size and int(d["seed"]) == e.seed
         assert int(d["d_embed"]) == e.hp.d_embed and float(d["clip_eps"]) == e.hp.clip_eps
+
+
+def test_command_line_front_end_selection(capsys):
+    """main.py:90-245 re-hosted: the grid size, the single-experiment rules and the array-task slices, without a GPU."""
+    from highway_rope_ppo_b200 import main as cli
+    from highway_rope_ppo_b200.experiments.sweep import define_experiments, select_experiments
+
+    assert cli.main(["--get-total-experiments"]) == 0
+    assert capsys.readouterr().out.strip() == "540"
+    assert cli.main(["--get-total-experiments", "--num-seeds", "1"]) == 0
+    assert capsys.readouterr().out.strip() == "180"
+    assert cli.main(["--run-single-experiment", "no_such_experiment"]) == 1            # reference: exit(1)
+    assert cli.main(["--run-single-experiment", "sorted_lr0.0001"]) == 1                # ambiguous prefix
+    assert cli.main(["--generate-slurm"]) == 2
+    a = cli.parse(["--array-task-id", "3", "--slurm-num-tasks", "68", "--n-jobs", "8"])
+    exps = define_experiments()
+    sel = select_experiments(exps, a.array_task_id, a.slurm_num_tasks, a.run_single_experiment)
+    assert [e.name for e in sel] == [e.name for e in exps[24:32]]                       # ceil(540 / 68) = 8 per task
