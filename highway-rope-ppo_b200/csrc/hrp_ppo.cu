@@ -1514,10 +1514,11 @@ int hrp_ppo_loss_grad(hrp_ppo *h, const float *params, const float *states, cons
     // main: d(h2) = [d(a1) | d(c1)] [Wa1 ; Wc1] (.) (h2>0): K = 2H against the transposed copies
     HRP_CUDA_OK(cudaStreamWaitEvent(s, h->ev[3], 0));
     if (gemm(false, true, Bi, H, H2, h->d12, H2, h->wt_ac, H2, h->dh2, H, nullptr, 0, h->h2, H, 0, 1, s) < 0) return -2;
-    // side 1: dW2, db2
-    HRP_CUDA_OK(after(4, s, s1));
-    if (wgrad(h, plan, h->part_w[1], H, H, B, h->dh2, H, h->h1, H, grad + L.w2, H, nullptr, s1)) return -2;
-    if (colsum(plan, h->part_b[1], h->dh2, H, B, H, grad + L.b2, H, nullptr, s1)) return -2;
+    // side 0 (behind the short heads kernel; side 1 is still busy with [dWa1 ; dWc1]): dW2, db2 start as soon as d(h2)
+    // exists, beside d(h1), so that dW1 at the end of the chain does not have to share the machine with them
+    HRP_CUDA_OK(after(4, s, s0));
+    if (wgrad(h, plan, h->part_w[1], H, H, B, h->dh2, H, h->h1, H, grad + L.w2, H, nullptr, s0)) return -2;
+    if (colsum(plan, h->part_b[1], h->dh2, H, B, H, grad + L.b2, H, nullptr, s0)) return -2;
     // main: d(h1) = d(h2) W2 (.) (h1>0), dW1; side 0: db1
     if (gemm(false, true, Bi, H, H, h->dh2, H, h->wt_2, H, h->dh1, H, nullptr, 0, h->h1, H, 0, 1, s) < 0) return -2;
     HRP_CUDA_OK(after(5, s, s0));
