@@ -134,6 +134,8 @@ class HighwayVecEnv:
     episodes as the single-GPU run.
     """
 
+    _next_uid = 0
+
     def __init__(self, cfg: Dict[str, Any], num_envs: int, device: Any = "cuda", embed: Optional[EmbedSpec] = None,
                  autoreset: bool = True, env_id_base: int = 0, seed: int = 0, real64: bool = False):
         # real64: the fp64 VALIDATION instantiation of the kernels (HRP_ENV_REAL64; parity tests only, slow)
@@ -170,6 +172,10 @@ class HighwayVecEnv:
         self.terminated = torch.zeros(E, dtype=torch.uint8, device=self.device)
         self.truncated = torch.zeros(E, dtype=torch.uint8, device=self.device)
         self.launches = 0  # kernels of this library enqueued through this handle
+        # identity of this handle for caches of captured launches (training/routine.py): id() of a closed env can be
+        # handed to a new one, a counter cannot
+        HighwayVecEnv._next_uid += 1
+        self.uid = HighwayVecEnv._next_uid
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
