@@ -43,7 +43,8 @@ class HostBufferPipeline:
                  "obs_d": torch.empty((Eg, S), device=dev),
                  "out": {"action": torch.empty((Eg, A), device=dev), "pre_tanh": torch.empty((Eg, A), device=dev),
                          "log_prob": torch.empty(Eg, device=dev), "value": torch.empty(Eg, device=dev)},
-                 "draw": agent.actor_critic.new_draw_counter(), "graph": None, "lane": 1 + gi,
+                 "draw": agent.actor_critic.new_draw_counter(), "draw0": agent.actor_critic._draw, "steps": 0,
+                 "graph": None, "lane": 1 + gi,
                  "row_base": int(getattr(env, "env_id_base", 0)), "pending": False, "index": gi}
             self.groups.append(g)
             self.buffers.append({"obs": g["obs_h"].numpy(), "action": g["act_h"].numpy(), "reward": g["rew_h"].numpy(),
@@ -101,6 +102,11 @@ class HostBufferPipeline:
         finally:
             torch.cuda.set_stream(home)
         g["pending"] = True
+        g["steps"] += 1
+        # keep the policy's host-side draw counter ahead of the device-resident ones: a later eager act() must not
+        # repeat (seed, row, draw) triples this pipeline has used
+        ac = self.agent.actor_critic
+        ac._draw = max(ac._draw, g["draw0"] + g["steps"])
         self.launches += 5 + int(self.kernel_fetch)
 
     def wait(self, gi: int) -> Dict[str, np.ndarray]:
