@@ -324,3 +324,24 @@ def test_graph_captured_rollout_equals_the_eager_rollout(highway_config):
     for a, b in zip(*runs):
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+def test_fetch_host_kernel_copies_pinned_buffers_exactly():
+    """hrp_fetch_host: the kernel-side host-to-device copy of a page-locked buffer (any byte count, 16-byte aligned
+    pointers), and its argument checks."""
+    from highway_rope_ppo_b200 import _lib
+
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    for n in (1, 15, 16, 17, 4096, 983040, 983040 + 7):
+        src = torch.randint(0, 256, (n,), dtype=torch.uint8).pin_memory()
+        dst = torch.zeros(n + 16, dtype=torch.uint8, device="cuda:0")
+        assert lib.hrp_fetch_host(dst.data_ptr(), src.data_ptr(), n, st) == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        assert torch.equal(dst[:n].cpu(), src) and int(dst[n:].sum()) == 0, n
+    src = torch.zeros(64, dtype=torch.uint8).pin_memory()
+    dst = torch.zeros(64, dtype=torch.uint8, device="cuda:0")
+    assert lib.hrp_fetch_host(dst.data_ptr() + 4, src.data_ptr(), 16, st) == -1          # misaligned destination
+    pageable = torch.zeros(64, dtype=torch.uint8)
+    assert lib.hrp_fetch_host(dst.data_ptr(), pageable.data_ptr(), 16, st) == -1          # not page-locked
+    assert lib.hrp_fetch_host(dst.data_ptr(), src.data_ptr(), 0, st) == 0
