@@ -709,7 +709,8 @@ int dispatch(int bn, int nsplit, dim3 grid, cudaStream_t s, int M, int N, int K,
              const float *bias2, float *C_lo, const TcDots &dots)
 {
 #define HRP_TC_ARGS grid, s, M, N, K, A, sam, sak, B, sbn, sbk, C, ldc, bias, relu, mask, ldm, accumulate, k_chunk, nseg, B2, bias2, C_lo, dots
-    if (bn == 64) return nsplit == 3 ? launch<AMODE, BMODE, 3, 64>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 64>(HRP_TC_ARGS);
+    if (bn == 32 && nsplit == 3) return launch<AMODE, BMODE, 3, 32>(HRP_TC_ARGS);
+    if (bn <= 64) return nsplit == 3 ? launch<AMODE, BMODE, 3, 64>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 64>(HRP_TC_ARGS);
     return nsplit == 3 ? launch<AMODE, BMODE, 3, 128>(HRP_TC_ARGS) : launch<AMODE, BMODE, 1, 128>(HRP_TC_ARGS);
 #undef HRP_TC_ARGS
 }
@@ -745,7 +746,7 @@ int hrp_tc_gemm_bn(int M, int N, int splits, int nseg)
 int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
                 int accumulate, int splits, int nsplit, cudaStream_t s, int nseg, const float *B2, const float *bias2,
-                float *C_lo, const TcDots *dots_in)
+                float *C_lo, const TcDots *dots_in, int narrow)
 {
     const TcDots dots = dots_in ? *dots_in : TcDots{nullptr, nullptr, 0, 0, nullptr, 0};
     int k_chunk = K;
@@ -762,6 +763,14 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
         if (nseg % 64 != 0 || nseg >= N || B2 == nullptr) { hrp_set_error("hrp_tc_gemm: bad N segmentation"); return -1; }
         if (nseg % 128 != 0) bn = 64;   // a tile must not straddle the two B matrices
     }
+    // `narrow` (the forward chains, where nothing else runs beside the GEMM): 32-wide N tiles when 64-wide ones leave at
+    // most one CTA per SM -- two CTAs (80 KB of stages each) then share an SM and the prologue / epilogue of one overlaps
+    // the main loop of the other: policy forward 43.3 -> 38.2 us.  Not for the backward pass, whose GEMMs already share
+    // the machine with the weight-gradient GEMMs of the side streams (optimizer step 127 -> 141 us with it).
+    // HRP_BN32=0 switches it off.
+    static const bool bn32 = !(getenv("HRP_BN32") && getenv("HRP_BN32")[0] == '0');
+    if (narrow && bn32 && bn == 64 && nsplit == 3 && N % 32 == 0 && N >= 64 && mt * ((N + 63) / 64) * splits <= 148 && !dots.out)
+        bn = 32;
     dim3 grid((N + bn - 1) / bn, mt, splits);
     if (dots.out && (splits != 1 || dots.H % bn != 0 || N % bn != 0 || ldc % 4 != 0 || !aligned(C, 16) || mask || C_lo)) {
         hrp_set_error("hrp_tc_gemm: the fused row-dot epilogue needs whole, aligned tiles that do not straddle H");

@@ -803,7 +803,7 @@ struct hrp_ppo {
 int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sak, const float *B, long long sbn,
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
                 int accumulate, int splits, int nsplit, cudaStream_t s, int nseg = 0, const float *B2 = nullptr,
-                const float *bias2 = nullptr, float *C_lo = nullptr, const TcDots *dots = nullptr);
+                const float *bias2 = nullptr, float *C_lo = nullptr, const TcDots *dots = nullptr, int narrow = 0);
 int hrp_tc_gemm_bn(int M, int N, int splits, int nseg);
 
 // TMA-fed 3xTF32 path on pre-split operands (hrp_gemm_tma.cu)
@@ -819,11 +819,12 @@ static int g_math_mode = 3;
 
 static int gemm(bool AT, bool BT, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C,
                 int ldc, const float *bias, int relu, const float *mask, int ldm, int accumulate, int splits,
-                cudaStream_t s)
+                cudaStream_t s, int narrow = 0)
 {
     if (g_math_mode != 0 && N >= 32 && M >= 32)
         return hrp_tc_gemm(M, N, K, A, AT ? 1 : lda, AT ? lda : 1, B, BT ? ldb : 1, BT ? 1 : ldb, C, ldc, bias, relu,
-                           mask, ldm, accumulate, splits, g_math_mode == 1 ? 1 : 3, s);
+                           mask, ldm, accumulate, splits, g_math_mode == 1 ? 1 : 3, s, 0, nullptr, nullptr, nullptr, nullptr,
+                           narrow);
     int k_chunk = K;
     if (splits > 1) {
         k_chunk = ((K + splits - 1) / splits + GK - 1) / GK * GK;
@@ -941,8 +942,8 @@ static int forward_impl(hrp_ppo *h, const float *params, const float *x, long lo
         HRP_CUDA_OK(cudaGetLastError());
         return 0;
     }
-    if (gemm(false, true, Bi, H, S, x, S, params + L.w1, S, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
-    if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+    if (gemm(false, true, Bi, H, S, x, S, params + L.w1, S, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, s, 1) < 0) return -2;
+    if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s, 1) < 0) return -2;
     if (g_math_mode != 0 && H % 64 == 0 && Bi >= 32) {
         if (hrp_tc_gemm(Bi, 2 * H, H, h->h2, H, 1, params + L.wa1, H, 1, h->ac, 2 * H, params + L.ba1, 1, nullptr, 0, 0, 1,
                         g_math_mode == 1 ? 1 : 3, s, H, params + L.wc1, params + L.bc1) < 0)
@@ -1135,8 +1136,8 @@ static int act_impl(hrp_ppo *h, const float *params, const float *states, const 
         const int H = L.H, Bi = (int)batch;
         const int bn = hrp_tc_gemm_bn(Bi, 2 * H, 1, H);
         if (fuse_on && g_math_mode != 0 && !(use_tma(h) && Bi >= 32) && H % 64 == 0 && Bi >= 32 && H % bn == 0) {
-            if (gemm(false, true, Bi, H, L.S, states, L.S, params + L.w1, L.S, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, s) < 0) return -2;
-            if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s) < 0) return -2;
+            if (gemm(false, true, Bi, H, L.S, states, L.S, params + L.w1, L.S, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, s, 1) < 0) return -2;
+            if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s, 1) < 0) return -2;
             // partial sums in the (idle) backward scratch d12: [2 H / bn tiles][B][4] <= [B][2 H] floats
             const TcDots dots{params + L.wa2, params + L.wc2, H, L.A, h->d12, 1};
             if (hrp_tc_gemm(Bi, 2 * H, H, h->h2, H, 1, params + L.wa1, H, 1, h->ac, 2 * H, params + L.ba1, 1, nullptr, 0, 0, 1,
