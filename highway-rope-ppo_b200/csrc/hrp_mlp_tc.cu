@@ -733,11 +733,12 @@ inline bool aligned(const void *p, int bytes) { return ((uintptr_t)p % bytes) ==
 }  // namespace
 
 // the N-tile width hrp_tc_gemm picks (the fused row-dot epilogue's caller sizes its partial buffer with it)
-int hrp_tc_gemm_bn(int M, int N, int splits, int nseg)
+int hrp_tc_gemm_bn(int M, int N, int splits, int nseg, int narrow)
 {
-    const int mt = (M + BM - 1) / BM;
-    int bn = (N <= 64 || mt * ((N + 127) / 128) * (splits > 1 ? splits : 1) < 120) ? 64 : 128;
+    const int mt = (M + BM - 1) / BM, sp = splits > 1 ? splits : 1;
+    int bn = (N <= 64 || mt * ((N + 127) / 128) * sp < 120) ? 64 : 128;
     if (nseg > 0 && nseg % 128 != 0) bn = 64;
+    (void)narrow;   // (64-wide instead of 128-wide tiles for the 2 H-wide head GEMM were measured slower: 40.6 against 38.2 us)
     return bn;
 }
 
@@ -758,11 +759,8 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
     }
     // 64-wide N tiles when 128-wide ones would leave most of the 148 SMs idle
     const int mt = (M + BM - 1) / BM;
-    int bn = (N <= 64 || mt * ((N + 127) / 128) * splits < 120) ? 64 : 128;
-    if (nseg > 0) {
-        if (nseg % 64 != 0 || nseg >= N || B2 == nullptr) { hrp_set_error("hrp_tc_gemm: bad N segmentation"); return -1; }
-        if (nseg % 128 != 0) bn = 64;   // a tile must not straddle the two B matrices
-    }
+    if (nseg > 0 && (nseg % 64 != 0 || nseg >= N || B2 == nullptr)) { hrp_set_error("hrp_tc_gemm: bad N segmentation"); return -1; }
+    int bn = hrp_tc_gemm_bn(M, N, splits, nseg, narrow);   // (a tile never straddles the two B matrices of a segmented operand)
     // `narrow` (the forward chains, where nothing else runs beside the GEMM): 32-wide N tiles when 64-wide ones leave at
     // most one CTA per SM -- two CTAs (80 KB of stages each) then share an SM and the prologue / epilogue of one overlaps
     // the main loop of the other: policy forward 43.3 -> 38.2 us.  Not for the backward pass, whose GEMMs already share

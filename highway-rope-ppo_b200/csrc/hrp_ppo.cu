@@ -804,7 +804,7 @@ int hrp_tc_gemm(int M, int N, int K, const float *A, long long sam, long long sa
                 long long sbk, float *C, int ldc, const float *bias, int relu, const float *mask, int ldm,
                 int accumulate, int splits, int nsplit, cudaStream_t s, int nseg = 0, const float *B2 = nullptr,
                 const float *bias2 = nullptr, float *C_lo = nullptr, const TcDots *dots = nullptr, int narrow = 0);
-int hrp_tc_gemm_bn(int M, int N, int splits, int nseg);
+int hrp_tc_gemm_bn(int M, int N, int splits, int nseg, int narrow = 0);
 
 // TMA-fed 3xTF32 path on pre-split operands (hrp_gemm_tma.cu)
 int hrp_tma_gemm(int M, int N, int K, const float *A, const float *A_lo, long long sam, long long sak, const float *B,
@@ -1134,14 +1134,14 @@ static int act_impl(hrp_ppo *h, const float *params, const float *states, const 
         // heads fused into the [a1 | c1] GEMM's epilogue whenever its tiles do not straddle H (HRP_FUSE_HEADS=0: off)
         static const bool fuse_on = !(getenv("HRP_FUSE_HEADS") && getenv("HRP_FUSE_HEADS")[0] == '0');
         const int H = L.H, Bi = (int)batch;
-        const int bn = hrp_tc_gemm_bn(Bi, 2 * H, 1, H);
+        const int bn = hrp_tc_gemm_bn(Bi, 2 * H, 1, H, 1);
         if (fuse_on && g_math_mode != 0 && !(use_tma(h) && Bi >= 32) && H % 64 == 0 && Bi >= 32 && H % bn == 0) {
             if (gemm(false, true, Bi, H, L.S, states, L.S, params + L.w1, L.S, h->h1, H, params + L.b1, 1, nullptr, 0, 0, 1, s, 1) < 0) return -2;
             if (gemm(false, true, Bi, H, H, h->h1, H, params + L.w2, H, h->h2, H, params + L.b2, 1, nullptr, 0, 0, 1, s, 1) < 0) return -2;
             // partial sums in the (idle) backward scratch d12: [2 H / bn tiles][B][4] <= [B][2 H] floats
             const TcDots dots{params + L.wa2, params + L.wc2, H, L.A, h->d12, 1};
             if (hrp_tc_gemm(Bi, 2 * H, H, h->h2, H, 1, params + L.wa1, H, 1, h->ac, 2 * H, params + L.ba1, 1, nullptr, 0, 0, 1,
-                            g_math_mode == 1 ? 1 : 3, s, H, params + L.wc1, params + L.bc1, nullptr, &dots) < 0)
+                            g_math_mode == 1 ? 1 : 3, s, H, params + L.wc1, params + L.bc1, nullptr, &dots, 1) < 0)
                 return -2;
             HRP_CUDA_OK(hrp_launch_pdl(heads_finish_kernel, dim3((unsigned)((batch + 127) / 128)), dim3(128), 0, s,
                                        (const float *)h->d12, H / bn, 2 * H / bn, params + L.ba2, params + L.bc2,
