@@ -345,3 +345,15 @@ def test_fetch_host_kernel_copies_pinned_buffers_exactly():
     pageable = torch.zeros(64, dtype=torch.uint8)
     assert lib.hrp_fetch_host(dst.data_ptr(), pageable.data_ptr(), 16, st) == -1          # not page-locked
     assert lib.hrp_fetch_host(dst.data_ptr(), src.data_ptr(), 0, st) == 0
+
+
+def test_command_line_front_end_runs_an_array_task(tmp_path, capsys):
+    """main.py re-hosted (python -m highway_rope_ppo_b200.main): one array task of the grid, multiplexed, end to end."""
+    from highway_rope_ppo_b200 import main as cli
+
+    rc = cli.main(["--array-task-id", "1", "--slurm-num-tasks", "135", "--n-jobs", "4", "--max-episodes", "4",
+                   "--artifacts-dir", str(tmp_path)])          # ceil(540 / 135) = 4 experiments: grid entries 4 .. 7
+    out = capsys.readouterr().out
+    assert rc == 0 and "best avg_reward" in out
+    names = sorted(p.name for p in tmp_path.glob("summary_*.csv"))
+    assert len(names) == 4 and all(n.startswith("summary_sorted_lr0.0001_hidden_dim128") for n in names)
