@@ -63,6 +63,8 @@ def parse():
     p.add_argument("--e2e-groups", type=int, default=1, choices=[1, 2, 4, 8],
                    help="env groups of the host-buffer loop: G groups of E/G envs on G streams (copies and host turn-around "
                         "of one under the kernels of the others)")
+    p.add_argument("--e2e-chunks", type=int, default=1,
+                   help="row chunks of the observation fetch: the policy of a chunk runs while the next one crosses PCIe")
     p.add_argument("--e2e-eager", action="store_true", help="host-buffer loop without CUDA graphs")
     p.add_argument("--e2e-copy-engine", action="store_true",
                    help="observation H2D by cudaMemcpyAsync instead of the fetch kernel (hrp_fetch_host)")
@@ -488,7 +490,8 @@ def run_ours(args):
         Eg = E // G
         genvs = [make_vec_env(Condition[cond_name], HIGHWAY_CONFIG, d_embed, over, num_envs=Eg, device=dev, seed=42,
                               env_id_base=rank * E + gi * Eg, strict_d_embed=False) for gi in range(G)]
-        pipe = HostBufferPipeline(agent, genvs, use_graphs=not args.e2e_eager, kernel_fetch=not args.e2e_copy_engine)
+        pipe = HostBufferPipeline(agent, genvs, use_graphs=not args.e2e_eager, kernel_fetch=not args.e2e_copy_engine,
+                                  chunks=args.e2e_chunks)
         pipe.reset(42)
         for _ in range(5):
             for gi in range(G):
@@ -509,7 +512,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * E * Ke / float(t.cpu()), "unit": UNIT,
                "h2d_bytes_per_step": E * S * 4, "d2h_bytes_per_step": E * 2 * 4 + E * S * 4 + E * 4 + 2 * E,
-               "steps": Ke, "groups": G, "cuda_graphs": not args.e2e_eager,
+               "steps": Ke, "groups": G, "chunks": args.e2e_chunks, "cuda_graphs": not args.e2e_eager,
                "h2d_by": "copy engine (cudaMemcpyAsync)" if args.e2e_copy_engine else "kernel reading the mapped pinned buffer (hrp_fetch_host)",
                "api": "HostBufferPipeline.launch / wait (training/host_pipeline.py): PPOAgent.act on a pinned-host "
                       "observation (H2D copy) + HighwayVecEnv.step_host_async (hrp_env_step_host_async): the device action "

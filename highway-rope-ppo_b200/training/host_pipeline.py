@@ -27,9 +27,12 @@ class HostBufferPipeline:
     pinned tensors: ``obs`` [E_g, N, F_out] -- both the policy's input and the step's output --, ``action`` [E_g, 2],
     ``reward``, ``terminated``, ``truncated`` [E_g])."""
 
-    def __init__(self, agent, groups: List[Any], use_graphs: bool = True, kernel_fetch: bool = True):
+    def __init__(self, agent, groups: List[Any], use_graphs: bool = True, kernel_fetch: bool = True, chunks: int = 1):
+        """``chunks`` > 1: the observation is fetched in row chunks, one after the other, and the policy of a chunk runs
+        (on its own stream and workspace lane) while the next chunk is still crossing PCIe; the env step waits for all."""
         self.agent, self.envs, self.use_graphs = agent, list(groups), bool(use_graphs)
         self.kernel_fetch, self._lib = bool(kernel_fetch), _lib.load()
+        self.chunks = max(1, int(chunks))
         dev = agent.device
         self.groups: List[Dict[str, Any]] = []
         self.buffers: List[Dict[str, np.ndarray]] = []
@@ -44,12 +47,16 @@ class HostBufferPipeline:
                  "out": {"action": torch.empty((Eg, A), device=dev), "pre_tanh": torch.empty((Eg, A), device=dev),
                          "log_prob": torch.empty(Eg, device=dev), "value": torch.empty(Eg, device=dev)},
                  "draw": agent.actor_critic.new_draw_counter(), "draw0": agent.actor_critic._draw, "steps": 0,
-                 "graph": None, "lane": 1 + gi,
+                 "graph": None, "lane": 1 + gi * self.chunks,
+                 # chunked only when the chunks are whole and 16-byte aligned (hrp_fetch_host)
+                 "C": self.chunks if Eg % self.chunks == 0 and (Eg // self.chunks * S * 4) % 16 == 0 else 1,
+                 "draws": [agent.actor_critic.new_draw_counter() for _ in range(self.chunks)],
+                 "cstreams": [torch.cuda.Stream(device=dev) for _ in range(self.chunks - 1)],
                  "row_base": int(getattr(env, "env_id_base", 0)), "pending": False, "index": gi}
             self.groups.append(g)
             self.buffers.append({"obs": g["obs_h"].numpy(), "action": g["act_h"].numpy(), "reward": g["rew_h"].numpy(),
                                  "terminated": g["te_h"].numpy(), "truncated": g["tr_h"].numpy()})
-        self.launches = 0   # kernels of this library enqueued (per group-step: [fetch,] 3 GEMMs, heads, env step)
+        self.launches = 0   # kernels of this library enqueued (per group-step and chunk: [fetch,] 3 GEMMs, heads; + env step)
 
     def reset(self, seed: int) -> None:
         for g, b in zip(self.groups, self.buffers):
@@ -60,13 +67,38 @@ class HostBufferPipeline:
         env, ac = g["env"], self.agent.actor_critic
         Eg, S = env.num_envs, env.N * env.F_out
         cur = torch.cuda.current_stream(self.agent.device)
-        if self.kernel_fetch:    # H2D observation by a kernel (hrp_fetch_host): the first GEMM follows it within ~1 us
-            _lib.check(self._lib.hrp_fetch_host(g["obs_d"].data_ptr(), g["obs_h"].data_ptr(), Eg * S * 4, cur.cuda_stream),
-                       "hrp_fetch_host")
-        else:                    # ... or by the copy engine
-            g["obs_d"].copy_(g["obs_h"].view(Eg, S), non_blocking=True)
+        C = g["C"]
+        rows = Eg // C
+        fetched = []
+        for c in range(C):       # the chunks cross PCIe one after the other, on the group's stream
+            lo, hi = c * rows, (c + 1) * rows
+            if self.kernel_fetch:    # H2D observation by a kernel (hrp_fetch_host): the first GEMM follows it within ~1 us
+                _lib.check(self._lib.hrp_fetch_host(g["obs_d"][lo:hi].data_ptr(), g["obs_h"][lo:hi].data_ptr(), rows * S * 4,
+                                                    cur.cuda_stream), "hrp_fetch_host")
+            else:                    # ... or by the copy engine
+                g["obs_d"][lo:hi].copy_(g["obs_h"][lo:hi].view(rows, S), non_blocking=True)
+            if C > 1:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                fetched.append(ev)
+        joins = []
+        for c in range(C):       # the policy of chunk c: rows [lo, hi), its own workspace lane, draw counter and stream
+            lo, hi = c * rows, (c + 1) * rows
+            ac.row_base = g["row_base"] + lo
+            out = g["out"] if C == 1 else {k: v[lo:hi] for k, v in g["out"].items()}
+            if c == C - 1:           # the last chunk stays on the group's stream (its fetch is the last one there)
+                self.agent.act(g["obs_d"][lo:hi], out=out, lane=g["lane"] + c, draw_counter=g["draws"][c])
+            else:
+                st = g["cstreams"][c]
+                st.wait_event(fetched[c])
+                with torch.cuda.stream(st):
+                    self.agent.act(g["obs_d"][lo:hi], out=out, lane=g["lane"] + c, draw_counter=g["draws"][c])
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                joins.append(ev)
+        for ev in joins:
+            cur.wait_event(ev)
         ac.row_base = g["row_base"]
-        self.agent.act(g["obs_d"], out=g["out"], lane=g["lane"], draw_counter=g["draw"])
         acted = torch.cuda.Event()
         acted.record(cur)
         g["side"].wait_event(acted)
@@ -107,7 +139,7 @@ class HostBufferPipeline:
         # repeat (seed, row, draw) triples this pipeline has used
         ac = self.agent.actor_critic
         ac._draw = max(ac._draw, g["draw0"] + g["steps"])
-        self.launches += 5 + int(self.kernel_fetch)
+        self.launches += g["C"] * (4 + int(self.kernel_fetch)) + 1
 
     def wait(self, gi: int) -> Dict[str, np.ndarray]:
         g = self.groups[gi]

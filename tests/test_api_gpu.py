@@ -252,8 +252,8 @@ def test_multiplexed_runner_reports_failures_per_experiment(highway_config, tmp_
     assert "rotate_dim" in res[1]["error_message"] and "error_traceback" in res[1]
 
 
-@pytest.mark.parametrize("groups,graphs", [(1, True), (2, True), (2, False)])
-def test_host_buffer_pipeline_equals_the_device_loop(highway_config, groups, graphs):
+@pytest.mark.parametrize("groups,graphs,chunks", [(1, True, 1), (2, True, 1), (2, False, 1), (1, True, 4), (2, True, 2)])
+def test_host_buffer_pipeline_equals_the_device_loop(highway_config, groups, graphs, chunks):
     """training/host_pipeline.py: the graphed, grouped host-buffer loop (pinned observation in, pinned results out)
     produces exactly the actions, observations, rewards and flags of the plain device-resident act + step loop."""
     from highway_rope_ppo_b200.experiments.config import Condition
@@ -278,7 +278,7 @@ def test_host_buffer_pipeline_equals_the_device_loop(highway_config, groups, gra
                      te.cpu().numpy().copy(), tr.cpu().numpy().copy()))
         obs = o.clone()
     Eg = E // groups
-    pipe = HostBufferPipeline(agent, [mk(Eg, g * Eg) for g in range(groups)], use_graphs=graphs)
+    pipe = HostBufferPipeline(agent, [mk(Eg, g * Eg) for g in range(groups)], use_graphs=graphs, chunks=chunks)
     pipe.reset(42)
     for t in range(steps):
         for g in range(groups):
