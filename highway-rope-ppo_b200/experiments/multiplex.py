@@ -190,6 +190,8 @@ class MultiplexedRunner(ExperimentRunner):
                 except Exception as err:
                     slot.fail(err)
             for g in groups.values():
+                if not g.slots:   # (the only experiment of this configuration failed while it was being set up)
+                    continue
                 g.build()
                 for s in g.slots:   # the policy of experiment e reads row e of the observation, writes row e of the results
                     row, A = g.res[s.e], 2
