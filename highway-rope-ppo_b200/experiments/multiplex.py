@@ -241,8 +241,11 @@ class MultiplexedRunner(ExperimentRunner):
         for s in asking("update"):
             def begin(s=s):
                 _rng_set(s.rng)   # the minibatch permutation comes from this experiment's numpy stream
-                with torch.cuda.stream(s.stream):
+                torch.cuda.set_stream(s.stream)   # (not the stream context: its enter / exit each query the device count)
+                try:
                     s.pending_update = s.agent.update_begin(last_value=s.req[1])
+                finally:
+                    torch.cuda.set_stream(main)
                 s.rng = _rng_get()
                 return _PENDING
             self._guard(s, begin)

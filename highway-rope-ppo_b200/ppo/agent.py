@@ -682,12 +682,15 @@ class PPOAgent:
             self._capture_stream = torch.cuda.Stream(self.device)
         cap = self._capture_stream
         cap.wait_stream(cur)
-        with torch.cuda.stream(cap):
+        torch.cuda.set_stream(cap)   # (not the stream context: its enter / exit each query the device count)
+        try:
             g.capture_begin()
             try:
                 fn()
             finally:
                 g.capture_end()
+        finally:
+            torch.cuda.set_stream(cur)
         cur.wait_stream(cap)
         return g
 
